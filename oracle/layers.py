@@ -1,0 +1,171 @@
+"""TEST INFRASTRUCTURE ONLY (oracle).  Plain-PyTorch (CPU, fp32 or fp64) restatement of the dense-API layers of the
+reference hot path.  It is the checker for the CUDA layers and the ``port`` CPU baseline of bench.py; the product
+package never imports it.
+
+Restated from (all paths relative to /root/reference):
+  * models/common.py:26-40                      MLP = Linear(bias = not bn) → FastBatchNorm1d → activation
+  * torch_points3d.core.common_modules.FastBatchNorm1d  (third-party, NOT vendored in the reference and unpinned —
+    restated from its published behaviour: wraps ``nn.BatchNorm1d(C, momentum=0.1)`` as attribute ``batch_norm``;
+    [B,N,C] input ⇒ statistics over B·N per channel; [N,C] input ⇒ plain BatchNorm1d)
+  * models/point_conv_big.py:8-58               PointConv            (depthwise-separable continuous conv)
+  * models/point_conv_big.py:61-88              ResNetBBlock
+  * models/point_conv_big.py:91-107             Upsampling
+  * models/point_conv_big.py:110-167            PointConvResNet
+  * models/continuous_crf_conv_big.py:7-78      ContinuousGaussianCRFConv (dense)
+
+Parameter / buffer names are identical to the reference's so state_dicts are interchangeable; the forward passes are
+written with advanced indexing instead of the reference's ``gather`` on a repeated int64 index, and the reference's
+B=1 ``.squeeze()`` defect (continuous_crf_conv_big.py:43) is not reproduced.  Pinned against the imported reference
+modules by tests/golden/make_golden.py (container only) → tests/golden/*.npz, checked in tests/test_oracle_pinning.py.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class FastBatchNorm1d(nn.Module):
+    def __init__(self, num_features, momentum=0.1, **kwargs):
+        super().__init__()
+        self.batch_norm = nn.BatchNorm1d(num_features, momentum=momentum, **kwargs)
+
+    def forward(self, x):
+        if x.dim() == 2:
+            return self.batch_norm(x)
+        if x.dim() == 3:   # [B, N, C]: statistics over B*N
+            return self.batch_norm(x.transpose(1, 2)).transpose(1, 2)
+        raise ValueError("Non supported number of dimensions {}".format(x.dim()))
+
+
+class MLP(nn.Module):                                   # common.py:26-40
+    def __init__(self, in_channels, out_channels, bn=True, activation=None):
+        super().__init__()
+        self.lin = nn.Linear(in_channels, out_channels, bias=not bn)
+        self.bn = FastBatchNorm1d(out_channels) if bn else None
+        self.activation = activation
+
+    def forward(self, x):
+        x = self.lin(x)
+        if self.bn is not None:
+            x = self.bn(x)
+        if self.activation is not None:
+            x = self.activation(x)
+        return x
+
+
+def take_rows(x, idx):
+    """x [B,N,F], idx [B,N',K] int64 → [B,N',K,F]   (point_conv_big.py:25-35, continuous_crf_conv_big.py:38-43)."""
+    B = x.shape[0]
+    b = torch.arange(B, device=x.device).view(B, 1, 1)
+    return x[b, idx]
+
+
+def _lrelu01():
+    return nn.LeakyReLU(negative_slope=0.1)
+
+
+class PointConv(nn.Module):                             # point_conv_big.py:8-58
+    def __init__(self, d_model):
+        super().__init__()
+        self.weight_nn = nn.Sequential(MLP(3, d_model, activation=_lrelu01()), MLP(d_model, d_model, activation=None))
+
+    def forward(self, x, pos, neighbor_idx):
+        support, centres = (pos, pos) if torch.is_tensor(pos) else pos
+        B, Nq, K = neighbor_idx.shape
+        rel = centres.unsqueeze(2) - take_rows(support, neighbor_idx)              # centre − neighbour  (:40)
+        w = self.weight_nn(rel.reshape(B, Nq * K, 3)).reshape(B, Nq, K, -1)       # BN statistics over all B·N'·K edges (:43)
+        return (w * take_rows(x, neighbor_idx)).sum(dim=2)                         # (:56-57)
+
+
+class ResNetBBlock(nn.Module):                          # point_conv_big.py:61-88
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        hidden = out_channels // 4
+        self.lin_in = MLP(in_channels, hidden, activation=_lrelu01())
+        self.lin_out = MLP(hidden, out_channels, activation=None)
+        self.shortcut = MLP(in_channels, out_channels, activation=None) if in_channels != out_channels else nn.Identity()
+        self.point_conv = PointConv(hidden)
+
+    def forward(self, x, pos, neighbor_idx):
+        residual = self.shortcut(x)
+        if not torch.is_tensor(pos):                                               # strided block: max over neighbours (:74-77,81-82)
+            residual = take_rows(residual, neighbor_idx).max(dim=2)[0]
+        x = self.lin_out(self.point_conv(self.lin_in(x), pos, neighbor_idx))
+        return F.leaky_relu(x + residual)                                          # default slope 0.01 (:88)
+
+
+class Upsampling(nn.Module):                            # point_conv_big.py:91-107
+    def __init__(self, down_channels, up_channels, out_channels):
+        super().__init__()
+        self.lin = MLP(down_channels, up_channels, activation=_lrelu01())
+        self.fusion = MLP(up_channels * 2, out_channels, activation=_lrelu01())
+
+    def forward(self, x_down, x_up, up_idx, neighbor_idx=None):
+        x_down = self.lin(take_rows(x_down, up_idx)[:, :, 0])
+        return self.fusion(torch.cat([x_up, x_down], dim=-1))
+
+
+class ContinuousGaussianCRFConv(nn.Module):             # continuous_crf_conv_big.py:7-78
+    def __init__(self, unary_channels, pairwise_channels, out_channels=None, steps=1):
+        super().__init__()
+        self.unary_channels = unary_channels
+        self.pairwise_channels = pairwise_channels
+        self.out_channels = out_channels if out_channels is not None else pairwise_channels
+        self.hidden_channels = self.out_channels // 4
+        self.steps = steps
+        h = self.hidden_channels
+        self.unary_nn = nn.Sequential(MLP(unary_channels, h, activation=_lrelu01()), MLP(h, h, activation=None))
+        self.pairwise_nn = nn.Sequential(MLP(pairwise_channels, h, activation=_lrelu01()), MLP(h, h, activation=None))
+        self.out_nn = MLP(h, self.out_channels, activation=_lrelu01())
+        self.fusion_nn = MLP(self.out_channels * 2, self.out_channels, activation=_lrelu01())
+        self.c = nn.Parameter(torch.eye(h))                                        # nn.init.eye_ (:35-36)
+
+    def forward(self, unary, pairwise, up_idx, neighbor_idx):
+        nbr = neighbor_idx[:, :, 1:]                                               # drop column 0 (assumed self) (:45-47,57)
+        u = self.unary_nn(unary)
+        y = self.pairwise_nn(pairwise)
+        z = take_rows(u, up_idx)[:, :, 0]                                          # nearest-coarse upsample (:60)
+        d = (y.unsqueeze(2) - take_rows(y, nbr)).pow(2).sum(dim=-1, keepdim=True)  # (:49-54)
+        s = (-d).softmax(dim=2)
+        eye = torch.eye(self.hidden_channels, dtype=z.dtype, device=z.device)
+        Cm = self.c.t() @ self.c                                                   # (:66)
+        Minv = torch.linalg.inv(eye + Cm)
+        x = z
+        for _ in range(self.steps):                                                # (:68-72)
+            m = (s * take_rows(x, nbr)).sum(dim=2)
+            x = (z + m @ Cm) @ Minv
+        x = self.out_nn(x)
+        return self.fusion_nn(torch.cat([x, pairwise], dim=-1))                    # (:76)
+
+
+class PointConvResNet(nn.Module):                       # point_conv_big.py:110-167
+    def __init__(self, in_channels, n_classes, use_crf=True, steps=1):
+        super().__init__()
+        L = [32, 64, 128, 256, 512]
+        self.C = n_classes
+        prev = in_channels
+        for lvl, ch in enumerate(L, start=1):
+            setattr(self, f"conv{lvl}_1", ResNetBBlock(prev, ch))
+            setattr(self, f"conv{lvl}_2", ResNetBBlock(ch, ch))
+            prev = ch
+        for lvl in (4, 3, 2, 1):
+            down, up = L[lvl], L[lvl - 1]
+            setattr(self, f"deconv{lvl}",
+                    ContinuousGaussianCRFConv(down, up, up, steps=steps) if use_crf else Upsampling(down, up, up))
+        self.classifier = nn.Sequential(MLP(L[0], L[0] * 4, activation=_lrelu01()), nn.Dropout(p=0.5),
+                                        nn.Linear(L[0] * 4, n_classes))
+
+    def forward(self, data):
+        x, ms = data.x, data.multiscale
+        skips = []
+        for lvl in range(1, 6):
+            if lvl == 1:
+                x = self.conv1_1(x, ms[0].pos, ms[0].neighbor_idx)
+            else:
+                x = getattr(self, f"conv{lvl}_1")(x, (ms[lvl - 2].pos, ms[lvl - 1].pos), ms[lvl - 2].sub_idx)
+            x = getattr(self, f"conv{lvl}_2")(x, ms[lvl - 1].pos, ms[lvl - 1].neighbor_idx)
+            skips.append(x)
+        for lvl in (4, 3, 2, 1):
+            x = getattr(self, f"deconv{lvl}")(x, skips[lvl - 1], ms[lvl - 1].up_idx, ms[lvl - 1].neighbor_idx)
+        return self.classifier(x).reshape(-1, self.C)

@@ -1,0 +1,16 @@
+"""Shared comparison helpers for the parity tests."""
+import numpy as np
+
+
+def rel_err(a, b, floor=0.0):
+    """max|a-b| / max(max|b|, floor) — error relative to the tensor's scale.  `floor` guards quantities that are
+    analytically zero (e.g. the gradient of a BatchNorm bias that feeds another BatchNorm), whose reference value is
+    rounding noise."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), floor, 1e-30))
+
+
+def grad_floor(golden, tag, frac=1e-3):
+    """frac × the largest parameter-gradient magnitude of the fixture `tag`."""
+    return frac * max(float(np.abs(v).max()) for k, v in golden.items() if k.startswith(tag + ".gparam."))
