@@ -1,0 +1,51 @@
+"""ctypes loader for the C-ABI CUDA library (include/crfconv_b200.h).  There is no CPU fallback: if the library is
+missing, or a call returns a non-zero status, a RuntimeError is raised."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcrfconv_b200.so")
+
+_lib = None
+
+_vp, _i64, _sz, _f32, _int = C.c_void_p, C.c_int64, C.c_size_t, C.c_float, C.c_int
+
+# name -> (restype, argtypes); mirrors include/crfconv_b200.h one to one (checked by tests/test_cabi.py)
+SIGNATURES = {
+    "crfconv_abi_version": (_int, []),
+    "crfconv_status_string": (C.c_char_p, [_int]),
+    "crfconv_knn_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64]),
+    "crfconv_knn_batch": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "crfconv_cpp_knn_batch": (_int, [_vp, _sz, _sz, _sz, _vp, _sz, _sz, _vp]),
+    "crfconv_grid_subsample_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "crfconv_grid_subsample": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _f32, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "crfconv_grid_subsample_host": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _f32, _int, _vp, _vp, _vp, _vp]),
+}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -m crfconv_b200.build` (or __graft_entry__.build()). "
+                "crfconv_b200 has no CPU / PyTorch fallback path.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)      # AttributeError here = header / library mismatch: fail loudly
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(status: int, what: str = ""):
+    if status != 0:
+        msg = lib().crfconv_status_string(int(status)).decode()
+        raise RuntimeError(f"crfconv_b200 {what} failed: {msg} (status {status})")
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -67,8 +67,9 @@ void knn_one_cloud(const float* pts, int64_t n, const float* qs, int64_t nq, int
                 best[pos] = c;
             }
             for (int64_t k = 0; k < K; ++k) {
-                // K > n: the reference leaves trailing slots unwritten (knn_.cxx:32,59); canonical fill = -1.
-                out[qi * K + k] = k < Ke ? best[k].i : -1;
+                // K > n: the reference never writes the trailing slots; in cpp_knn_omp they keep the zeros of the
+                // per-query std::vector<size_t>(K) (knn_.cxx:59,65-67).  Canonical fill = 0, like that variant.
+                out[qi * K + k] = k < Ke ? best[k].i : 0;
                 if (out_d) out_d[qi * K + k] = k < Ke ? best[k].d : INFINITY;
             }
         }

@@ -42,7 +42,7 @@ def test_knn_oracle_distance_multiset_on_tie_heavy_clouds(golden, name):
 def test_knn_oracle_k_larger_than_n():
     pts = np.random.default_rng(0).random((5, 3)).astype(np.float32)
     idx = on.knn(pts, pts, 8)
-    assert np.all(idx[:, 5:] == -1) and np.all(np.sort(idx[:, :5], 1) == np.arange(5))
+    assert np.all(idx[:, 5:] == 0) and np.all(np.sort(idx[:, :5], 1) == np.arange(5))
 
 
 @pytest.mark.skipif(not on.have_ref_knn(), reason="compiled reference kNN not available")
