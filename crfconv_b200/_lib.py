@@ -22,6 +22,20 @@ SIGNATURES = {
     "crfconv_grid_subsample_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "crfconv_grid_subsample": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _f32, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "crfconv_grid_subsample_host": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _f32, _int, _vp, _vp, _vp, _vp]),
+    "crfconv_linear_fwd": (_int, [_vp, _int, _vp, _vp, _f32, _vp, _i64, _i64, _vp, _int, _vp, _vp, _vp, _vp, _i64, _int, _int, _vp]),
+    "crfconv_bn_finalize_fwd": (_int, [_vp, _i64, _vp, _vp, _f32, _f32, _int, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
+    "crfconv_bn_act_fwd": (_int, [_vp, _vp, _vp, _vp, _f32, _vp, _i64, _int, _vp]),
+    "crfconv_bn_bwd_reduce": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _i64, _int, _vp]),
+    "crfconv_bn_finalize_bwd": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _int, _vp]),
+    "crfconv_linear_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32,
+                                  _vp, _int, _vp, _vp, _f32, _vp, _i64, _i64, _vp, _int, _vp, _vp, _int, _vp, _int, _vp, _vp,
+                                  _i64, _int, _int, _vp]),
+    "crfconv_crf_compat_fwd": (_int, [_vp, _vp, _vp, _vp, _int, _vp]),
+    "crfconv_crf_compat_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
+    "crfconv_crf_upsample_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
+    "crfconv_crf_upsample_bwd": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
+    "crfconv_crf_step_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _vp]),
+    "crfconv_crf_step_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _vp]),
 }
 
 

@@ -1,0 +1,170 @@
+"""Drop-in for the reference's ``models/continuous_crf_conv_big.py`` (:7-78): ``ContinuousGaussianCRFConv`` with the same
+constructor, forward signature, sub-module names and ``state_dict`` keys (``unary_nn.{0,1}.*``, ``pairwise_nn.{0,1}.*``,
+``out_nn.*``, ``fusion_nn.*``, ``c``), executed as ONE autograd node that drives the sm_100a kernels:
+
+    unary_nn / pairwise_nn : tensor-core Linear passes with BN statistics in the epilogue and BN+LeakyReLU on the fly
+    z = u[up_idx]          : fused with unary_nn's last BatchNorm                                      (:60)
+    mean-field steps       : csrc/crf.cu — distances, softmax over k, aggregation, C / (I+C)^-1 in registers   (:68-72)
+    out_nn, fusion_nn      : the concat [x, pairwise] (:76) is never materialised (two-segment GEMM)
+
+Unlike the reference it accepts B = 1 (the reference crashes there: ``.squeeze()`` at :43), and ``(I+C)^-1`` is computed
+once per forward instead of once per step.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .common import MLP, bn_forward_state
+
+
+def _mlp_params(m: MLP):
+    return m.lin.weight, m.bn.batch_norm.weight, m.bn.batch_norm.bias
+
+
+class _CRFConvFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, unary, pairwise, up_idx, neighbor_idx, steps, training, mods, c, *params):
+        if not (unary.is_cuda and pairwise.is_cuda):
+            raise RuntimeError("crfconv_b200 layers run on CUDA tensors only (no CPU fallback)")
+        (W1u, _, _, W2u, _, _, W1p, _, _, W2p, _, _, Wo, _, _, Wf, _, _) = [p.detach().contiguous().float() for p in params]
+        bns = [m.bn.batch_norm for m in mods]          # order: u0, u1, p0, p1, out, fusion
+        B, Nc, Cu = unary.shape
+        _, N, Cp = pairwise.shape
+        K = neighbor_idx.shape[-1]
+        dev = unary.device
+        U, P = ops.as2d(unary), ops.as2d(pairwise)
+        up = up_idx.detach().reshape(B, N).contiguous().to(torch.int64)
+        nbr = neighbor_idx.detach().contiguous().to(torch.int64)
+        Mc, M = B * Nc, B * N
+        F, Co = W2u.shape[0], Wf.shape[0]
+
+        def tr(bn):
+            return training or not bn.track_running_stats
+
+        # unary_nn / pairwise_nn, layer 1 and 2 (:58-59)
+        s1u, fin = bn_forward_state(F, dev, Mc, bns[0], tr(bns[0]))
+        H1u = ops.linear_fwd(U, W1u, stats=s1u.stats); fin()
+        s1p, fin = bn_forward_state(F, dev, M, bns[2], tr(bns[2]))
+        H1p = ops.linear_fwd(P, W1p, stats=s1p.stats); fin()
+        s2u, fin = bn_forward_state(F, dev, Mc, bns[1], tr(bns[1]))
+        H2u = ops.linear_fwd(H1u, W2u, scale1=s1u.scale, shift1=s1u.shift, slope1=0.1, stats=s2u.stats); fin()
+        s2p, fin = bn_forward_state(F, dev, M, bns[3], tr(bns[3]))
+        H2p = ops.linear_fwd(H1p, W2p, scale1=s1p.scale, shift1=s1p.shift, slope1=0.1, stats=s2p.stats); fin()
+        # mean field (:60-72)
+        cc = c.detach().contiguous().float()
+        Cm, Minv = ops.crf_compat_fwd(cc)
+        z = ops.crf_upsample_fwd(H2u, s2u, up, B, N, Nc)
+        xs = [z]
+        for _ in range(steps):
+            xs.append(ops.crf_step_fwd(H2p, s2p.scale, z, xs[-1], nbr, Cm, Minv, B, N, K))
+        # out_nn, fusion_nn (:74-76)
+        so, fin = bn_forward_state(Co, dev, M, bns[4], tr(bns[4]))
+        H3 = ops.linear_fwd(xs[-1], Wo, stats=so.stats); fin()
+        sf, fin = bn_forward_state(Co, dev, M, bns[5], tr(bns[5]))
+        Hf = ops.linear_fwd(H3, Wf, scale1=so.scale, shift1=so.shift, slope1=0.1, X2=P, stats=sf.stats); fin()
+        out = ops.bn_act_fwd(Hf, sf, 0.1)
+
+        ctx.dims = (B, N, Nc, K, F, Co, Cu, Cp, steps)
+        ctx.bn = (s1u, s2u, s1p, s2p, so, sf)
+        ctx.save_for_backward(U, P, up, nbr, H1u, H2u, H1p, H2p, H3, Hf, Cm, Minv, cc, W1u, W2u, W1p, W2p, Wo, Wf, *xs)
+        return out.view(B, N, Co)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (U, P, up, nbr, H1u, H2u, H1p, H2p, H3, Hf, Cm, Minv, cc, W1u, W2u, W1p, W2p, Wo, Wf, *xs) = ctx.saved_tensors
+        B, N, Nc, K, F, Co, Cu, Cp, steps = ctx.dims
+        s1u, s2u, s1p, s2p, so, sf = ctx.bn
+        dev = gout.device
+        Mc, M = B * Nc, B * N
+        z = xs[0]
+        g2 = ops.as2d(gout)
+
+        def zeros(*shape):
+            return torch.zeros(*shape, dtype=torch.float32, device=dev)
+
+        dW = {k: zeros(*w.shape) for k, w in (("1u", W1u), ("2u", W2u), ("1p", W1p), ("2p", W2p), ("o", Wo), ("f", Wf))}
+        dg = {k: zeros(n) for k, n in (("1u", F), ("2u", F), ("1p", F), ("2p", F), ("o", Co), ("f", Co))}
+        db = {k: zeros(n) for k, n in (("1u", F), ("2u", F), ("1p", F), ("2p", F), ("o", Co), ("f", Co))}
+
+        # fusion_nn
+        ops.bn_backward_prepare(g2, Hf, sf, 0.1, dg["f"], db["f"])
+        dO = torch.empty((M, Co), dtype=torch.float32, device=dev)
+        dP = torch.empty((M, Cp), dtype=torch.float32, device=dev)
+        ops.linear_bwd(g2, Hf, sf, 0.1, H3, Wf, scale1=so.scale, shift1=so.shift, slope1=0.1, X2=P, dX1=dO, dX2=dP, dW=dW["f"])
+        # out_nn
+        ops.bn_backward_prepare(dO, H3, so, 0.1, dg["o"], db["o"])
+        g = torch.empty((M, F), dtype=torch.float32, device=dev)
+        ops.linear_bwd(dO, H3, so, 0.1, xs[-1], Wo, dX1=g, dW=dW["o"])
+        # mean-field steps, last to first
+        Gz, Gy, GC, GM = zeros(M, F), zeros(M, F), zeros(F, F), zeros(F, F)
+        m_out, v_out, h_out = (torch.empty((M, F), dtype=torch.float32, device=dev) for _ in range(3))
+        for t in range(steps, 0, -1):
+            gprev = zeros(M, F)
+            ops.crf_step_bwd(H2p, s2p.scale, z, xs[t - 1], nbr, Cm, Minv, g, Gz, gprev, Gy, m_out, v_out, h_out, B, N, K)
+            ops.linear_bwd(m_out, None, None, 1.0, h_out, GC, dW=GC)      # GC += mᵀ·h   (W argument unused by wgrad)
+            ops.linear_bwd(v_out, None, None, 1.0, g, GM, dW=GM)          # GM += vᵀ·g
+            g = gprev
+        Gc = zeros(F, F)
+        ops.crf_compat_bwd(cc, Minv, GC, GM, Gc)
+        Gu = zeros(Mc, F)
+        if steps > 0:
+            ops.crf_upsample_bwd(Gz, g, up, Gu, B, N, Nc)      # dL/dz = Σ_t h^t + g^0
+        else:
+            ops.crf_upsample_bwd(g, None, up, Gu, B, N, Nc)
+        # unary_nn
+        ops.bn_backward_prepare(Gu, H2u, s2u, 1.0, dg["2u"], db["2u"])
+        dA = torch.empty((Mc, F), dtype=torch.float32, device=dev)
+        ops.linear_bwd(Gu, H2u, s2u, 1.0, H1u, W2u, scale1=s1u.scale, shift1=s1u.shift, slope1=0.1, dX1=dA, dW=dW["2u"])
+        ops.bn_backward_prepare(dA, H1u, s1u, 0.1, dg["1u"], db["1u"])
+        dU = torch.empty((Mc, Cu), dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        ops.linear_bwd(dA, H1u, s1u, 0.1, U, W1u, dX1=dU, dW=dW["1u"])
+        # pairwise_nn (its input gradient accumulates onto the fusion_nn branch)
+        ops.bn_backward_prepare(Gy, H2p, s2p, 1.0, dg["2p"], db["2p"])
+        dA = torch.empty((M, F), dtype=torch.float32, device=dev)
+        ops.linear_bwd(Gy, H2p, s2p, 1.0, H1p, W2p, scale1=s1p.scale, shift1=s1p.shift, slope1=0.1, dX1=dA, dW=dW["2p"])
+        ops.bn_backward_prepare(dA, H1p, s1p, 0.1, dg["1p"], db["1p"])
+        need_p = ctx.needs_input_grad[1]
+        ops.linear_bwd(dA, H1p, s1p, 0.1, P, W1p, dX1=dP if need_p else None, acc1=True, dW=dW["1p"])
+
+        grads = []
+        for k in ("1u", "2u", "1p", "2p", "o", "f"):
+            grads += [dW[k], dg[k], db[k]]
+        return (dU.view(B, Nc, Cu) if dU is not None else None, dP.view(B, N, Cp) if need_p else None, None, None, None, None,
+                None, Gc, *grads)
+
+
+class ContinuousGaussianCRFConv(nn.Module):
+    def __init__(self, unary_channels, pairwise_channels, out_channels=None, steps=1):
+        super(ContinuousGaussianCRFConv, self).__init__()
+        self.unary_channels = unary_channels
+        self.pairwise_channels = pairwise_channels
+        self.out_channels = out_channels if out_channels is not None else pairwise_channels
+        self.hidden_channels = self.out_channels // 4
+        self.steps = steps
+
+        act = lambda: nn.LeakyReLU(negative_slope=0.1)   # noqa: E731
+        self.unary_nn = nn.Sequential(MLP(self.unary_channels, self.hidden_channels, activation=act()),
+                                      MLP(self.hidden_channels, self.hidden_channels, activation=None))
+        self.pairwise_nn = nn.Sequential(MLP(self.pairwise_channels, self.hidden_channels, activation=act()),
+                                         MLP(self.hidden_channels, self.hidden_channels, activation=None))
+        self.out_nn = MLP(self.hidden_channels, self.out_channels, activation=act())
+        self.fusion_nn = MLP(self.out_channels * 2, self.out_channels, activation=act())
+        self.c = nn.Parameter(torch.Tensor(self.hidden_channels, self.hidden_channels))
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        nn.init.eye_(self.c)
+
+    def forward(self, unary, pairwise, up_idx, neighbor_idx):
+        if self.pairwise_channels != self.out_channels:
+            # the reference's fusion_nn silently requires this too (continuous_crf_conv_big.py:29,76)
+            raise RuntimeError("ContinuousGaussianCRFConv: fusion_nn needs pairwise_channels == out_channels")
+        if self.hidden_channels not in (4, 8, 16, 32, 64):
+            raise RuntimeError("ContinuousGaussianCRFConv: hidden channels (out_channels // 4) must be 4, 8, 16, 32 or 64")
+        mods = (self.unary_nn[0], self.unary_nn[1], self.pairwise_nn[0], self.pairwise_nn[1], self.out_nn, self.fusion_nn)
+        params = []
+        for m in (self.unary_nn[0], self.unary_nn[1], self.pairwise_nn[0], self.pairwise_nn[1], self.out_nn, self.fusion_nn):
+            params += list(_mlp_params(m))
+        return _CRFConvFunction.apply(unary, pairwise, up_idx, neighbor_idx, self.steps, self.training, mods, self.c, *params)

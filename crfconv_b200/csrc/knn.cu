@@ -9,6 +9,7 @@
 // K-th distance is strictly below a lower bound on the *computed* distance of every unvisited point; the bound is
 // derived from per-cell edge tables that are valid for the exact f32 binning function (monotonicity argument in
 // DESIGN.md §kNN), so the result is independent of the grid and equals a brute-force scan.
+#include "../../include/crfconv_b200.h"
 #include "common.cuh"
 
 namespace crf {

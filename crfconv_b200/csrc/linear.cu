@@ -1,0 +1,662 @@
+// Linear (+ training-mode BatchNorm + LeakyReLU) chains of the hot path on sm_100a tensor cores.
+//
+// Every dense contraction of the reference goes through models/common.py:26-40
+//     MLP = nn.Linear(bias = not bn) → FastBatchNorm1d (statistics over all B·N rows) → activation
+// The rows (M = B·N points or B·N·K edges) outnumber the channels by 10^3-10^5, so these GEMMs are A-streaming
+// (HBM/L2-bound) and the BatchNorm forces a grid-wide statistics barrier between a Linear and its activation.  The
+// chain is therefore cut at the BatchNorms, and each kernel
+//     (a) applies the PREVIOUS layer's BN affine + LeakyReLU while staging its A operand (never materialised), and
+//     (b) emits Σ / Σ² of its OWN output in the epilogue (double-precision atomics, one per column per CTA),
+// so a Linear→BN→act→Linear→BN chain costs one pass per Linear.  Backward mirrors it: the BN-backward transform
+//     dH = γ·istd · (dV − mean(dV) − Ĥ·mean(dV·Ĥ)),   dV = dA · lrelu'(V)
+// is applied on the fly while staging dH for the dgrad (dX = dH·W) and wgrad (dW = dHᵀ·A) contractions.
+// Contractions run on mma.sync m16n8k8 tf32 with 3xTF32 error compensation (mma.cuh) – fp32-grade results.
+#include <algorithm>
+#include <type_traits>
+
+#include "../../include/crfconv_b200.h"
+#include "common.cuh"
+#include "mma.cuh"
+
+namespace crf {
+namespace lin {
+
+constexpr int kThreads = 256;
+constexpr int BM = 128;      // rows per CTA tile (fwd / dgrad)
+constexpr int BK = 32;       // reduction chunk
+constexpr int AS = BK + 4;   // smem row stride for [row][k] operands read as (g, t): bank = 4g + t
+
+__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.0f ? v : v * slope; }
+
+// ------------------------------------------------------------------------------------------ forward
+struct FwdArgs {
+    const float* X1; int C1;                      // segment 1: [M, C1] (row-gathered through idx1 when given)
+    const float* scale1; const float* shift1; float slope1;   // prologue of segment 1: lrelu(x*scale+shift); null = identity
+    const int64_t* idx1; int64_t rows_dst; int64_t rows_src;  // gather: src row = (m / rows_dst) * rows_src + idx1[m]
+    const float* X2; int C2;                      // segment 2: [M, C2] raw (may be null / 0)
+    const float* W;                               // [Cout, C1 + C2] row-major (nn.Linear.weight)
+    const float* bias;                            // [Cout] or null
+    float* Y;                                     // [M, Cout]
+    double* stats;                                // [2*Cout]: Σ, Σ² over rows (or null)
+    int64_t M; int Cout;
+};
+
+template <int BN, bool X3>
+__global__ void __launch_bounds__(kThreads) fwd_kernel(const FwdArgs a) {
+    __shared__ __align__(16) float As[BM][AS];
+    __shared__ __align__(16) float Ws[BN][AS];
+    __shared__ float s_sum[BN], s_sq[BN];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int64_t m0 = (int64_t)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const int Ktot = a.C1 + a.C2;
+    if (tid < BN) { s_sum[tid] = 0.0f; s_sq[tid] = 0.0f; }
+
+    float acc[BN / 8][4];
+#pragma unroll
+    for (int i = 0; i < BN / 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+    const int c4 = tid & 7;          // float4 column slot inside the 32-wide chunk
+    const int r0 = tid >> 3;         // 0..31
+
+    for (int seg = 0; seg < 2; ++seg) {
+        const float* X = seg == 0 ? a.X1 : a.X2;
+        const int C = seg == 0 ? a.C1 : a.C2;
+        if (C == 0 || X == nullptr) continue;
+        const int coloff = seg == 0 ? 0 : a.C1;
+        const bool pro = (seg == 0) && a.scale1 != nullptr;
+        const bool vecA = ((C & 3) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+        const bool vecW = ((Ktot & 3) == 0) && ((coloff & 3) == 0) && ((C & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.W) & 15) == 0);
+        for (int kc = 0; kc < C; kc += BK) {
+            const int k = kc + 4 * c4;
+            float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+            if (pro) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (k + e < C) { sc[e] = __ldg(a.scale1 + k + e); sh[e] = __ldg(a.shift1 + k + e); }
+            }
+            // ---- stage A (4 rows per thread)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = r0 + 32 * j;
+                const int64_t m = m0 + r;
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                if (m < a.M && k < C) {
+                    int64_t srow = m;
+                    if (seg == 0 && a.idx1) srow = (m / a.rows_dst) * a.rows_src + __ldg(a.idx1 + m);
+                    const float* p = X + srow * C + k;
+                    if (vecA) {
+                        const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+                        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (k + e < C) v[e] = __ldg(p + e);
+                    }
+                    if (pro) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (k + e < C) v[e] = lrelu(fmaf(v[e], sc[e], sh[e]), a.slope1);
+                    }
+                }
+                *reinterpret_cast<float4*>(&As[r][4 * c4]) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+            // ---- stage W: Ws[n][kk] = W[n0+n][coloff + kc + kk]
+            for (int q = tid; q < BN * 8; q += kThreads) {
+                const int n = q >> 3, kk = 4 * (q & 7);
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                if (n0 + n < a.Cout && kc + kk < C) {
+                    const float* p = a.W + (int64_t)(n0 + n) * Ktot + coloff + kc + kk;
+                    if (vecW) {
+                        const float4 x = __ldg(reinterpret_cast<const float4*>(p));
+                        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (kc + kk + e < C) v[e] = __ldg(p + e);
+                    }
+                }
+                *reinterpret_cast<float4*>(&Ws[n][kk]) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+            __syncthreads();
+            // ---- tensor-core contraction of this chunk
+            const int kmax = min(BK, C - kc);
+#pragma unroll
+            for (int ks = 0; ks < BK / 8; ++ks) {
+                if (ks * 8 < kmax) {
+                    const float af[4] = {As[16 * w + g][ks * 8 + t], As[16 * w + g + 8][ks * 8 + t],
+                                         As[16 * w + g][ks * 8 + t + 4], As[16 * w + g + 8][ks * 8 + t + 4]};
+                    FragA fa;
+                    make_frag_a<X3>(fa, af);
+#pragma unroll
+                    for (int nt = 0; nt < BN / 8; ++nt) {
+                        FragB fb;
+                        make_frag_b<X3>(fb, Ws[nt * 8 + g][ks * 8 + t], Ws[nt * 8 + g][ks * 8 + t + 4]);
+                        mma_frag<X3>(acc[nt], fa, fb);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- epilogue: bias, store, column statistics
+    const int64_t row_a = m0 + 16 * w + g, row_b = row_a + 8;
+    const bool va = row_a < a.M, vb = row_b < a.M;
+    const bool vec_st = (a.Cout & 1) == 0;
+#pragma unroll
+    for (int nt = 0; nt < BN / 8; ++nt) {
+        const int col = n0 + nt * 8 + 2 * t;
+        float c0 = acc[nt][0], c1 = acc[nt][1], c2 = acc[nt][2], c3 = acc[nt][3];
+        if (a.bias) {
+            const float b0 = col < a.Cout ? __ldg(a.bias + col) : 0.f, b1 = col + 1 < a.Cout ? __ldg(a.bias + col + 1) : 0.f;
+            c0 += b0; c1 += b1; c2 += b0; c3 += b1;
+        }
+        if (vec_st && col + 1 < a.Cout) {
+            if (va) *reinterpret_cast<float2*>(a.Y + row_a * a.Cout + col) = make_float2(c0, c1);
+            if (vb) *reinterpret_cast<float2*>(a.Y + row_b * a.Cout + col) = make_float2(c2, c3);
+        } else {
+            if (va && col < a.Cout) a.Y[row_a * a.Cout + col] = c0;
+            if (va && col + 1 < a.Cout) a.Y[row_a * a.Cout + col + 1] = c1;
+            if (vb && col < a.Cout) a.Y[row_b * a.Cout + col] = c2;
+            if (vb && col + 1 < a.Cout) a.Y[row_b * a.Cout + col + 1] = c3;
+        }
+        if (a.stats) {
+            float s0 = (va ? c0 : 0.f) + (vb ? c2 : 0.f), s1 = (va ? c1 : 0.f) + (vb ? c3 : 0.f);
+            float q0 = (va ? c0 * c0 : 0.f) + (vb ? c2 * c2 : 0.f), q1 = (va ? c1 * c1 : 0.f) + (vb ? c3 * c3 : 0.f);
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                q0 += __shfl_xor_sync(0xffffffffu, q0, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+            }
+            if (g == 0) {
+                atomicAdd(&s_sum[nt * 8 + 2 * t], s0); atomicAdd(&s_sum[nt * 8 + 2 * t + 1], s1);
+                atomicAdd(&s_sq[nt * 8 + 2 * t], q0);  atomicAdd(&s_sq[nt * 8 + 2 * t + 1], q1);
+            }
+        }
+    }
+    if (a.stats) {
+        __syncthreads();
+        if (tid < BN && n0 + tid < a.Cout) {
+            atomicAdd(a.stats + n0 + tid, (double)s_sum[tid]);
+            atomicAdd(a.stats + a.Cout + n0 + tid, (double)s_sq[tid]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------- BatchNorm bookkeeping
+// Training: batch statistics from Σ / Σ² → scale/shift (+ saved mean / invstd, running-stat update with momentum and
+// unbiased variance, exactly nn.BatchNorm1d).  Eval: scale/shift from the running statistics.
+__global__ void bn_finalize_fwd_kernel(const double* __restrict__ stats, double count, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float eps, float momentum, int training,
+                                       float* running_mean, float* running_var, float* __restrict__ scale,
+                                       float* __restrict__ shift, float* __restrict__ mean_out, float* __restrict__ invstd_out, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float mean, invstd;
+    if (training) {
+        const double mu = stats[c] / count;
+        double var = stats[C + c] / count - mu * mu;
+        if (var < 0.0) var = 0.0;
+        mean = (float)mu;
+        invstd = (float)(1.0 / sqrt(var + (double)eps));
+        if (running_mean) {
+            const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+            running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)mu;
+            running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unb;
+        }
+    } else {
+        mean = running_mean[c];
+        invstd = 1.0f / sqrtf(running_var[c] + eps);
+    }
+    const float gm = gamma ? gamma[c] : 1.0f, bt = beta ? beta[c] : 0.0f;
+    const float sc = gm * invstd;
+    scale[c] = sc;
+    shift[c] = bt - mean * sc;
+    if (mean_out) mean_out[c] = mean;
+    if (invstd_out) invstd_out[c] = invstd;
+}
+
+// Y = lrelu(H*scale + shift (+ R), slope).  C % 4 == 0.
+__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict__ H, const float* __restrict__ scale,
+                                                         const float* __restrict__ shift, const float* __restrict__ R,
+                                                         float slope, float* __restrict__ Y, int64_t total4, int C4) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4) * 4;
+        const float4 h = __ldg(reinterpret_cast<const float4*>(H) + i);
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c));
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + c));
+        float4 v = make_float4(fmaf(h.x, sc.x, sh.x), fmaf(h.y, sc.y, sh.y), fmaf(h.z, sc.z, sh.z), fmaf(h.w, sc.w, sh.w));
+        if (R) {
+            const float4 r = __ldg(reinterpret_cast<const float4*>(R) + i);
+            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        }
+        v.x = lrelu(v.x, slope); v.y = lrelu(v.y, slope); v.z = lrelu(v.z, slope); v.w = lrelu(v.w, slope);
+        reinterpret_cast<float4*>(Y)[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ backward
+// Per-channel description of a BatchNorm(+LeakyReLU) node for the on-the-fly backward transform.
+struct BnBwd {
+    const float* scale;    // γ·istd        (null ⇒ plain Linear output: dH = dY)
+    const float* shift;    // β − μ·scale
+    const float* mean;
+    const float* invstd;
+    const float* k1;       // mean over rows of dV
+    const float* k2;       // mean over rows of dV·Ĥ
+    const float* act_ref;  // [M, C] saved activation output whose sign selects the LeakyReLU branch (null ⇒ use V)
+    float slope;           // 1 ⇒ no activation
+};
+
+__device__ __forceinline__ float bn_dv(float dy, float h, float ref, bool has_ref, float sc, float sh, float slope) {
+    const float pre = has_ref ? ref : fmaf(h, sc, sh);
+    return pre > 0.0f ? dy : dy * slope;
+}
+
+// s1[c] = Σ_rows dV, s2[c] = Σ_rows dV·Ĥ (double atomics).  C % 4 == 0, C <= 1024.
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ dY, const float* __restrict__ H, BnBwd bn,
+                                                            double* __restrict__ sums, int64_t M, int C) {
+    __shared__ float red[256 * 8];
+    const int C4 = C >> 2;
+    const int tpr = C4;                           // threads per row
+    const int rows_per_it = 256 / tpr;            // C4 divides 256 for C in {8,...,1024}
+    const int tid = threadIdx.x;
+    const int cslot = tid % tpr, rslot = tid / tpr;
+    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    if (rslot < rows_per_it) {
+        const int c = cslot * 4;
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(bn.scale + c)), sh = __ldg(reinterpret_cast<const float4*>(bn.shift + c));
+        const float4 mu = __ldg(reinterpret_cast<const float4*>(bn.mean + c)), is = __ldg(reinterpret_cast<const float4*>(bn.invstd + c));
+        const bool has_ref = bn.act_ref != nullptr;
+        for (int64_t m = (int64_t)blockIdx.x * rows_per_it + rslot; m < M; m += (int64_t)gridDim.x * rows_per_it) {
+            const float4 dy = __ldg(reinterpret_cast<const float4*>(dY + m * C + c));
+            const float4 h = __ldg(reinterpret_cast<const float4*>(H + m * C + c));
+            float4 rf = make_float4(0, 0, 0, 0);
+            if (has_ref) rf = __ldg(reinterpret_cast<const float4*>(bn.act_ref + m * C + c));
+            const float d0 = bn_dv(dy.x, h.x, rf.x, has_ref, sc.x, sh.x, bn.slope), d1 = bn_dv(dy.y, h.y, rf.y, has_ref, sc.y, sh.y, bn.slope);
+            const float d2 = bn_dv(dy.z, h.z, rf.z, has_ref, sc.z, sh.z, bn.slope), d3 = bn_dv(dy.w, h.w, rf.w, has_ref, sc.w, sh.w, bn.slope);
+            s1[0] += d0; s1[1] += d1; s1[2] += d2; s1[3] += d3;
+            s2[0] += d0 * (h.x - mu.x) * is.x; s2[1] += d1 * (h.y - mu.y) * is.y;
+            s2[2] += d2 * (h.z - mu.z) * is.z; s2[3] += d3 * (h.w - mu.w) * is.w;
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { red[tid * 8 + e] = s1[e]; red[tid * 8 + 4 + e] = s2[e]; }
+    __syncthreads();
+    // thread j < tpr*8 owns (column slot, which of 8 values); sums over the row slots
+    for (int j = tid; j < tpr * 8; j += 256) {
+        const int cs = j / 8, e = j % 8;
+        float tot = 0.0f;
+        for (int r = 0; r < rows_per_it; ++r) tot += red[(r * tpr + cs) * 8 + e];
+        const int c = cs * 4 + (e & 3);
+        atomicAdd(sums + (e < 4 ? 0 : C) + c, (double)tot);
+    }
+}
+
+// k1 = s1/M, k2 = s2/M; dγ += s2, dβ += s1.
+__global__ void bn_finalize_bwd_kernel(const double* __restrict__ sums, double count, float* __restrict__ k1, float* __restrict__ k2,
+                                       float* dgamma, float* dbeta, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double s1 = sums[c], s2 = sums[C + c];
+    k1[c] = (float)(s1 / count);
+    k2[c] = (float)(s2 / count);
+    if (dgamma) dgamma[c] += (float)s2;
+    if (dbeta) dbeta[c] += (float)s1;
+}
+
+// dH for 4 consecutive channels starting at c (c % 4 == 0, c + 3 < C).
+__device__ __forceinline__ void load_dh4(const float* __restrict__ dY, const float* __restrict__ H, const BnBwd& bn, int64_t m, int C,
+                                         int c, float (&out)[4]) {
+    const float4 dy = __ldg(reinterpret_cast<const float4*>(dY + m * C + c));
+    if (bn.scale == nullptr) { out[0] = dy.x; out[1] = dy.y; out[2] = dy.z; out[3] = dy.w; return; }
+    const float4 h = __ldg(reinterpret_cast<const float4*>(H + m * C + c));
+    const bool has_ref = bn.act_ref != nullptr;
+    float4 rf = make_float4(0, 0, 0, 0);
+    if (has_ref) rf = __ldg(reinterpret_cast<const float4*>(bn.act_ref + m * C + c));
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(bn.scale + c)), sh = __ldg(reinterpret_cast<const float4*>(bn.shift + c));
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(bn.mean + c)), is = __ldg(reinterpret_cast<const float4*>(bn.invstd + c));
+    const float4 k1 = __ldg(reinterpret_cast<const float4*>(bn.k1 + c)), k2 = __ldg(reinterpret_cast<const float4*>(bn.k2 + c));
+    out[0] = sc.x * (bn_dv(dy.x, h.x, rf.x, has_ref, sc.x, sh.x, bn.slope) - k1.x - (h.x - mu.x) * is.x * k2.x);
+    out[1] = sc.y * (bn_dv(dy.y, h.y, rf.y, has_ref, sc.y, sh.y, bn.slope) - k1.y - (h.y - mu.y) * is.y * k2.y);
+    out[2] = sc.z * (bn_dv(dy.z, h.z, rf.z, has_ref, sc.z, sh.z, bn.slope) - k1.z - (h.z - mu.z) * is.z * k2.z);
+    out[3] = sc.w * (bn_dv(dy.w, h.w, rf.w, has_ref, sc.w, sh.w, bn.slope) - k1.w - (h.w - mu.w) * is.w * k2.w);
+}
+
+// scalar variant for Cout % 4 != 0 (plain Linear only, e.g. the 13-class head)
+__device__ __forceinline__ float load_dh1(const float* __restrict__ dY, int64_t m, int C, int c) { return __ldg(dY + m * C + c); }
+
+struct DgradArgs {
+    const float* dY; const float* H; BnBwd bn;    // upstream gradient wrt this layer's activation output, pre-BN output
+    const float* W;                               // [Cout, C1 + C2]
+    float* dX1; int C1; int acc1;                 // gradient wrt segment 1 input (post-prologue), [M, C1]; acc ⇒ +=
+    float* dX2; int C2; int acc2;
+    int64_t M; int Cout;
+};
+
+constexpr int BS8 = 8;   // extra stride so that [k][n] operands read as (t, g) hit bank 8t + g
+
+template <int BN, bool X3>
+__global__ void __launch_bounds__(kThreads) dgrad_kernel(const DgradArgs a) {
+    __shared__ __align__(16) float As[BM][AS];           // dH tile [row][cout chunk]
+    __shared__ __align__(16) float Ws[BK][BN + BS8];     // W chunk [cout][cin tile]
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int64_t m0 = (int64_t)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;                      // input-channel tile
+    const int Ktot = a.C1 + a.C2;
+    const int C = a.Cout;
+    const bool vecA = (C & 3) == 0;
+    const bool vecW = ((Ktot & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.W) & 15) == 0);
+
+    float acc[BN / 8][4];
+#pragma unroll
+    for (int i = 0; i < BN / 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    const int c4 = tid & 7, r0 = tid >> 3;
+
+    for (int kc = 0; kc < C; kc += BK) {
+        const int k = kc + 4 * c4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = r0 + 32 * j;
+            const int64_t m = m0 + r;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (m < a.M && k < C) {
+                if (vecA) load_dh4(a.dY, a.H, a.bn, m, C, k, v);
+                else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (k + e < C) v[e] = load_dh1(a.dY, m, C, k + e);
+                }
+            }
+            *reinterpret_cast<float4*>(&As[r][4 * c4]) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        // Ws[kk][n] = W[kc+kk][n0+n]
+        for (int q = tid; q < BK * (BN / 4); q += kThreads) {
+            const int kk = q / (BN / 4), n = 4 * (q % (BN / 4));
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (kc + kk < C && n0 + n < Ktot) {
+                const float* p = a.W + (int64_t)(kc + kk) * Ktot + n0 + n;
+                if (vecW) {
+                    const float4 x = __ldg(reinterpret_cast<const float4*>(p));
+                    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (n0 + n + e < Ktot) v[e] = __ldg(p + e);
+                }
+            }
+            *reinterpret_cast<float4*>(&Ws[kk][n]) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        __syncthreads();
+        const int kmax = min(BK, C - kc);
+#pragma unroll
+        for (int ks = 0; ks < BK / 8; ++ks) {
+            if (ks * 8 < kmax) {
+                const float af[4] = {As[16 * w + g][ks * 8 + t], As[16 * w + g + 8][ks * 8 + t],
+                                     As[16 * w + g][ks * 8 + t + 4], As[16 * w + g + 8][ks * 8 + t + 4]};
+                FragA fa;
+                make_frag_a<X3>(fa, af);
+#pragma unroll
+                for (int nt = 0; nt < BN / 8; ++nt) {
+                    FragB fb;
+                    make_frag_b<X3>(fb, Ws[ks * 8 + t][nt * 8 + g], Ws[ks * 8 + t + 4][nt * 8 + g]);
+                    mma_frag<X3>(acc[nt], fa, fb);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const int64_t row_a = m0 + 16 * w + g, row_b = row_a + 8;
+    const bool va = row_a < a.M, vb = row_b < a.M;
+#pragma unroll
+    for (int nt = 0; nt < BN / 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int col = n0 + nt * 8 + 2 * t + e;
+            if (col >= Ktot) continue;
+            float* dst; int cc, ld, accm;
+            if (col < a.C1) { dst = a.dX1; cc = col; ld = a.C1; accm = a.acc1; }
+            else            { dst = a.dX2; cc = col - a.C1; ld = a.C2; accm = a.acc2; }
+            if (!dst) continue;
+            if (va) { float* p = dst + row_a * ld + cc; *p = accm ? *p + acc[nt][e] : acc[nt][e]; }
+            if (vb) { float* p = dst + row_b * ld + cc; *p = accm ? *p + acc[nt][2 + e] : acc[nt][2 + e]; }
+        }
+    }
+}
+
+// dW[co, k] += Σ_m dH[m, co] · A[m, k],  A = [prologue(X1) | X2].  Output tile 64 (co) × 64 (k) per CTA; CTAs along
+// x split the rows; partial tiles are combined with fp32 atomics.
+struct WgradArgs {
+    const float* dY; const float* H; BnBwd bn;
+    const float* X1; int C1; const float* scale1; const float* shift1; float slope1;
+    const int64_t* idx1; int64_t rows_dst; int64_t rows_src;
+    const float* X2; int C2;
+    float* dW;            // [Cout, C1 + C2]
+    float* dbias;         // [Cout] or null: += Σ_m dH
+    int64_t M; int Cout;
+    int64_t rows_per_cta;
+};
+
+constexpr int WR = 64;          // rows per staging tile
+constexpr int WS = 64 + BS8;    // smem stride
+
+template <bool X3>
+__global__ void __launch_bounds__(kThreads) wgrad_kernel(const WgradArgs a) {
+    __shared__ __align__(16) float Ds[WR][WS];   // dH tile  [m][co]
+    __shared__ __align__(16) float Xs[WR][WS];   // A tile   [m][k]
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int Ktot = a.C1 + a.C2;
+    const int co0 = blockIdx.y * 64, k0 = blockIdx.z * 64;
+    const int64_t mbeg = (int64_t)blockIdx.x * a.rows_per_cta, mend = min(a.M, mbeg + a.rows_per_cta);
+    const int wr = (w & 3) * 16;       // co rows of this warp inside the tile
+    const int wc = (w >> 2) * 32;      // k cols of this warp inside the tile
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    float bsum = 0.0f;                 // bias gradient: thread tid<64 owns column co0+tid
+    const bool vecD = (a.Cout & 3) == 0;
+    const int c16 = tid & 15, rr = tid >> 4;   // 16 float4 per 64-wide row, 16 rows per pass
+
+    for (int64_t mt = mbeg; mt < mend; mt += WR) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = rr + 16 * j;
+            const int64_t m = mt + r;
+            // dH tile
+            {
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                const int c = co0 + 4 * c16;
+                if (m < mend && c < a.Cout) {
+                    if (vecD) load_dh4(a.dY, a.H, a.bn, m, a.Cout, c, v);
+                    else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (c + e < a.Cout) v[e] = load_dh1(a.dY, m, a.Cout, c + e);
+                    }
+                }
+                *reinterpret_cast<float4*>(&Ds[r][4 * c16]) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+            // A tile (global column k0 + 4*c16 .. +3; may straddle nothing: C1 % 4 == 0 or scalar path)
+            {
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                const int kg = k0 + 4 * c16;
+                if (m < mend && kg < Ktot) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int kk = kg + e;
+                        if (kk >= Ktot) break;
+                        if (kk < a.C1) {
+                            int64_t srow = m;
+                            if (a.idx1) srow = (m / a.rows_dst) * a.rows_src + __ldg(a.idx1 + m);
+                            float x = __ldg(a.X1 + srow * a.C1 + kk);
+                            if (a.scale1) x = lrelu(fmaf(x, __ldg(a.scale1 + kk), __ldg(a.shift1 + kk)), a.slope1);
+                            v[e] = x;
+                        } else {
+                            v[e] = __ldg(a.X2 + m * a.C2 + (kk - a.C1));
+                        }
+                    }
+                }
+                *reinterpret_cast<float4*>(&Xs[r][4 * c16]) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        }
+        __syncthreads();
+        if (a.dbias && blockIdx.z == 0 && tid < 64) {
+            float s = 0.0f;
+            for (int r = 0; r < WR; ++r) s += Ds[r][tid];
+            bsum += s;
+        }
+#pragma unroll
+        for (int ks = 0; ks < WR / 8; ++ks) {
+            // A operand = dHᵀ: (row = co, col = m)
+            const float af[4] = {Ds[ks * 8 + t][wr + g], Ds[ks * 8 + t][wr + g + 8], Ds[ks * 8 + t + 4][wr + g], Ds[ks * 8 + t + 4][wr + g + 8]};
+            FragA fa;
+            make_frag_a<X3>(fa, af);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                FragB fb;
+                make_frag_b<X3>(fb, Xs[ks * 8 + t][wc + nt * 8 + g], Xs[ks * 8 + t + 4][wc + nt * 8 + g]);
+                mma_frag<X3>(acc[nt], fa, fb);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int co = co0 + wr + g + (e >= 2 ? 8 : 0);
+            const int k = k0 + wc + nt * 8 + 2 * t + (e & 1);
+            if (co < a.Cout && k < Ktot) atomicAdd(a.dW + (int64_t)co * Ktot + k, acc[nt][e]);
+        }
+    }
+    if (a.dbias && blockIdx.z == 0 && tid < 64 && co0 + tid < a.Cout) atomicAdd(a.dbias + co0 + tid, bsum);
+}
+
+template <typename F>
+inline int dispatch_bn(int n, F&& f) {
+    if (n > 32) return f(std::integral_constant<int, 64>{});
+    if (n > 16) return f(std::integral_constant<int, 32>{});
+    if (n > 8) return f(std::integral_constant<int, 16>{});
+    return f(std::integral_constant<int, 8>{});
+}
+
+}  // namespace lin
+}  // namespace crf
+
+using namespace crf;
+
+extern "C" {
+
+// Y[M,Cout] = [lrelu(X1*scale1+shift1) | X2] · Wᵀ (+ bias);  stats[0:Cout] += Σ_rows Y, stats[Cout:2Cout] += Σ_rows Y².
+// X1 rows may be gathered: source row of output row m = (m / rows_dst) * rows_src + idx1[m]   (idx1 null ⇒ identity).
+// precision: 0 = 3xTF32 (fp32-grade), 1 = single-pass TF32.
+int crfconv_linear_fwd(const float* X1, int C1, const float* scale1, const float* shift1, float slope1, const int64_t* idx1,
+                       int64_t rows_dst, int64_t rows_src, const float* X2, int C2, const float* W, const float* bias, float* Y,
+                       double* stats, int64_t M, int Cout, int precision, void* stream) {
+    if (M < 0 || Cout <= 0 || C1 < 0 || C2 < 0 || C1 + C2 <= 0) return CRF_ERR_INVALID_ARG;
+    if (M == 0) return CRF_OK;
+    if ((C1 > 0 && !X1) || (C2 > 0 && !X2) || !W || !Y) return CRF_ERR_INVALID_ARG;
+    if (idx1 && (rows_dst <= 0 || rows_src <= 0)) return CRF_ERR_INVALID_ARG;
+    lin::FwdArgs a{X1, C1, scale1, shift1, slope1, idx1, rows_dst, rows_src, X2, C2, W, bias, Y, stats, M, Cout};
+    cudaStream_t st = (cudaStream_t)stream;
+    return lin::dispatch_bn(Cout, [&](auto bn) {
+        constexpr int BN = decltype(bn)::value;
+        dim3 grid((unsigned)ceil_div(M, lin::BM), (unsigned)ceil_div(Cout, BN));
+        if (precision == 0) lin::fwd_kernel<BN, true><<<grid, lin::kThreads, 0, st>>>(a);
+        else lin::fwd_kernel<BN, false><<<grid, lin::kThreads, 0, st>>>(a);
+        CRF_LAUNCH_CHECK();
+        return CRF_OK;
+    });
+}
+
+int crfconv_bn_finalize_fwd(const double* stats, int64_t count, const float* gamma, const float* beta, float eps, float momentum,
+                            int training, float* running_mean, float* running_var, float* scale, float* shift, float* mean,
+                            float* invstd, int C, void* stream) {
+    if (C <= 0 || !scale || !shift || (training && !stats) || (!training && (!running_mean || !running_var))) return CRF_ERR_INVALID_ARG;
+    lin::bn_finalize_fwd_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
+        stats, (double)count, gamma, beta, eps, momentum, training, running_mean, running_var, scale, shift, mean, invstd, C);
+    CRF_LAUNCH_CHECK();
+    return CRF_OK;
+}
+
+// Y = lrelu(H*scale + shift (+ R), slope)
+int crfconv_bn_act_fwd(const float* H, const float* scale, const float* shift, const float* R, float slope, float* Y, int64_t M,
+                       int C, void* stream) {
+    if (M < 0 || C <= 0 || (C & 3)) return CRF_ERR_INVALID_ARG;
+    if (M == 0) return CRF_OK;
+    const int64_t total4 = M * (C / 4);
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(total4, 256), (int64_t)kNumSMs * 16);
+    lin::bn_act_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(H, scale, shift, R, slope, Y, total4, C / 4);
+    CRF_LAUNCH_CHECK();
+    return CRF_OK;
+}
+
+// sums[0:C] += Σ dV, sums[C:2C] += Σ dV·Ĥ with dV = dY·lrelu'(pre), pre = act_ref ? act_ref : H*scale+shift.
+int crfconv_bn_bwd_reduce(const float* dY, const float* H, const float* act_ref, const float* scale, const float* shift,
+                          const float* mean, const float* invstd, float slope, double* sums, int64_t M, int C, void* stream) {
+    if (M < 0 || C <= 0 || (C & 3) || C > 1024 || (256 % (C / 4)) != 0) return CRF_ERR_UNSUPPORTED;
+    if (M == 0) return CRF_OK;
+    lin::BnBwd bn{scale, shift, mean, invstd, nullptr, nullptr, act_ref, slope};
+    const int rows_per_it = 256 / (C / 4);
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(M, rows_per_it * 8), (int64_t)kNumSMs * 8);
+    lin::bn_bwd_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dY, H, bn, sums, M, C);
+    CRF_LAUNCH_CHECK();
+    return CRF_OK;
+}
+
+int crfconv_bn_finalize_bwd(const double* sums, int64_t count, float* k1, float* k2, float* dgamma, float* dbeta, int C, void* stream) {
+    if (C <= 0 || !sums || !k1 || !k2) return CRF_ERR_INVALID_ARG;
+    lin::bn_finalize_bwd_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, (double)count, k1, k2, dgamma, dbeta, C);
+    CRF_LAUNCH_CHECK();
+    return CRF_OK;
+}
+
+// Gradient of crfconv_linear_fwd wrt its (post-prologue) inputs and its weight.  The upstream gradient is given wrt the
+// layer's ACTIVATION output (dY); the BN(+LeakyReLU) backward transform is applied on the fly (scale == NULL ⇒ the layer
+// had no BN: dH = dY).   dX1 / dX2 may be NULL (not needed); acc ⇒ accumulate into the destination.
+int crfconv_linear_bwd(const float* dY, const float* H, const float* act_ref, const float* scale, const float* shift,
+                       const float* mean, const float* invstd, const float* k1, const float* k2, float slope,
+                       const float* X1, int C1, const float* scale1, const float* shift1, float slope1, const int64_t* idx1,
+                       int64_t rows_dst, int64_t rows_src, const float* X2, int C2, const float* W, float* dX1, int acc1,
+                       float* dX2, int acc2, float* dW, float* dbias, int64_t M, int Cout, int precision, void* stream) {
+    if (M < 0 || Cout <= 0 || C1 < 0 || C2 < 0 || C1 + C2 <= 0 || !dY || !W) return CRF_ERR_INVALID_ARG;
+    if (M == 0) return CRF_OK;
+    if (scale && (Cout & 3)) return CRF_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    lin::BnBwd bn{scale, shift, mean, invstd, k1, k2, act_ref, slope};
+    const int Ktot = C1 + C2;
+    if (dX1 || dX2) {
+        if (idx1 && dX1) return CRF_ERR_UNSUPPORTED;   // gathered inputs: scatter the gradient with crfconv_scatter_add_rows
+        lin::DgradArgs a{dY, H, bn, W, dX1, C1, acc1, dX2, C2, acc2, M, Cout};
+        int rc = lin::dispatch_bn(Ktot, [&](auto bnv) {
+            constexpr int BN = decltype(bnv)::value;
+            dim3 grid((unsigned)ceil_div(M, lin::BM), (unsigned)ceil_div(Ktot, BN));
+            if (precision == 0) lin::dgrad_kernel<BN, true><<<grid, lin::kThreads, 0, st>>>(a);
+            else lin::dgrad_kernel<BN, false><<<grid, lin::kThreads, 0, st>>>(a);
+            CRF_LAUNCH_CHECK();
+            return CRF_OK;
+        });
+        if (rc != CRF_OK) return rc;
+    }
+    if (dW) {
+        lin::WgradArgs a{dY, H, bn, X1, C1, scale1, shift1, slope1, idx1, rows_dst, rows_src, X2, C2, dW, dbias, M, Cout, 0};
+        const int ty = (int)ceil_div(Cout, 64), tz = (int)ceil_div(Ktot, 64);
+        int64_t splits = std::max<int64_t>(1, std::min<int64_t>(ceil_div(M, 256), (int64_t)(2 * kNumSMs) / (ty * tz) + 1));
+        a.rows_per_cta = ceil_div(ceil_div(M, splits), lin::WR) * lin::WR;
+        splits = ceil_div(M, a.rows_per_cta);
+        dim3 grid((unsigned)splits, (unsigned)ty, (unsigned)tz);
+        if (precision == 0) lin::wgrad_kernel<true><<<grid, lin::kThreads, 0, st>>>(a);
+        else lin::wgrad_kernel<false><<<grid, lin::kThreads, 0, st>>>(a);
+        CRF_LAUNCH_CHECK();
+    }
+    return CRF_OK;
+}
+
+}  // extern "C"

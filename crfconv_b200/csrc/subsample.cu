@@ -17,6 +17,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "../../include/crfconv_b200.h"
 #include "common.cuh"
 #include "scan.cuh"
 

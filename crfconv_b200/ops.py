@@ -1,0 +1,153 @@
+"""Thin torch-tensor wrappers over the C-ABI layer kernels (include/crfconv_b200.h).  torch is used for device memory
+and streams only; every arithmetic op below runs in libcrfconv_b200.so.  All activations are row-major [rows, C] fp32
+CUDA tensors."""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import _lib
+
+# 0 = 3xTF32 (fp32-grade, default: matches the fp32 reference to ~1e-6), 1 = single-pass TF32
+PRECISION = int(os.environ.get("CRFCONV_PRECISION", "0"))
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t, name, dtype=torch.float32):
+    assert t.is_cuda and t.dtype == dtype and t.is_contiguous(), f"{name}: need contiguous CUDA {dtype} tensor"
+    return t
+
+
+def as2d(x):
+    """[B,N,C] or [M,C] → contiguous fp32 [M,C] view/copy."""
+    x = x.detach()
+    if x.dtype != torch.float32:
+        x = x.float()
+    return x.reshape(-1, x.shape[-1]).contiguous()
+
+
+class BN:
+    """Per-BatchNorm scratch: f64 Σ/Σ² accumulators, fused affine (scale, shift), saved mean/invstd, backward k1/k2."""
+    __slots__ = ("C", "stats", "scale", "shift", "mean", "invstd", "k1", "k2", "count", "training")
+
+    def __init__(self, C, device):
+        self.C = C
+        self.stats = torch.zeros(2 * C, dtype=torch.float64, device=device)
+        buf = torch.empty(6, C, dtype=torch.float32, device=device)
+        self.scale, self.shift, self.mean, self.invstd, self.k1, self.k2 = buf.unbind(0)
+        self.count = 0
+        self.training = True
+
+
+def linear_fwd(X1, W, *, scale1=None, shift1=None, slope1=1.0, idx1=None, rows_dst=0, rows_src=0, X2=None, bias=None,
+               stats=None, M=None, out=None):
+    L = _lib.lib()
+    C1 = X1.shape[1]
+    C2 = X2.shape[1] if X2 is not None else 0
+    if M is None:
+        M = idx1.numel() if idx1 is not None else X1.shape[0]
+    Cout = W.shape[0]
+    assert W.shape[1] == C1 + C2 and W.is_contiguous()
+    Y = out if out is not None else torch.empty((M, Cout), dtype=torch.float32, device=X1.device)
+    rc = L.crfconv_linear_fwd(_p(X1), C1, _p(scale1), _p(shift1), float(slope1), _p(idx1), int(rows_dst), int(rows_src), _p(X2), C2,
+                              _p(W), _p(bias), _p(Y), _p(stats), int(M), int(Cout), PRECISION, _lib.stream_ptr())
+    _lib.check(rc, "linear_fwd")
+    return Y
+
+
+def bn_finalize_fwd(bn: BN, count, gamma, beta, eps, momentum, training, running_mean, running_var):
+    L = _lib.lib()
+    bn.count, bn.training = int(count), bool(training)
+    rc = L.crfconv_bn_finalize_fwd(_p(bn.stats), int(count), _p(gamma), _p(beta), float(eps), float(momentum), int(bool(training)),
+                                   _p(running_mean), _p(running_var), _p(bn.scale), _p(bn.shift), _p(bn.mean), _p(bn.invstd),
+                                   bn.C, _lib.stream_ptr())
+    _lib.check(rc, "bn_finalize_fwd")
+
+
+def bn_act_fwd(H, bn: BN, slope, R=None, out=None):
+    L = _lib.lib()
+    Y = out if out is not None else torch.empty_like(H)
+    rc = L.crfconv_bn_act_fwd(_p(H), _p(bn.scale), _p(bn.shift), _p(R), float(slope), _p(Y), H.shape[0], H.shape[1], _lib.stream_ptr())
+    _lib.check(rc, "bn_act_fwd")
+    return Y
+
+
+def bn_backward_prepare(dY, H, bn: BN, slope, dgamma, dbeta, act_ref=None):
+    """Reduces Σ dV and Σ dV·Ĥ, accumulates dγ / dβ and fills bn.k1 / bn.k2 for the on-the-fly dH transform."""
+    L = _lib.lib()
+    sums = torch.zeros(2 * bn.C, dtype=torch.float64, device=H.device)
+    rc = L.crfconv_bn_bwd_reduce(_p(dY), _p(H), _p(act_ref), _p(bn.scale), _p(bn.shift), _p(bn.mean), _p(bn.invstd), float(slope),
+                                 _p(sums), H.shape[0], bn.C, _lib.stream_ptr())
+    _lib.check(rc, "bn_bwd_reduce")
+    rc = L.crfconv_bn_finalize_bwd(_p(sums), bn.count, _p(bn.k1), _p(bn.k2), _p(dgamma), _p(dbeta), bn.C, _lib.stream_ptr())
+    _lib.check(rc, "bn_finalize_bwd")
+    if not bn.training:      # eval-mode BN is a fixed affine map: dH = scale·dV
+        bn.k1.zero_()
+        bn.k2.zero_()
+
+
+def linear_bwd(dY, H, bn, slope, X1, W, *, scale1=None, shift1=None, slope1=1.0, idx1=None, rows_dst=0, rows_src=0, X2=None,
+               dX1=None, acc1=False, dX2=None, acc2=False, dW=None, dbias=None, act_ref=None):
+    """bn = BN (after bn_backward_prepare) or None for a plain Linear."""
+    L = _lib.lib()
+    C1 = X1.shape[1]
+    C2 = X2.shape[1] if X2 is not None else 0
+    M, Cout = dY.shape
+    b = bn
+    rc = L.crfconv_linear_bwd(_p(dY), _p(H), _p(act_ref), _p(b.scale) if b else None, _p(b.shift) if b else None,
+                              _p(b.mean) if b else None, _p(b.invstd) if b else None, _p(b.k1) if b else None,
+                              _p(b.k2) if b else None, float(slope),
+                              _p(X1), C1, _p(scale1), _p(shift1), float(slope1), _p(idx1), int(rows_dst), int(rows_src), _p(X2), C2,
+                              _p(W), _p(dX1), int(acc1), _p(dX2), int(acc2), _p(dW), _p(dbias), int(M), int(Cout), PRECISION,
+                              _lib.stream_ptr())
+    _lib.check(rc, "linear_bwd")
+
+
+# ------------------------------------------------------------------------------------------ CRF mean-field
+def crf_compat_fwd(c):
+    L = _lib.lib()
+    F = c.shape[0]
+    Cm, Minv = torch.empty_like(c), torch.empty_like(c)
+    scratch = torch.empty(3 * F * F, dtype=torch.float64, device=c.device)
+    _lib.check(L.crfconv_crf_compat_fwd(_p(c), _p(Cm), _p(Minv), _p(scratch), F, _lib.stream_ptr()), "crf_compat_fwd")
+    return Cm, Minv
+
+
+def crf_compat_bwd(c, Minv, GC, GM, Gc):
+    L = _lib.lib()
+    F = c.shape[0]
+    scratch = torch.empty(3 * F * F, dtype=torch.float64, device=c.device)
+    _lib.check(L.crfconv_crf_compat_bwd(_p(c), _p(Minv), _p(GC), _p(GM), _p(Gc), _p(scratch), F, _lib.stream_ptr()), "crf_compat_bwd")
+
+
+def crf_upsample_fwd(Hu, bn: BN, up_idx, B, N, Nc):
+    L = _lib.lib()
+    F = Hu.shape[1]
+    z = torch.empty((B * N, F), dtype=torch.float32, device=Hu.device)
+    _lib.check(L.crfconv_crf_upsample_fwd(_p(Hu), _p(bn.scale), _p(bn.shift), _p(up_idx), _p(z), B, N, Nc, F, _lib.stream_ptr()),
+               "crf_upsample_fwd")
+    return z
+
+
+def crf_upsample_bwd(Gz, G0, up_idx, Gu, B, N, Nc):
+    L = _lib.lib()
+    _lib.check(L.crfconv_crf_upsample_bwd(_p(Gz), _p(G0), _p(up_idx), _p(Gu), B, N, Nc, Gz.shape[1], _lib.stream_ptr()),
+               "crf_upsample_bwd")
+
+
+def crf_step_fwd(Hy, scale_y, z, xprev, nbr, Cm, Minv, B, N, K):
+    L = _lib.lib()
+    xout = torch.empty_like(z)
+    _lib.check(L.crfconv_crf_step_fwd(_p(Hy), _p(scale_y), _p(z), _p(xprev), _p(nbr), _p(Cm), _p(Minv), _p(xout), B, N, K, z.shape[1],
+                                      _lib.stream_ptr()), "crf_step_fwd")
+    return xout
+
+
+def crf_step_bwd(Hy, scale_y, z, xprev, nbr, Cm, Minv, g, Gz, gprev, Gy, m_out, v_out, h_out, B, N, K):
+    L = _lib.lib()
+    _lib.check(L.crfconv_crf_step_bwd(_p(Hy), _p(scale_y), _p(z), _p(xprev), _p(nbr), _p(Cm), _p(Minv), _p(g), _p(Gz), _p(gprev), _p(Gy),
+                                      _p(m_out), _p(v_out), _p(h_out), B, N, K, z.shape[1], _lib.stream_ptr()), "crf_step_bwd")

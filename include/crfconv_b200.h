@@ -65,6 +65,72 @@ int crfconv_grid_subsample_host(const float* points, int64_t N, const float* fea
                                 const int32_t* classes, int64_t ldim, float sampleDl, int order, float* out_points,
                                 float* out_features, int32_t* out_classes, int64_t* M_out);
 
+/* ------------------------------------------------------------- Linear + BatchNorm + LeakyReLU chains (MLP)
+ * Replaces models/common.py:26-40 (MLP = nn.Linear(bias = not bn) → FastBatchNorm1d → activation) as it is used by
+ * models/continuous_crf_conv_big.py:20-29 and models/point_conv_big.py:20-23,65-70.  All pointers are device
+ * pointers, tensors are row-major [rows, channels] f32.  precision: 0 = 3xTF32 (fp32-grade), 1 = one TF32 pass.  */
+
+/* Y[M,Cout] = [ lrelu(X1*scale1 + shift1, slope1) | X2 ] · Wᵀ (+ bias).  scale1 == NULL ⇒ X1 is used as is.
+ * idx1 != NULL ⇒ X1 rows are gathered: source row of output row m is (m / rows_dst) * rows_src + idx1[m]
+ * (point_conv_big.py:97-101).  stats != NULL ⇒ stats[0:Cout] += Σ_rows Y, stats[Cout:2Cout] += Σ_rows Y² (f64). */
+int crfconv_linear_fwd(const float* X1, int C1, const float* scale1, const float* shift1, float slope1, const int64_t* idx1,
+                       int64_t rows_dst, int64_t rows_src, const float* X2, int C2, const float* W, const float* bias, float* Y,
+                       double* stats, int64_t M, int Cout, int precision, void* stream);
+
+/* nn.BatchNorm1d bookkeeping (momentum, eps, biased variance for normalisation, unbiased for running_var).
+ * training: scale = γ·istd, shift = β − μ·scale from Σ/Σ², running stats updated in place (may be NULL);
+ * eval: from running statistics.  mean / invstd (saved for backward) may be NULL. */
+int crfconv_bn_finalize_fwd(const double* stats, int64_t count, const float* gamma, const float* beta, float eps, float momentum,
+                            int training, float* running_mean, float* running_var, float* scale, float* shift, float* mean,
+                            float* invstd, int C, void* stream);
+
+/* Y = lrelu(H*scale + shift (+ R), slope);  C % 4 == 0.  R (residual, point_conv_big.py:88) may be NULL. */
+int crfconv_bn_act_fwd(const float* H, const float* scale, const float* shift, const float* R, float slope, float* Y, int64_t M,
+                       int C, void* stream);
+
+/* BatchNorm backward reductions: sums[0:C] += Σ dV, sums[C:2C] += Σ dV·Ĥ, dV = dY·lrelu'(pre), Ĥ = (H−mean)·invstd,
+ * pre = act_ref ? act_ref : H*scale+shift. */
+int crfconv_bn_bwd_reduce(const float* dY, const float* H, const float* act_ref, const float* scale, const float* shift,
+                          const float* mean, const float* invstd, float slope, double* sums, int64_t M, int C, void* stream);
+
+/* k1 = sums[0:C]/count, k2 = sums[C:2C]/count; dgamma += sums[C:2C], dbeta += sums[0:C] (either may be NULL). */
+int crfconv_bn_finalize_bwd(const double* sums, int64_t count, float* k1, float* k2, float* dgamma, float* dbeta, int C, void* stream);
+
+/* Backward of crfconv_linear_fwd.  dY is the gradient wrt the layer's activation output; the BN(+LeakyReLU) backward
+ * dH = scale·(dV − k1 − Ĥ·k2) is applied on the fly (scale == NULL ⇒ no BN, dH = dY).  Produces dX1 [M,C1] / dX2 [M,C2]
+ * (gradients wrt the post-prologue inputs; NULL ⇒ skipped; acc ⇒ +=), dW [Cout,C1+C2] += dHᵀ·[prologue(X1)|X2],
+ * dbias += Σ dH (NULL ⇒ skipped). */
+int crfconv_linear_bwd(const float* dY, const float* H, const float* act_ref, const float* scale, const float* shift,
+                       const float* mean, const float* invstd, const float* k1, const float* k2, float slope,
+                       const float* X1, int C1, const float* scale1, const float* shift1, float slope1, const int64_t* idx1,
+                       int64_t rows_dst, int64_t rows_src, const float* X2, int C2, const float* W, float* dX1, int acc1,
+                       float* dX2, int acc2, float* dW, float* dbias, int64_t M, int Cout, int precision, void* stream);
+
+/* ------------------------------------------------------------------------ continuous-CRF mean-field
+ * Replaces the body of ContinuousGaussianCRFConv.forward, models/continuous_crf_conv_big.py:56-72 (and its autograd
+ * backward).  F = hidden channels ∈ {4,8,16,32,64}; neighbor_idx [B,N,K] i64 local to each cloud, column 0 skipped
+ * (:45-47); up_idx [B,N,1] i64 into the Nc coarse points of the same cloud (:60). */
+
+/* Cm = cᵀc, Minv = (I + Cm)^{-1} (:66,72).  scratch: 3·F·F doubles. */
+int crfconv_crf_compat_fwd(const float* c, float* Cm, float* Minv, double* scratch, int F, void* stream);
+/* Gc += c·(G + Gᵀ), G = GC − Minvᵀ·GM·Minvᵀ. */
+int crfconv_crf_compat_bwd(const float* c, const float* Minv, const float* GC, const float* GM, float* Gc, double* scratch, int F,
+                           void* stream);
+/* z[B·N,F] = (Hu*scale + shift)[up_idx]  — unary_nn's last BatchNorm fused into the nearest-coarse upsample. */
+int crfconv_crf_upsample_fwd(const float* Hu, const float* scale, const float* shift, const int64_t* up_idx, float* z, int64_t B,
+                             int64_t N, int64_t Nc, int F, void* stream);
+/* Gu[B·Nc,F] += (Gz + G0) scattered through up_idx (G0 may be NULL). */
+int crfconv_crf_upsample_bwd(const float* Gz, const float* G0, const int64_t* up_idx, float* Gu, int64_t B, int64_t N, int64_t Nc,
+                             int F, void* stream);
+/* xout = (z + (S·xprev)·Cm)·Minv, S = softmax_k(−‖y_i − y_j‖²), y = Hy*scale_y (+shift, which cancels). */
+int crfconv_crf_step_fwd(const float* Hy, const float* scale_y, const float* z, const float* xprev, const int64_t* neighbor_idx,
+                         const float* Cm, const float* Minv, float* xout, int64_t B, int64_t N, int K, int F, void* stream);
+/* Backward of one step given g = dL/dxout: Gz += g·Minvᵀ (=h); gprev += Σ_i s_ij·(h_i·Cmᵀ) (zero-initialised by caller);
+ * Gy += gradient through the distances wrt y; m_out / v_out / h_out rows feed GC = mᵀh and GM = vᵀg. */
+int crfconv_crf_step_bwd(const float* Hy, const float* scale_y, const float* z, const float* xprev, const int64_t* neighbor_idx,
+                         const float* Cm, const float* Minv, const float* g, float* Gz, float* gprev, float* Gy, float* m_out,
+                         float* v_out, float* h_out, int64_t B, int64_t N, int K, int F, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

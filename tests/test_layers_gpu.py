@@ -1,0 +1,138 @@
+"""GPU parity of the layer kernels (through the C ABI) against (a) the golden vectors produced by the UNMODIFIED
+reference modules and (b) the CPU oracle (oracle/layers.py) on fresh seeded inputs.
+Tolerance (north_star): outputs and gradients within 1e-3 relative in fp32; measured error is ~1e-5 with the default
+3xTF32 contractions.  `rel_err` is max|a-b| / max|b| per tensor (tests/_util.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import layers as ol
+from oracle import native as on
+from oracle import synthetic
+from tests._util import grad_floor, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def _load(module, g, tag):
+    sd = {k[len(tag) + 4:]: torch.from_numpy(v) for k, v in g.items() if k.startswith(tag + ".sd.")}
+    module.load_state_dict(sd)
+    return module.cuda().train()
+
+
+def _check_against_golden(module, g, tag, inputs, grad_inputs, tol=TOL):
+    for t in grad_inputs:
+        t.requires_grad_(True)
+    out = module(*inputs)
+    (out * torch.from_numpy(g[tag + ".cot"]).cuda()).sum().backward()
+    floor = grad_floor(g, tag)
+    errs = {"out": rel_err(out.detach().cpu().numpy(), g[tag + ".out"])}
+    for i, t in enumerate(grad_inputs):
+        errs[f"gin{i}"] = rel_err(t.grad.cpu().numpy(), g[f"{tag}.gin{i}"])
+    for n, p in module.named_parameters():
+        assert p.grad is not None, n
+        errs["grad " + n] = rel_err(p.grad.cpu().numpy(), g[f"{tag}.gparam.{n}"], floor)
+    for n, b in module.named_buffers():
+        errs["buf " + n] = rel_err(b.detach().cpu().numpy(), g[f"{tag}.buf_after.{n}"])
+    bad = {k: v for k, v in errs.items() if not v < tol}
+    assert not bad, f"{tag}: {bad}"
+    return max(errs.values())
+
+
+@pytest.mark.parametrize("tag,Cu,Cp,steps", [("crf_s1", 128, 64, 1), ("crf_s3", 64, 32, 3)])
+def test_crf_layer_vs_reference_golden(golden, tag, Cu, Cp, steps):
+    from crfconv_b200.continuous_crf_conv_big import ContinuousGaussianCRFConv
+    g = golden("layer_golden")
+    m = _load(ContinuousGaussianCRFConv(Cu, Cp, Cp, steps=steps), g, tag)
+    u, p = torch.from_numpy(g[tag + ".unary"]).cuda(), torch.from_numpy(g[tag + ".pairwise"]).cuda()
+    worst = _check_against_golden(m, g, tag, (u, p, torch.from_numpy(g[tag + ".up_idx"]).cuda(),
+                                              torch.from_numpy(g[tag + ".neighbor_idx"]).cuda()), (u, p))
+    print(f"{tag}: worst rel err {worst:.2e}")
+
+
+def _oracle_vs_product(make_oracle, make_product, inputs_cpu, grad_idx, seed=0, tol=TOL):
+    torch.manual_seed(seed)
+    mo = make_oracle()
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for n, p in mo.named_parameters():
+            if "batch_norm.weight" in n:
+                p.copy_(1 + 0.2 * torch.randn(p.shape, generator=g))
+            elif "batch_norm.bias" in n:
+                p.copy_(0.2 * torch.randn(p.shape, generator=g))
+            elif n.endswith("c"):
+                p.copy_(torch.eye(p.shape[0]) + 0.1 * torch.randn(p.shape, generator=g))
+    mp = make_product()
+    mp.load_state_dict(mo.state_dict())
+    mp = mp.cuda().train()
+    mo.train()
+    ic = [t.clone() for t in inputs_cpu]
+    ig = [t.clone().cuda() for t in inputs_cpu]
+    for i in grad_idx:
+        ic[i].requires_grad_(True)
+        ig[i].requires_grad_(True)
+    oo = mo(*ic)
+    cot = torch.randn(oo.shape, generator=g)
+    (oo * cot).sum().backward()
+    og = mp(*ig)
+    (og * cot.cuda()).sum().backward()
+    errs = {"out": rel_err(og.detach().cpu().numpy(), oo.detach().numpy())}
+    for i in grad_idx:
+        errs[f"gin{i}"] = rel_err(ig[i].grad.cpu().numpy(), ic[i].grad.numpy())
+    floor = 1e-3 * max(float(p.grad.abs().max()) for p in mo.parameters())
+    po = dict(mo.named_parameters())
+    for n, p in mp.named_parameters():
+        errs["grad " + n] = rel_err(p.grad.cpu().numpy(), po[n].grad.numpy(), floor)
+    bo = dict(mo.named_buffers())
+    for n, b in mp.named_buffers():
+        errs["buf " + n] = rel_err(b.cpu().numpy(), bo[n].numpy())
+    bad = {k: v for k, v in errs.items() if not v < tol}
+    assert not bad, bad
+    return max(errs.values())
+
+
+@pytest.mark.parametrize("B,N,Cu,Co,steps", [(1, 2048, 128, 64, 1), (3, 1000, 64, 32, 2), (2, 640, 512, 256, 1), (2, 4096, 256, 128, 5)])
+def test_crf_layer_vs_oracle(B, N, Cu, Co, steps):
+    """All four decoder shapes of PointConvResNet (point_conv_big.py:131-134), B=1 included, ragged N (not a multiple of
+    the 128-row tile)."""
+    from crfconv_b200.continuous_crf_conv_big import ContinuousGaussianCRFConv
+    inp = synthetic.crf_layer_inputs(B, N, 16, Cu, Co, 4, seed=N, knn_batch_fn=on.knn_batch)
+    worst = _oracle_vs_product(lambda: ol.ContinuousGaussianCRFConv(Cu, Co, Co, steps=steps),
+                               lambda: ContinuousGaussianCRFConv(Cu, Co, Co, steps=steps),
+                               [inp.unary, inp.pairwise, inp.up_idx, inp.neighbor_idx], (0, 1), seed=N)
+    print(f"crf B={B} N={N} Cu={Cu} Co={Co} T={steps}: worst rel err {worst:.2e}")
+
+
+@pytest.mark.parametrize("cin,cout,bn,act", [(6, 32, True, "lrelu"), (128, 64, True, None), (32, 128, True, "lrelu"),
+                                             (128, 13, False, None), (64, 16, False, "lrelu"), (3, 8, True, "lrelu")])
+def test_mlp_vs_oracle(cin, cout, bn, act):
+    from crfconv_b200.common import MLP
+    import torch.nn as nn
+    mk = lambda cls: (lambda: cls(cin, cout, bn=bn, activation=nn.LeakyReLU(0.1) if act else None))   # noqa: E731
+    x = torch.randn(3, 777, cin, generator=torch.Generator().manual_seed(cin))
+    _oracle_vs_product(mk(ol.MLP), mk(MLP), [x], (0,), seed=cout)
+
+
+def test_eval_mode_uses_running_statistics():
+    from crfconv_b200.continuous_crf_conv_big import ContinuousGaussianCRFConv
+    inp = synthetic.crf_layer_inputs(2, 512, 16, 128, 64, 4, seed=3, knn_batch_fn=on.knn_batch)
+    torch.manual_seed(0)
+    mo = ol.ContinuousGaussianCRFConv(128, 64, 64)
+    mp = ContinuousGaussianCRFConv(128, 64, 64)
+    mp.load_state_dict(mo.state_dict())
+    mp = mp.cuda()
+    args = [inp.unary, inp.pairwise, inp.up_idx, inp.neighbor_idx]
+    for _ in range(2):                       # two training steps move the running statistics
+        mo.train()(*args); mp.train()(*[a.cuda() for a in args])
+    with torch.no_grad():
+        eo = mo.eval()(*args)
+        ep = mp.eval()(*[a.cuda() for a in args])
+    assert rel_err(ep.cpu().numpy(), eo.numpy()) < TOL
+    assert int(mp.out_nn.bn.batch_norm.num_batches_tracked) == 2
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    from crfconv_b200.common import MLP
+    with pytest.raises(RuntimeError, match="CUDA"):
+        MLP(8, 8)(torch.randn(4, 8))
