@@ -22,6 +22,7 @@ SIGNATURES = {
     "crfconv_grid_subsample_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "crfconv_grid_subsample": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _f32, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "crfconv_grid_subsample_host": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _f32, _int, _vp, _vp, _vp, _vp]),
+    "crfconv_set_fast_path": (_int, [_int]),
     "crfconv_linear_fwd": (_int, [_vp, _int, _vp, _vp, _f32, _vp, _i64, _i64, _vp, _int, _vp, _vp, _vp, _vp, _i64, _int, _int, _vp]),
     "crfconv_bn_finalize_fwd": (_int, [_vp, _i64, _vp, _vp, _f32, _f32, _int, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "crfconv_bn_act_fwd": (_int, [_vp, _vp, _vp, _vp, _f32, _vp, _i64, _int, _vp]),
@@ -35,7 +36,7 @@ SIGNATURES = {
     "crfconv_crf_upsample_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
     "crfconv_crf_upsample_bwd": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
     "crfconv_crf_step_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _vp]),
-    "crfconv_crf_step_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _vp]),
+    "crfconv_crf_step_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _i64, _i64, _int, _int, _vp]),
 }
 
 

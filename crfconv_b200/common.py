@@ -42,9 +42,9 @@ def _slope_of(activation):
     return None
 
 
-def bn_forward_state(C, device, count, bn_module, training):
+def bn_forward_state(C, device, count, bn_module, training, stats=None):
     """Allocates the per-call BN scratch; returns (state, finalize) where finalize() must run after the producing GEMM."""
-    st = ops.BN(C, device)
+    st = ops.BN(C, device, stats)
 
     def finalize():
         ops.bn_finalize_fwd(st, count, bn_module.weight, bn_module.bias, bn_module.eps,

@@ -30,6 +30,9 @@ class _CRFConvFunction(torch.autograd.Function):
             raise RuntimeError("crfconv_b200 layers run on CUDA tensors only (no CPU fallback)")
         (W1u, _, _, W2u, _, _, W1p, _, _, W2p, _, _, Wo, _, _, Wf, _, _) = [p.detach().contiguous().float() for p in params]
         bns = [m.bn.batch_norm for m in mods]          # order: u0, u1, p0, p1, out, fusion
+        sl = [m.slope for m in mods]                   # LeakyReLU slopes (1.0 = no activation), reference: .1, 1, .1, 1, .1, .1
+        if any(v is None for v in sl) or sl[1] != 1.0 or sl[3] != 1.0:
+            raise RuntimeError("ContinuousGaussianCRFConv: only LeakyReLU/ReLU/None activations in the reference positions are fused")
         B, Nc, Cu = unary.shape
         _, N, Cp = pairwise.shape
         K = neighbor_idx.shape[-1]
@@ -43,15 +46,17 @@ class _CRFConvFunction(torch.autograd.Function):
         def tr(bn):
             return training or not bn.track_running_stats
 
+        fstats = ops.Flat(2 * (4 * F + 2 * Co), torch.float64, dev)
+
         # unary_nn / pairwise_nn, layer 1 and 2 (:58-59)
-        s1u, fin = bn_forward_state(F, dev, Mc, bns[0], tr(bns[0]))
+        s1u, fin = bn_forward_state(F, dev, Mc, bns[0], tr(bns[0]), fstats.take(2 * F))
         H1u = ops.linear_fwd(U, W1u, stats=s1u.stats); fin()
-        s1p, fin = bn_forward_state(F, dev, M, bns[2], tr(bns[2]))
+        s1p, fin = bn_forward_state(F, dev, M, bns[2], tr(bns[2]), fstats.take(2 * F))
         H1p = ops.linear_fwd(P, W1p, stats=s1p.stats); fin()
-        s2u, fin = bn_forward_state(F, dev, Mc, bns[1], tr(bns[1]))
-        H2u = ops.linear_fwd(H1u, W2u, scale1=s1u.scale, shift1=s1u.shift, slope1=0.1, stats=s2u.stats); fin()
-        s2p, fin = bn_forward_state(F, dev, M, bns[3], tr(bns[3]))
-        H2p = ops.linear_fwd(H1p, W2p, scale1=s1p.scale, shift1=s1p.shift, slope1=0.1, stats=s2p.stats); fin()
+        s2u, fin = bn_forward_state(F, dev, Mc, bns[1], tr(bns[1]), fstats.take(2 * F))
+        H2u = ops.linear_fwd(H1u, W2u, scale1=s1u.scale, shift1=s1u.shift, slope1=sl[0], stats=s2u.stats); fin()
+        s2p, fin = bn_forward_state(F, dev, M, bns[3], tr(bns[3]), fstats.take(2 * F))
+        H2p = ops.linear_fwd(H1p, W2p, scale1=s1p.scale, shift1=s1p.shift, slope1=sl[2], stats=s2p.stats); fin()
         # mean field (:60-72)
         cc = c.detach().contiguous().float()
         Cm, Minv = ops.crf_compat_fwd(cc)
@@ -60,14 +65,15 @@ class _CRFConvFunction(torch.autograd.Function):
         for _ in range(steps):
             xs.append(ops.crf_step_fwd(H2p, s2p.scale, z, xs[-1], nbr, Cm, Minv, B, N, K))
         # out_nn, fusion_nn (:74-76)
-        so, fin = bn_forward_state(Co, dev, M, bns[4], tr(bns[4]))
+        so, fin = bn_forward_state(Co, dev, M, bns[4], tr(bns[4]), fstats.take(2 * Co))
         H3 = ops.linear_fwd(xs[-1], Wo, stats=so.stats); fin()
-        sf, fin = bn_forward_state(Co, dev, M, bns[5], tr(bns[5]))
-        Hf = ops.linear_fwd(H3, Wf, scale1=so.scale, shift1=so.shift, slope1=0.1, X2=P, stats=sf.stats); fin()
-        out = ops.bn_act_fwd(Hf, sf, 0.1)
+        sf, fin = bn_forward_state(Co, dev, M, bns[5], tr(bns[5]), fstats.take(2 * Co))
+        Hf = ops.linear_fwd(H3, Wf, scale1=so.scale, shift1=so.shift, slope1=sl[4], X2=P, stats=sf.stats); fin()
+        out = ops.bn_act_fwd(Hf, sf, sl[5])
 
         ctx.dims = (B, N, Nc, K, F, Co, Cu, Cp, steps)
         ctx.bn = (s1u, s2u, s1p, s2p, so, sf)
+        ctx.sl = sl
         ctx.save_for_backward(U, P, up, nbr, H1u, H2u, H1p, H2p, H3, Hf, Cm, Minv, cc, W1u, W2u, W1p, W2p, Wo, Wf, *xs)
         return out.view(B, N, Co)
 
@@ -76,57 +82,61 @@ class _CRFConvFunction(torch.autograd.Function):
         (U, P, up, nbr, H1u, H2u, H1p, H2p, H3, Hf, Cm, Minv, cc, W1u, W2u, W1p, W2p, Wo, Wf, *xs) = ctx.saved_tensors
         B, N, Nc, K, F, Co, Cu, Cp, steps = ctx.dims
         s1u, s2u, s1p, s2p, so, sf = ctx.bn
+        sl = ctx.sl
         dev = gout.device
         Mc, M = B * Nc, B * N
         z = xs[0]
         g2 = ops.as2d(gout)
 
-        def zeros(*shape):
-            return torch.zeros(*shape, dtype=torch.float32, device=dev)
-
-        dW = {k: zeros(*w.shape) for k, w in (("1u", W1u), ("2u", W2u), ("1p", W1p), ("2p", W2p), ("o", Wo), ("f", Wf))}
-        dg = {k: zeros(n) for k, n in (("1u", F), ("2u", F), ("1p", F), ("2p", F), ("o", Co), ("f", Co))}
-        db = {k: zeros(n) for k, n in (("1u", F), ("2u", F), ("1p", F), ("2p", F), ("o", Co), ("f", Co))}
+        wl = (("1u", W1u), ("2u", W2u), ("1p", W1p), ("2p", W2p), ("o", Wo), ("f", Wf))
+        cl = (("1u", F), ("2u", F), ("1p", F), ("2p", F), ("o", Co), ("f", Co))
+        small = ops.Flat(sum(w.numel() for _, w in wl) + 2 * sum(n for _, n in cl) + 3 * F * F, torch.float32, dev)
+        sums = ops.Flat(2 * sum(n for _, n in cl), torch.float64, dev)
+        big = ops.Flat((steps + 1) * M * F + Mc * F, torch.float32, dev)       # scatter targets: Gy, gprev per step, Gu
+        zeros = small.take
+        dW = {k: small.take(*w.shape) for k, w in wl}
+        dg = {k: small.take(n) for k, n in cl}
+        db = {k: small.take(n) for k, n in cl}
 
         # fusion_nn
-        ops.bn_backward_prepare(g2, Hf, sf, 0.1, dg["f"], db["f"])
+        ops.bn_backward_prepare(g2, Hf, sf, sl[5], dg["f"], db["f"], sums=sums.take(2 * Co))
         dO = torch.empty((M, Co), dtype=torch.float32, device=dev)
         dP = torch.empty((M, Cp), dtype=torch.float32, device=dev)
-        ops.linear_bwd(g2, Hf, sf, 0.1, H3, Wf, scale1=so.scale, shift1=so.shift, slope1=0.1, X2=P, dX1=dO, dX2=dP, dW=dW["f"])
+        ops.linear_bwd(g2, Hf, sf, sl[5], H3, Wf, scale1=so.scale, shift1=so.shift, slope1=sl[4], X2=P, dX1=dO, dX2=dP, dW=dW["f"])
         # out_nn
-        ops.bn_backward_prepare(dO, H3, so, 0.1, dg["o"], db["o"])
+        ops.bn_backward_prepare(dO, H3, so, sl[4], dg["o"], db["o"], sums=sums.take(2 * Co))
         g = torch.empty((M, F), dtype=torch.float32, device=dev)
-        ops.linear_bwd(dO, H3, so, 0.1, xs[-1], Wo, dX1=g, dW=dW["o"])
+        ops.linear_bwd(dO, H3, so, sl[4], xs[-1], Wo, dX1=g, dW=dW["o"])
         # mean-field steps, last to first
-        Gz, Gy, GC, GM = zeros(M, F), zeros(M, F), zeros(F, F), zeros(F, F)
-        m_out, v_out, h_out = (torch.empty((M, F), dtype=torch.float32, device=dev) for _ in range(3))
+        Gy, GC, GM = big.take(M, F), zeros(F, F), zeros(F, F)
+        Gz, m_out, v_out, h_out = (torch.empty((M, F), dtype=torch.float32, device=dev) for _ in range(4))
         for t in range(steps, 0, -1):
-            gprev = zeros(M, F)
-            ops.crf_step_bwd(H2p, s2p.scale, z, xs[t - 1], nbr, Cm, Minv, g, Gz, gprev, Gy, m_out, v_out, h_out, B, N, K)
+            gprev = big.take(M, F)
+            ops.crf_step_bwd(H2p, s2p.scale, z, xs[t - 1], nbr, Cm, Minv, g, Gz, gprev, Gy, m_out, v_out, h_out, t != steps, B, N, K)
             ops.linear_bwd(m_out, None, None, 1.0, h_out, GC, dW=GC)      # GC += mᵀ·h   (W argument unused by wgrad)
             ops.linear_bwd(v_out, None, None, 1.0, g, GM, dW=GM)          # GM += vᵀ·g
             g = gprev
         Gc = zeros(F, F)
         ops.crf_compat_bwd(cc, Minv, GC, GM, Gc)
-        Gu = zeros(Mc, F)
+        Gu = big.take(Mc, F)
         if steps > 0:
             ops.crf_upsample_bwd(Gz, g, up, Gu, B, N, Nc)      # dL/dz = Σ_t h^t + g^0
         else:
             ops.crf_upsample_bwd(g, None, up, Gu, B, N, Nc)
         # unary_nn
-        ops.bn_backward_prepare(Gu, H2u, s2u, 1.0, dg["2u"], db["2u"])
+        ops.bn_backward_prepare(Gu, H2u, s2u, 1.0, dg["2u"], db["2u"], sums=sums.take(2 * F))
         dA = torch.empty((Mc, F), dtype=torch.float32, device=dev)
-        ops.linear_bwd(Gu, H2u, s2u, 1.0, H1u, W2u, scale1=s1u.scale, shift1=s1u.shift, slope1=0.1, dX1=dA, dW=dW["2u"])
-        ops.bn_backward_prepare(dA, H1u, s1u, 0.1, dg["1u"], db["1u"])
+        ops.linear_bwd(Gu, H2u, s2u, 1.0, H1u, W2u, scale1=s1u.scale, shift1=s1u.shift, slope1=sl[0], dX1=dA, dW=dW["2u"])
+        ops.bn_backward_prepare(dA, H1u, s1u, sl[0], dg["1u"], db["1u"], sums=sums.take(2 * F))
         dU = torch.empty((Mc, Cu), dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
-        ops.linear_bwd(dA, H1u, s1u, 0.1, U, W1u, dX1=dU, dW=dW["1u"])
+        ops.linear_bwd(dA, H1u, s1u, sl[0], U, W1u, dX1=dU, dW=dW["1u"])
         # pairwise_nn (its input gradient accumulates onto the fusion_nn branch)
-        ops.bn_backward_prepare(Gy, H2p, s2p, 1.0, dg["2p"], db["2p"])
+        ops.bn_backward_prepare(Gy, H2p, s2p, 1.0, dg["2p"], db["2p"], sums=sums.take(2 * F))
         dA = torch.empty((M, F), dtype=torch.float32, device=dev)
-        ops.linear_bwd(Gy, H2p, s2p, 1.0, H1p, W2p, scale1=s1p.scale, shift1=s1p.shift, slope1=0.1, dX1=dA, dW=dW["2p"])
-        ops.bn_backward_prepare(dA, H1p, s1p, 0.1, dg["1p"], db["1p"])
+        ops.linear_bwd(Gy, H2p, s2p, 1.0, H1p, W2p, scale1=s1p.scale, shift1=s1p.shift, slope1=sl[2], dX1=dA, dW=dW["2p"])
+        ops.bn_backward_prepare(dA, H1p, s1p, sl[2], dg["1p"], db["1p"], sums=sums.take(2 * F))
         need_p = ctx.needs_input_grad[1]
-        ops.linear_bwd(dA, H1p, s1p, 0.1, P, W1p, dX1=dP if need_p else None, acc1=True, dW=dW["1p"])
+        ops.linear_bwd(dA, H1p, s1p, sl[2], P, W1p, dX1=dP if need_p else None, acc1=True, dW=dW["1p"])
 
         grads = []
         for k in ("1u", "2u", "1p", "2p", "o", "f"):

@@ -110,7 +110,8 @@ struct StepArgs {
     float* xout;           // [B*N, F]  x^t
     // backward
     const float* g;        // [B*N, F]  dL/dx^t
-    float* Gz;             // [B*N, F]  += h_i            (owner writes)
+    float* Gz;             // [B*N, F]  (+)= h_i          (owner writes; += when gz_acc)
+    int gz_acc;
     float* gprev;          // [B*N, F]  += s_ij q_i       (scatter, zero-initialised by the caller)
     float* Gy;             // [B*N, F]  += distance-path gradient wrt y (scatter)
     float* m_out;          // [B*N, F]  m_i               (for GC = mᵀh)
@@ -231,8 +232,8 @@ __global__ void __launch_bounds__(256) step_bwd_kernel(const StepArgs a) {
     if (valid) {
         red_add_v4(a.Gy + p * F + c0, gyi);
         float* gz = a.Gz + p * F + c0;
-        float4 o = *reinterpret_cast<float4*>(gz);
-        o.x += h.x; o.y += h.y; o.z += h.z; o.w += h.w;
+        float4 o = h;
+        if (a.gz_acc) { const float4 old = *reinterpret_cast<float4*>(gz); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
         *reinterpret_cast<float4*>(gz) = o;
         *reinterpret_cast<float4*>(a.h_out + p * F + c0) = h;
         *reinterpret_cast<float4*>(a.m_out + p * F + c0) = msg;
@@ -383,11 +384,11 @@ int crfconv_crf_step_fwd(const float* Hy, const float* scale_y, const float* z, 
     });
 }
 
-// Backward of one step.  g = dL/dx^t.  Gz += h (owner rows), gprev += Σ s_ij q_i (must be zero-initialised),
+// Backward of one step.  g = dL/dx^t.  Gz = h, or += h when gz_acc (owner rows), gprev += Σ s_ij q_i (must be zero-initialised),
 // Gy += distance-path gradient (zero-initialised by the caller before the first step), m/v/h rows for GC = mᵀh, GM = vᵀg.
 int crfconv_crf_step_bwd(const float* Hy, const float* scale_y, const float* z, const float* xprev, const int64_t* neighbor_idx,
                          const float* Cm, const float* Minv, const float* g, float* Gz, float* gprev, float* Gy, float* m_out,
-                         float* v_out, float* h_out, int64_t B, int64_t N, int K, int F, void* stream) {
+                         float* v_out, float* h_out, int gz_acc, int64_t B, int64_t N, int K, int F, void* stream) {
     if (B < 0 || N < 0 || K < 1 || !Hy || !scale_y || !z || !xprev || !neighbor_idx || !Cm || !Minv || !g || !Gz || !gprev || !Gy ||
         !m_out || !v_out || !h_out)
         return CRF_ERR_INVALID_ARG;
@@ -395,7 +396,7 @@ int crfconv_crf_step_bwd(const float* Hy, const float* scale_y, const float* z, 
     mf::StepArgs a{};
     a.Hy = Hy; a.scale_y = scale_y; a.z = z; a.xprev = xprev; a.nbr = neighbor_idx; a.Cm = Cm; a.Minv = Minv;
     a.total = B * N; a.N = N; a.K = K;
-    a.g = g; a.Gz = Gz; a.gprev = gprev; a.Gy = Gy; a.m_out = m_out; a.v_out = v_out; a.h_out = h_out;
+    a.g = g; a.Gz = Gz; a.gz_acc = gz_acc; a.gprev = gprev; a.Gy = Gy; a.m_out = m_out; a.v_out = v_out; a.h_out = h_out;
     return mf::dispatch_f(F, [&](auto f) {
         constexpr int FF = decltype(f)::value;
         constexpr int PPW = 32 / (FF / 4);

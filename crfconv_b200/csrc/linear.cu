@@ -12,10 +12,12 @@
 // is applied on the fly while staging dH for the dgrad (dX = dH·W) and wgrad (dW = dHᵀ·A) contractions.
 // Contractions run on mma.sync m16n8k8 tf32 with 3xTF32 error compensation (mma.cuh) – fp32-grade results.
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "../../include/crfconv_b200.h"
 #include "common.cuh"
+#include "linear_args.cuh"
 #include "mma.cuh"
 
 namespace crf {
@@ -29,17 +31,7 @@ constexpr int AS = BK + 4;   // smem row stride for [row][k] operands read as (g
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.0f ? v : v * slope; }
 
 // ------------------------------------------------------------------------------------------ forward
-struct FwdArgs {
-    const float* X1; int C1;                      // segment 1: [M, C1] (row-gathered through idx1 when given)
-    const float* scale1; const float* shift1; float slope1;   // prologue of segment 1: lrelu(x*scale+shift); null = identity
-    const int64_t* idx1; int64_t rows_dst; int64_t rows_src;  // gather: src row = (m / rows_dst) * rows_src + idx1[m]
-    const float* X2; int C2;                      // segment 2: [M, C2] raw (may be null / 0)
-    const float* W;                               // [Cout, C1 + C2] row-major (nn.Linear.weight)
-    const float* bias;                            // [Cout] or null
-    float* Y;                                     // [M, Cout]
-    double* stats;                                // [2*Cout]: Σ, Σ² over rows (or null)
-    int64_t M; int Cout;
-};
+
 
 template <int BN, bool X3>
 __global__ void __launch_bounds__(kThreads) fwd_kernel(const FwdArgs a) {
@@ -239,17 +231,6 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------ backward
-// Per-channel description of a BatchNorm(+LeakyReLU) node for the on-the-fly backward transform.
-struct BnBwd {
-    const float* scale;    // γ·istd        (null ⇒ plain Linear output: dH = dY)
-    const float* shift;    // β − μ·scale
-    const float* mean;
-    const float* invstd;
-    const float* k1;       // mean over rows of dV
-    const float* k2;       // mean over rows of dV·Ĥ
-    const float* act_ref;  // [M, C] saved activation output whose sign selects the LeakyReLU branch (null ⇒ use V)
-    float slope;           // 1 ⇒ no activation
-};
 
 __device__ __forceinline__ float bn_dv(float dy, float h, float ref, bool has_ref, float sc, float sh, float slope) {
     const float pre = has_ref ? ref : fmaf(h, sc, sh);
@@ -329,13 +310,7 @@ __device__ __forceinline__ void load_dh4(const float* __restrict__ dY, const flo
 // scalar variant for Cout % 4 != 0 (plain Linear only, e.g. the 13-class head)
 __device__ __forceinline__ float load_dh1(const float* __restrict__ dY, int64_t m, int C, int c) { return __ldg(dY + m * C + c); }
 
-struct DgradArgs {
-    const float* dY; const float* H; BnBwd bn;    // upstream gradient wrt this layer's activation output, pre-BN output
-    const float* W;                               // [Cout, C1 + C2]
-    float* dX1; int C1; int acc1;                 // gradient wrt segment 1 input (post-prologue), [M, C1]; acc ⇒ +=
-    float* dX2; int C2; int acc2;
-    int64_t M; int Cout;
-};
+
 
 constexpr int BS8 = 8;   // extra stride so that [k][n] operands read as (t, g) hit bank 8t + g
 
@@ -431,16 +406,7 @@ __global__ void __launch_bounds__(kThreads) dgrad_kernel(const DgradArgs a) {
 
 // dW[co, k] += Σ_m dH[m, co] · A[m, k],  A = [prologue(X1) | X2].  Output tile 64 (co) × 64 (k) per CTA; CTAs along
 // x split the rows; partial tiles are combined with fp32 atomics.
-struct WgradArgs {
-    const float* dY; const float* H; BnBwd bn;
-    const float* X1; int C1; const float* scale1; const float* shift1; float slope1;
-    const int64_t* idx1; int64_t rows_dst; int64_t rows_src;
-    const float* X2; int C2;
-    float* dW;            // [Cout, C1 + C2]
-    float* dbias;         // [Cout] or null: += Σ_m dH
-    int64_t M; int Cout;
-    int64_t rows_per_cta;
-};
+
 
 constexpr int WR = 64;          // rows per staging tile
 constexpr int WS = 64 + BS8;    // smem stride
@@ -539,6 +505,22 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const WgradArgs a) {
     if (a.dbias && blockIdx.z == 0 && tid < 64 && co0 + tid < a.Cout) atomicAdd(a.dbias + co0 + tid, bsum);
 }
 
+inline bool force_generic() {
+    static const bool v = [] { const char* e = getenv("CRFCONV_FORCE_GENERIC"); return e && e[0] == '1'; }();
+    return v;
+}
+// The bf16x3 fast path (≈2^-17 per product) is used from this many rows on; smaller problems are launch-bound anyway and
+// take the generic 3xTF32 kernels (≈2^-21), which keeps ill-conditioned tiny batches inside the 1e-3 parity budget.
+inline int64_t fast_min_rows() {
+    static const int64_t v = [] { const char* e = getenv("CRFCONV_FAST_MIN_ROWS"); return e ? (int64_t)atoll(e) : (int64_t)8192; }();
+    return v;
+}
+static int g_fast_override = -1;   // -1: rule above; 0: never; 1: always (crfconv_set_fast_path, used by the tests)
+inline bool use_fast(int64_t M) {
+    if (g_fast_override >= 0) return g_fast_override == 1;
+    return !force_generic() && M >= fast_min_rows();
+}
+
 template <typename F>
 inline int dispatch_bn(int n, F&& f) {
     if (n > 32) return f(std::integral_constant<int, 64>{});
@@ -554,6 +536,14 @@ using namespace crf;
 
 extern "C" {
 
+// Test / experiment knob: -1 = default rule (fast bf16x3 kernels from CRFCONV_FAST_MIN_ROWS rows on), 0 = generic kernels
+// only, 1 = fast kernels whenever the shape allows.  Returns the previous setting.
+int crfconv_set_fast_path(int mode) {
+    const int prev = lin::g_fast_override;
+    lin::g_fast_override = mode < 0 ? -1 : (mode ? 1 : 0);
+    return prev;
+}
+
 // Y[M,Cout] = [lrelu(X1*scale1+shift1) | X2] · Wᵀ (+ bias);  stats[0:Cout] += Σ_rows Y, stats[Cout:2Cout] += Σ_rows Y².
 // X1 rows may be gathered: source row of output row m = (m / rows_dst) * rows_src + idx1[m]   (idx1 null ⇒ identity).
 // precision: 0 = 3xTF32 (fp32-grade), 1 = single-pass TF32.
@@ -566,6 +556,11 @@ int crfconv_linear_fwd(const float* X1, int C1, const float* scale1, const float
     if (idx1 && (rows_dst <= 0 || rows_src <= 0)) return CRF_ERR_INVALID_ARG;
     lin::FwdArgs a{X1, C1, scale1, shift1, slope1, idx1, rows_dst, rows_src, X2, C2, W, bias, Y, stats, M, Cout};
     cudaStream_t st = (cudaStream_t)stream;
+    if (lin::use_fast(M)) {
+        int rc2 = CRF_OK;
+        if (lin::try_fwd2(a, precision, st, &rc2)) return rc2;
+    }
+    if (precision == 2) precision = 1;     // generic kernels: single-pass TF32 stands in for single-pass bf16
     return lin::dispatch_bn(Cout, [&](auto bn) {
         constexpr int BN = decltype(bn)::value;
         dim3 grid((unsigned)ceil_div(M, lin::BM), (unsigned)ceil_div(Cout, BN));
@@ -632,13 +627,16 @@ int crfconv_linear_bwd(const float* dY, const float* H, const float* act_ref, co
     cudaStream_t st = (cudaStream_t)stream;
     lin::BnBwd bn{scale, shift, mean, invstd, k1, k2, act_ref, slope};
     const int Ktot = C1 + C2;
+    const int gprec = precision == 2 ? 1 : precision;    // precision seen by the generic (TF32) kernels
     if (dX1 || dX2) {
         if (idx1 && dX1) return CRF_ERR_UNSUPPORTED;   // gathered inputs: scatter the gradient with crfconv_scatter_add_rows
         lin::DgradArgs a{dY, H, bn, W, dX1, C1, acc1, dX2, C2, acc2, M, Cout};
-        int rc = lin::dispatch_bn(Ktot, [&](auto bnv) {
+        int rc = CRF_OK;
+        if (!(lin::use_fast(M) && lin::try_dgrad2(a, precision, st, &rc)))
+        rc = lin::dispatch_bn(Ktot, [&](auto bnv) {
             constexpr int BN = decltype(bnv)::value;
             dim3 grid((unsigned)ceil_div(M, lin::BM), (unsigned)ceil_div(Ktot, BN));
-            if (precision == 0) lin::dgrad_kernel<BN, true><<<grid, lin::kThreads, 0, st>>>(a);
+            if (gprec == 0) lin::dgrad_kernel<BN, true><<<grid, lin::kThreads, 0, st>>>(a);
             else lin::dgrad_kernel<BN, false><<<grid, lin::kThreads, 0, st>>>(a);
             CRF_LAUNCH_CHECK();
             return CRF_OK;
@@ -647,12 +645,16 @@ int crfconv_linear_bwd(const float* dY, const float* H, const float* act_ref, co
     }
     if (dW) {
         lin::WgradArgs a{dY, H, bn, X1, C1, scale1, shift1, slope1, idx1, rows_dst, rows_src, X2, C2, dW, dbias, M, Cout, 0};
+        if (lin::use_fast(M)) {
+            int rc2 = CRF_OK;
+            if (lin::try_wgrad2(a, precision, st, &rc2)) return rc2;
+        }
         const int ty = (int)ceil_div(Cout, 64), tz = (int)ceil_div(Ktot, 64);
         int64_t splits = std::max<int64_t>(1, std::min<int64_t>(ceil_div(M, 256), (int64_t)(2 * kNumSMs) / (ty * tz) + 1));
         a.rows_per_cta = ceil_div(ceil_div(M, splits), lin::WR) * lin::WR;
         splits = ceil_div(M, a.rows_per_cta);
         dim3 grid((unsigned)splits, (unsigned)ty, (unsigned)tz);
-        if (precision == 0) lin::wgrad_kernel<true><<<grid, lin::kThreads, 0, st>>>(a);
+        if (gprec == 0) lin::wgrad_kernel<true><<<grid, lin::kThreads, 0, st>>>(a);
         else lin::wgrad_kernel<false><<<grid, lin::kThreads, 0, st>>>(a);
         CRF_LAUNCH_CHECK();
     }

@@ -13,6 +13,54 @@ from . import _lib
 PRECISION = int(os.environ.get("CRFCONV_PRECISION", "0"))
 
 
+COUNTERS = {"launches": 0}       # number of crfconv_b200 kernels launched (bench.py's gpu_launches)
+_PROFILE = None                   # when a dict: name -> list of (start_event, end_event, algorithmic_bytes)
+
+
+def _nbytes(*tensors):
+    return sum(t.numel() * t.element_size() for t in tensors if t is not None)
+
+
+class _call:
+    """Counts kernel launches and, in profiling mode, brackets the C-ABI call with CUDA events on the launching stream."""
+
+    def __init__(self, name, kernels, nbytes):
+        self.name, self.kernels, self.nbytes = name, kernels, nbytes
+
+    def __enter__(self):
+        COUNTERS["launches"] += self.kernels
+        if _PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _PROFILE is not None:
+            self.e1.record()
+            _PROFILE.setdefault(self.name, []).append((self.e0, self.e1, self.nbytes))
+        return False
+
+
+def profile_calls(fn, repeats=3):
+    """Runs fn() `repeats` times with per-call CUDA-event timing; returns {kernel-name: {ms, calls, bytes}} per fn() call."""
+    global _PROFILE
+    fn()
+    torch.cuda.synchronize()
+    _PROFILE = {}
+    try:
+        for _ in range(repeats):
+            fn()
+        torch.cuda.synchronize()
+        out = {}
+        for name, recs in _PROFILE.items():
+            out[name] = {"ms": sum(a.elapsed_time(b) for a, b, _ in recs) / repeats, "calls": len(recs) / repeats,
+                         "bytes": sum(n for _, _, n in recs) / repeats}
+        return out
+    finally:
+        _PROFILE = None
+
+
 def _p(t):
     return None if t is None else t.data_ptr()
 
@@ -34,9 +82,9 @@ class BN:
     """Per-BatchNorm scratch: f64 Σ/Σ² accumulators, fused affine (scale, shift), saved mean/invstd, backward k1/k2."""
     __slots__ = ("C", "stats", "scale", "shift", "mean", "invstd", "k1", "k2", "count", "training")
 
-    def __init__(self, C, device):
+    def __init__(self, C, device, stats=None):
         self.C = C
-        self.stats = torch.zeros(2 * C, dtype=torch.float64, device=device)
+        self.stats = stats if stats is not None else torch.zeros(2 * C, dtype=torch.float64, device=device)   # must be zeroed
         buf = torch.empty(6, C, dtype=torch.float32, device=device)
         self.scale, self.shift, self.mean, self.invstd, self.k1, self.k2 = buf.unbind(0)
         self.count = 0
@@ -53,15 +101,38 @@ def linear_fwd(X1, W, *, scale1=None, shift1=None, slope1=1.0, idx1=None, rows_d
     Cout = W.shape[0]
     assert W.shape[1] == C1 + C2 and W.is_contiguous()
     Y = out if out is not None else torch.empty((M, Cout), dtype=torch.float32, device=X1.device)
-    rc = L.crfconv_linear_fwd(_p(X1), C1, _p(scale1), _p(shift1), float(slope1), _p(idx1), int(rows_dst), int(rows_src), _p(X2), C2,
-                              _p(W), _p(bias), _p(Y), _p(stats), int(M), int(Cout), PRECISION, _lib.stream_ptr())
+    nb = M * (C1 + C2 + Cout) * 4 + (M * 8 if idx1 is not None else 0)
+    with _call(f"linear_fwd[{C1 + C2}->{Cout}]", 1, nb):
+        rc = _linear_fwd_call(L, X1, C1, scale1, shift1, slope1, idx1, rows_dst, rows_src, X2, C2, W, bias, Y, stats, M, Cout)
     _lib.check(rc, "linear_fwd")
     return Y
+
+
+def _linear_fwd_call(L, X1, C1, scale1, shift1, slope1, idx1, rows_dst, rows_src, X2, C2, W, bias, Y, stats, M, Cout):
+    return L.crfconv_linear_fwd(_p(X1), C1, _p(scale1), _p(shift1), float(slope1), _p(idx1), int(rows_dst), int(rows_src), _p(X2), C2,
+                              _p(W), _p(bias), _p(Y), _p(stats), int(M), int(Cout), PRECISION, _lib.stream_ptr())
+
+
+class Flat:
+    """One zero-filled allocation carved into views (a single memset instead of one fill kernel per small tensor)."""
+
+    def __init__(self, numel, dtype, device):
+        self.buf = torch.zeros(int(numel), dtype=dtype, device=device)
+        self.off = 0
+
+    def take(self, *shape):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        v = self.buf[self.off:self.off + n].view(*shape)
+        self.off += n
+        return v
 
 
 def bn_finalize_fwd(bn: BN, count, gamma, beta, eps, momentum, training, running_mean, running_var):
     L = _lib.lib()
     bn.count, bn.training = int(count), bool(training)
+    COUNTERS["launches"] += 1
     rc = L.crfconv_bn_finalize_fwd(_p(bn.stats), int(count), _p(gamma), _p(beta), float(eps), float(momentum), int(bool(training)),
                                    _p(running_mean), _p(running_var), _p(bn.scale), _p(bn.shift), _p(bn.mean), _p(bn.invstd),
                                    bn.C, _lib.stream_ptr())
@@ -71,18 +142,23 @@ def bn_finalize_fwd(bn: BN, count, gamma, beta, eps, momentum, training, running
 def bn_act_fwd(H, bn: BN, slope, R=None, out=None):
     L = _lib.lib()
     Y = out if out is not None else torch.empty_like(H)
-    rc = L.crfconv_bn_act_fwd(_p(H), _p(bn.scale), _p(bn.shift), _p(R), float(slope), _p(Y), H.shape[0], H.shape[1], _lib.stream_ptr())
+    with _call(f"bn_act_fwd[{H.shape[1]}]", 1, _nbytes(H, R, Y)):
+        rc = L.crfconv_bn_act_fwd(_p(H), _p(bn.scale), _p(bn.shift), _p(R), float(slope), _p(Y), H.shape[0], H.shape[1], _lib.stream_ptr())
     _lib.check(rc, "bn_act_fwd")
     return Y
 
 
-def bn_backward_prepare(dY, H, bn: BN, slope, dgamma, dbeta, act_ref=None):
-    """Reduces Σ dV and Σ dV·Ĥ, accumulates dγ / dβ and fills bn.k1 / bn.k2 for the on-the-fly dH transform."""
+def bn_backward_prepare(dY, H, bn: BN, slope, dgamma, dbeta, act_ref=None, sums=None):
+    """Reduces Σ dV and Σ dV·Ĥ, accumulates dγ / dβ and fills bn.k1 / bn.k2 for the on-the-fly dH transform.
+    `sums` (optional) = zero-initialised f64 scratch of 2·C entries."""
     L = _lib.lib()
-    sums = torch.zeros(2 * bn.C, dtype=torch.float64, device=H.device)
-    rc = L.crfconv_bn_bwd_reduce(_p(dY), _p(H), _p(act_ref), _p(bn.scale), _p(bn.shift), _p(bn.mean), _p(bn.invstd), float(slope),
-                                 _p(sums), H.shape[0], bn.C, _lib.stream_ptr())
+    if sums is None:
+        sums = torch.zeros(2 * bn.C, dtype=torch.float64, device=H.device)
+    with _call(f"bn_bwd_reduce[{bn.C}]", 1, _nbytes(dY, H, act_ref)):
+        rc = L.crfconv_bn_bwd_reduce(_p(dY), _p(H), _p(act_ref), _p(bn.scale), _p(bn.shift), _p(bn.mean), _p(bn.invstd), float(slope),
+                                     _p(sums), H.shape[0], bn.C, _lib.stream_ptr())
     _lib.check(rc, "bn_bwd_reduce")
+    COUNTERS["launches"] += 1
     rc = L.crfconv_bn_finalize_bwd(_p(sums), bn.count, _p(bn.k1), _p(bn.k2), _p(dgamma), _p(dbeta), bn.C, _lib.stream_ptr())
     _lib.check(rc, "bn_finalize_bwd")
     if not bn.training:      # eval-mode BN is a fixed affine map: dH = scale·dV
@@ -98,13 +174,23 @@ def linear_bwd(dY, H, bn, slope, X1, W, *, scale1=None, shift1=None, slope1=1.0,
     C2 = X2.shape[1] if X2 is not None else 0
     M, Cout = dY.shape
     b = bn
-    rc = L.crfconv_linear_bwd(_p(dY), _p(H), _p(act_ref), _p(b.scale) if b else None, _p(b.shift) if b else None,
+    nb = _nbytes(dY, H if b else None, act_ref, X1 if dW is not None else None, X2 if dW is not None else None, dX1, dX2,
+                 dX1 if acc1 else None, dX2 if acc2 else None)
+    with _call(f"linear_bwd[{Cout}<-{C1 + C2}]" + ("" if dW is not None else ":dgrad") + ("" if (dX1 is not None or dX2 is not None) else ":wgrad"),
+               int(dW is not None) + int(dX1 is not None or dX2 is not None), nb):
+        rc = _linear_bwd_call(L, dY, H, act_ref, b, slope, X1, C1, scale1, shift1, slope1, idx1, rows_dst, rows_src, X2, C2, W, dX1, acc1,
+                              dX2, acc2, dW, dbias, M, Cout)
+    _lib.check(rc, "linear_bwd")
+
+
+def _linear_bwd_call(L, dY, H, act_ref, b, slope, X1, C1, scale1, shift1, slope1, idx1, rows_dst, rows_src, X2, C2, W, dX1, acc1, dX2, acc2,
+                     dW, dbias, M, Cout):
+    return L.crfconv_linear_bwd(_p(dY), _p(H), _p(act_ref), _p(b.scale) if b else None, _p(b.shift) if b else None,
                               _p(b.mean) if b else None, _p(b.invstd) if b else None, _p(b.k1) if b else None,
                               _p(b.k2) if b else None, float(slope),
                               _p(X1), C1, _p(scale1), _p(shift1), float(slope1), _p(idx1), int(rows_dst), int(rows_src), _p(X2), C2,
                               _p(W), _p(dX1), int(acc1), _p(dX2), int(acc2), _p(dW), _p(dbias), int(M), int(Cout), PRECISION,
                               _lib.stream_ptr())
-    _lib.check(rc, "linear_bwd")
 
 
 # ------------------------------------------------------------------------------------------ CRF mean-field
@@ -113,6 +199,7 @@ def crf_compat_fwd(c):
     F = c.shape[0]
     Cm, Minv = torch.empty_like(c), torch.empty_like(c)
     scratch = torch.empty(3 * F * F, dtype=torch.float64, device=c.device)
+    COUNTERS["launches"] += 1
     _lib.check(L.crfconv_crf_compat_fwd(_p(c), _p(Cm), _p(Minv), _p(scratch), F, _lib.stream_ptr()), "crf_compat_fwd")
     return Cm, Minv
 
@@ -121,6 +208,7 @@ def crf_compat_bwd(c, Minv, GC, GM, Gc):
     L = _lib.lib()
     F = c.shape[0]
     scratch = torch.empty(3 * F * F, dtype=torch.float64, device=c.device)
+    COUNTERS["launches"] += 1
     _lib.check(L.crfconv_crf_compat_bwd(_p(c), _p(Minv), _p(GC), _p(GM), _p(Gc), _p(scratch), F, _lib.stream_ptr()), "crf_compat_bwd")
 
 
@@ -128,26 +216,32 @@ def crf_upsample_fwd(Hu, bn: BN, up_idx, B, N, Nc):
     L = _lib.lib()
     F = Hu.shape[1]
     z = torch.empty((B * N, F), dtype=torch.float32, device=Hu.device)
-    _lib.check(L.crfconv_crf_upsample_fwd(_p(Hu), _p(bn.scale), _p(bn.shift), _p(up_idx), _p(z), B, N, Nc, F, _lib.stream_ptr()),
-               "crf_upsample_fwd")
+    with _call(f"crf_upsample_fwd[{F}]", 1, _nbytes(Hu, up_idx, z)):
+        rc = L.crfconv_crf_upsample_fwd(_p(Hu), _p(bn.scale), _p(bn.shift), _p(up_idx), _p(z), B, N, Nc, F, _lib.stream_ptr())
+    _lib.check(rc, "crf_upsample_fwd")
     return z
 
 
 def crf_upsample_bwd(Gz, G0, up_idx, Gu, B, N, Nc):
     L = _lib.lib()
-    _lib.check(L.crfconv_crf_upsample_bwd(_p(Gz), _p(G0), _p(up_idx), _p(Gu), B, N, Nc, Gz.shape[1], _lib.stream_ptr()),
-               "crf_upsample_bwd")
+    with _call(f"crf_upsample_bwd[{Gz.shape[1]}]", 1, _nbytes(Gz, G0, up_idx, Gu)):
+        rc = L.crfconv_crf_upsample_bwd(_p(Gz), _p(G0), _p(up_idx), _p(Gu), B, N, Nc, Gz.shape[1], _lib.stream_ptr())
+    _lib.check(rc, "crf_upsample_bwd")
 
 
 def crf_step_fwd(Hy, scale_y, z, xprev, nbr, Cm, Minv, B, N, K):
     L = _lib.lib()
     xout = torch.empty_like(z)
-    _lib.check(L.crfconv_crf_step_fwd(_p(Hy), _p(scale_y), _p(z), _p(xprev), _p(nbr), _p(Cm), _p(Minv), _p(xout), B, N, K, z.shape[1],
-                                      _lib.stream_ptr()), "crf_step_fwd")
+    with _call(f"crf_step_fwd[{z.shape[1]}]", 1, _nbytes(Hy, z, xprev, nbr, xout)):
+        rc = L.crfconv_crf_step_fwd(_p(Hy), _p(scale_y), _p(z), _p(xprev), _p(nbr), _p(Cm), _p(Minv), _p(xout), B, N, K, z.shape[1],
+                                    _lib.stream_ptr())
+    _lib.check(rc, "crf_step_fwd")
     return xout
 
 
-def crf_step_bwd(Hy, scale_y, z, xprev, nbr, Cm, Minv, g, Gz, gprev, Gy, m_out, v_out, h_out, B, N, K):
+def crf_step_bwd(Hy, scale_y, z, xprev, nbr, Cm, Minv, g, Gz, gprev, Gy, m_out, v_out, h_out, gz_acc, B, N, K):
     L = _lib.lib()
-    _lib.check(L.crfconv_crf_step_bwd(_p(Hy), _p(scale_y), _p(z), _p(xprev), _p(nbr), _p(Cm), _p(Minv), _p(g), _p(Gz), _p(gprev), _p(Gy),
-                                      _p(m_out), _p(v_out), _p(h_out), B, N, K, z.shape[1], _lib.stream_ptr()), "crf_step_bwd")
+    with _call(f"crf_step_bwd[{z.shape[1]}]", 1, _nbytes(Hy, z, xprev, nbr, g, Gz, Gz, gprev, Gy, m_out, v_out, h_out)):
+        rc = L.crfconv_crf_step_bwd(_p(Hy), _p(scale_y), _p(z), _p(xprev), _p(nbr), _p(Cm), _p(Minv), _p(g), _p(Gz), _p(gprev), _p(Gy),
+                                    _p(m_out), _p(v_out), _p(h_out), int(gz_acc), B, N, K, z.shape[1], _lib.stream_ptr())
+    _lib.check(rc, "crf_step_bwd")

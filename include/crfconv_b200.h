@@ -70,6 +70,10 @@ int crfconv_grid_subsample_host(const float* points, int64_t N, const float* fea
  * models/continuous_crf_conv_big.py:20-29 and models/point_conv_big.py:20-23,65-70.  All pointers are device
  * pointers, tensors are row-major [rows, channels] f32.  precision: 0 = 3xTF32 (fp32-grade), 1 = one TF32 pass.  */
 
+/* Kernel selection knob for tests / experiments: -1 = default rule (persistent bf16x3 kernels for large row counts,
+ * generic 3xTF32 kernels otherwise), 0 = generic only, 1 = fast whenever the shape allows.  Returns the previous mode. */
+int crfconv_set_fast_path(int mode);
+
 /* Y[M,Cout] = [ lrelu(X1*scale1 + shift1, slope1) | X2 ] · Wᵀ (+ bias).  scale1 == NULL ⇒ X1 is used as is.
  * idx1 != NULL ⇒ X1 rows are gathered: source row of output row m is (m / rows_dst) * rows_src + idx1[m]
  * (point_conv_big.py:97-101).  stats != NULL ⇒ stats[0:Cout] += Σ_rows Y, stats[Cout:2Cout] += Σ_rows Y² (f64). */
@@ -125,11 +129,11 @@ int crfconv_crf_upsample_bwd(const float* Gz, const float* G0, const int64_t* up
 /* xout = (z + (S·xprev)·Cm)·Minv, S = softmax_k(−‖y_i − y_j‖²), y = Hy*scale_y (+shift, which cancels). */
 int crfconv_crf_step_fwd(const float* Hy, const float* scale_y, const float* z, const float* xprev, const int64_t* neighbor_idx,
                          const float* Cm, const float* Minv, float* xout, int64_t B, int64_t N, int K, int F, void* stream);
-/* Backward of one step given g = dL/dxout: Gz += g·Minvᵀ (=h); gprev += Σ_i s_ij·(h_i·Cmᵀ) (zero-initialised by caller);
+/* Backward of one step given g = dL/dxout: Gz = (gz_acc ? Gz : 0) + g·Minvᵀ (=h); gprev += Σ_i s_ij·(h_i·Cmᵀ) (zero-initialised by caller);
  * Gy += gradient through the distances wrt y; m_out / v_out / h_out rows feed GC = mᵀh and GM = vᵀg. */
 int crfconv_crf_step_bwd(const float* Hy, const float* scale_y, const float* z, const float* xprev, const int64_t* neighbor_idx,
                          const float* Cm, const float* Minv, const float* g, float* Gz, float* gprev, float* Gy, float* m_out,
-                         float* v_out, float* h_out, int64_t B, int64_t N, int K, int F, void* stream);
+                         float* v_out, float* h_out, int gz_acc, int64_t B, int64_t N, int K, int F, void* stream);
 
 #ifdef __cplusplus
 }

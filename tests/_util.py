@@ -14,3 +14,10 @@ def rel_err(a, b, floor=0.0):
 def grad_floor(golden, tag, frac=1e-3):
     """frac × the largest parameter-gradient magnitude of the fixture `tag`."""
     return frac * max(float(np.abs(v).max()) for k, v in golden.items() if k.startswith(tag + ".gparam."))
+
+
+def rel_l2(a, b, floor=0.0):
+    """||a-b||_2 / max(||b||_2, floor·sqrt(n)) — robust to the handful of LeakyReLU kink flips that any two finite-precision
+    implementations of a 10^7-activation layer disagree on (a flipped branch changes one gradient entry by O(1))."""
+    a, b = np.asarray(a, dtype=np.float64).ravel(), np.asarray(b, dtype=np.float64).ravel()
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), floor * np.sqrt(b.size), 1e-30))

@@ -1,0 +1,123 @@
+"""GPU unit parity of the Linear/BatchNorm C-ABI ops against an fp64 PyTorch statement of the same formulas, for both
+kernel generations (generic 3xTF32 and persistent bf16x3) and every shape the CRF layer and the ResNet blocks use.
+Tolerance relative to the tensor's max: forward 2e-5 (both generations contract the forward in 3xTF32), backward 2e-5 (generic,
+3xTF32) / 2e-4 (fast, bf16x3) — well inside the 1e-3 layer budget.  The backward reference is built from the product's own
+forward output H, so that a LeakyReLU branch decided differently at |pre-activation| ~ 1e-6 cannot masquerade as a backward error."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from crfconv_b200 import ops as o
+    return o
+
+
+def lrelu(v, s):
+    return torch.where(v > 0, v, v * s)
+
+
+def rel(a, b):
+    return float((a.double() - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+SHAPES = [  # (M, C1, C2, Cout)
+    (9000, 128, 0, 16), (9000, 64, 0, 16), (9000, 16, 0, 16), (9000, 16, 0, 64), (9000, 64, 64, 64), (8200, 8, 0, 8),
+    (8200, 32, 32, 32), (8200, 8, 0, 32), (8200, 64, 0, 8), (12345, 32, 0, 8), (8200, 64, 0, 64), (8200, 128, 0, 64), (8200, 6, 0, 32),
+]
+
+
+@pytest.mark.parametrize("fast", [0, 1])
+@pytest.mark.parametrize("M,C1,C2,Cout", SHAPES)
+def test_linear_fwd_and_bwd(ops, fast, M, C1, C2, Cout):
+    from crfconv_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(M + C1 + Cout)
+    rn = lambda *s: torch.randn(*s, generator=g, device="cuda")   # noqa: E731
+    X1, X2 = rn(M, C1), (rn(M, C2) if C2 else None)
+    W = rn(Cout, C1 + C2) / (C1 + C2) ** 0.5
+    sc1, sh1 = 1 + 0.2 * rn(C1), 0.2 * rn(C1)
+    gamma, beta = 1 + 0.2 * rn(Cout), 0.2 * rn(Cout)
+    dY = rn(M, Cout)
+    tol = 2e-4 if fast else 2e-5
+    ftol = 2e-5
+    prev = L.crfconv_set_fast_path(fast)
+    try:
+        # ---------------- forward: H = [lrelu(X1*sc+sh, .1) | X2] Wᵀ with Σ/Σ² epilogue
+        bn = ops.BN(Cout, X1.device)
+        H = ops.linear_fwd(X1, W, scale1=sc1, shift1=sh1, slope1=0.1, X2=X2, stats=bn.stats)
+        A = lrelu(X1.double() * sc1.double() + sh1.double(), 0.1)
+        if C2:
+            A = torch.cat([A, X2.double()], 1)
+        Href = A @ W.double().t()
+        assert rel(H, Href) < ftol
+        assert rel(bn.stats[:Cout], Href.sum(0)) < 1e-4 and rel(bn.stats[Cout:], (Href ** 2).sum(0)) < 1e-4
+        ops.bn_finalize_fwd(bn, M, gamma, beta, 1e-5, 0.1, True, None, None)
+        mu, var = Href.mean(0), Href.var(0, unbiased=False)
+        assert rel(bn.mean, mu) < 1e-4 and rel(bn.invstd, (var + 1e-5).rsqrt()) < 1e-4
+        # ---------------- backward through lrelu(BN(H), .1), referenced to the product's own H
+        Href = H.double()
+        mu, var = Href.mean(0), Href.var(0, unbiased=False)
+        Hh = (Href - mu) * (var + 1e-5).rsqrt()
+        V = Hh * gamma.double() + beta.double()
+        dV = torch.where(V > 0, dY.double(), dY.double() * 0.1)
+        dgam, dbet = torch.zeros(Cout, device="cuda"), torch.zeros(Cout, device="cuda")
+        ops.bn_backward_prepare(dY, H, bn, 0.1, dgam, dbet)
+        assert rel(dbet, dV.sum(0)) < 1e-4 and rel(dgam, (dV * Hh).sum(0)) < 1e-4
+        dH = gamma.double() * (var + 1e-5).rsqrt() * (dV - dV.mean(0) - Hh * (dV * Hh).mean(0))
+        dX1, dX2 = torch.empty_like(X1), (torch.full_like(X2, 1.0) if C2 else None)
+        dW = torch.zeros_like(W)
+        ops.linear_bwd(dY, H, bn, 0.1, X1, W, scale1=sc1, shift1=sh1, slope1=0.1, X2=X2, dX1=dX1, dX2=dX2, acc2=True, dW=dW)
+        dA = dH @ W.double()
+        assert rel(dX1, dA[:, :C1]) < tol
+        if C2:
+            assert rel(dX2, dA[:, C1:] + 1.0) < tol          # acc2: accumulated onto the ones
+        assert rel(dW, dH.t() @ A) < tol
+        # ---------------- plain (no BN) wgrad-only and dgrad-only calls, as used for GC = mᵀh
+        if C2 == 0:
+            dW2 = torch.zeros_like(W)
+            ops.linear_bwd(dY, None, None, 1.0, X1, W, dW=dW2)
+            assert rel(dW2, dY.double().t() @ X1.double()) < tol
+            dX = torch.empty_like(X1)
+            ops.linear_bwd(dY, None, None, 1.0, X1, W, dX1=dX)
+            assert rel(dX, dY.double() @ W.double()) < tol
+    finally:
+        L.crfconv_set_fast_path(prev)
+
+
+@pytest.mark.parametrize("fast", [0, 1])
+def test_residual_activation_reference(ops, fast):
+    """act_ref path: the LeakyReLU branch is taken from a saved output (ResNetBBlock's lrelu(BN(h)+residual), point_conv_big.py:88)."""
+    from crfconv_b200 import _lib
+    L = _lib.lib()
+    M, C1, Cout = 8300, 16, 64
+    g = torch.Generator(device="cuda").manual_seed(7)
+    rn = lambda *s: torch.randn(*s, generator=g, device="cuda")   # noqa: E731
+    X1, W, R, dY = rn(M, C1), rn(Cout, C1) / 4, rn(M, Cout), rn(M, Cout)
+    gamma, beta = 1 + 0.2 * rn(Cout), 0.2 * rn(Cout)
+    prev = L.crfconv_set_fast_path(fast)
+    try:
+        bn = ops.BN(Cout, X1.device)
+        H = ops.linear_fwd(X1, W, stats=bn.stats)
+        ops.bn_finalize_fwd(bn, M, gamma, beta, 1e-5, 0.1, True, None, None)
+        out = ops.bn_act_fwd(H, bn, 0.01, R=R)
+        Href = X1.double() @ W.double().t()
+        mu, var = Href.mean(0), Href.var(0, unbiased=False)
+        Hh = (Href - mu) * (var + 1e-5).rsqrt()
+        oref = lrelu(Hh * gamma.double() + beta.double() + R.double(), 0.01)
+        assert rel(out, oref) < 2e-5
+        Href = H.double()
+        mu, var = Href.mean(0), Href.var(0, unbiased=False)
+        Hh = (Href - mu) * (var + 1e-5).rsqrt()
+        dV = torch.where(out.double() > 0, dY.double(), dY.double() * 0.01)
+        dgam, dbet = torch.zeros(Cout, device="cuda"), torch.zeros(Cout, device="cuda")
+        ops.bn_backward_prepare(dY, H, bn, 0.01, dgam, dbet, act_ref=out)
+        dH = gamma.double() * (var + 1e-5).rsqrt() * (dV - dV.mean(0) - Hh * (dV * Hh).mean(0))
+        dX, dW = torch.empty_like(X1), torch.zeros_like(W)
+        ops.linear_bwd(dY, H, bn, 0.01, X1, W, dX1=dX, dW=dW, act_ref=out)
+        tol = 2e-4 if fast else 2e-5
+        assert rel(dX, dH @ W.double()) < tol and rel(dW, dH.t() @ X1.double()) < tol
+    finally:
+        L.crfconv_set_fast_path(prev)
