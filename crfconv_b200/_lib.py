@@ -31,6 +31,14 @@ SIGNATURES = {
     "crfconv_linear_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32,
                                   _vp, _int, _vp, _vp, _f32, _vp, _i64, _i64, _vp, _int, _vp, _vp, _int, _vp, _int, _vp, _vp,
                                   _i64, _int, _int, _vp]),
+    "crfconv_relpos": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
+    "crfconv_pointconv_aggregate_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _vp]),
+    "crfconv_pointconv_aggregate_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _vp]),
+    "crfconv_gather_max_fwd": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _vp]),
+    "crfconv_gather_max_bwd": (_int, [_vp, _vp, _vp, _i64, _int, _vp]),
+    "crfconv_lrelu_bwd": (_int, [_vp, _vp, _f32, _vp, _i64, _vp]),
+    "crfconv_add_inplace": (_int, [_vp, _vp, _i64, _vp]),
+    "crfconv_scatter_add_rows": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
     "crfconv_crf_compat_fwd": (_int, [_vp, _vp, _vp, _vp, _int, _vp]),
     "crfconv_crf_compat_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "crfconv_crf_upsample_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),

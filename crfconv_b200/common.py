@@ -28,7 +28,7 @@ class FastBatchNorm1d(nn.Module):
             raise ValueError("Non supported number of dimensions {}".format(x.dim()))
         bn = self.batch_norm
         eye = torch.eye(bn.num_features, device=x.device, dtype=torch.float32)
-        return _LinearBNAct.apply(x, eye, None, bn.weight, bn.bias, bn, self.training or not bn.track_running_stats, 1.0)
+        return _LinearBNAct.apply(x, None, None, None, eye, None, bn.weight, bn.bias, bn, self.training or not bn.track_running_stats, 1.0)
 
 
 def _slope_of(activation):
@@ -56,59 +56,88 @@ def bn_forward_state(C, device, count, bn_module, training, stats=None):
 
 
 class _LinearBNAct(torch.autograd.Function):
-    """y = lrelu( BN( x·Wᵀ ) , slope )  or, without BN,  y = lrelu( x·Wᵀ + b , slope )."""
+    """y = lrelu( BN( [x1[idx] | x2]·Wᵀ ) (+ R) , slope )   or, without BN,   y = lrelu( [x1 | x2]·Wᵀ + b , slope ).
+
+    x1 [B,N1,C1] (rows gathered through idx [B,N,1] when given), x2 [B,N,C2] or None (the concat is never materialised),
+    R [B,N,Cout] or None (residual added before the activation, point_conv_big.py:88)."""
 
     @staticmethod
-    def forward(ctx, x, W, bias, gamma, beta, bn_module, training, slope):
-        if not x.is_cuda:
+    def forward(ctx, x1, x2, idx, R, W, bias, gamma, beta, bn_module, training, slope):
+        if not x1.is_cuda:
             raise RuntimeError("crfconv_b200 layers run on CUDA tensors only (no CPU fallback)")
-        x2 = ops.as2d(x)
+        a1 = ops.as2d(x1)
+        a2 = ops.as2d(x2) if x2 is not None else None
+        r2 = ops.as2d(R) if R is not None else None
         Wc = W.detach().contiguous().float()
-        M, Cout = x2.shape[0], Wc.shape[0]
+        Cout = Wc.shape[0]
+        gidx, rows_dst, rows_src = None, 0, 0
+        lead = x1.shape[:-1]
+        if idx is not None:
+            gidx = idx.detach().reshape(idx.shape[0], -1).contiguous().to(torch.int64)
+            rows_dst, rows_src = gidx.shape[1], x1.shape[1]
+            lead = (x1.shape[0], rows_dst)
+        M = gidx.numel() if gidx is not None else a1.shape[0]
         if bn_module is not None:
-            st, fin = bn_forward_state(Cout, x.device, M, bn_module, training)
-            H = ops.linear_fwd(x2, Wc, stats=st.stats if training else None)
+            st, fin = bn_forward_state(Cout, x1.device, M, bn_module, training)
+            H = ops.linear_fwd(a1, Wc, idx1=gidx, rows_dst=rows_dst, rows_src=rows_src, X2=a2, stats=st.stats if training else None, M=M)
             fin()
-            Y = ops.bn_act_fwd(H, st, slope)
+            Y = ops.bn_act_fwd(H, st, slope, R=r2)
         else:
             st = None
-            H = ops.linear_fwd(x2, Wc, bias=bias.detach().contiguous().float() if bias is not None else None)
-            if slope == 1.0:
+            H = ops.linear_fwd(a1, Wc, idx1=gidx, rows_dst=rows_dst, rows_src=rows_src, X2=a2,
+                               bias=bias.detach().contiguous().float() if bias is not None else None, M=M)
+            if slope == 1.0 and r2 is None:
                 Y = H
             else:
-                st = ops.BN(Cout, x.device)            # identity affine, used only for the activation kernel
+                st = ops.BN(Cout, x1.device)           # identity affine, used only for the (residual +) activation kernel
                 st.scale.fill_(1.0); st.shift.zero_(); st.mean.zero_(); st.invstd.fill_(1.0)
-                Y = ops.bn_act_fwd(H, st, slope)
+                st.count, st.training = M, False
+                Y = ops.bn_act_fwd(H, st, slope, R=r2)
         ctx.has_bn, ctx.slope, ctx.st = bn_module is not None, slope, st
-        ctx.has_bias = bias is not None
-        ctx.x_shape = x.shape
-        ctx.save_for_backward(x2, Wc, H)
-        return Y.view(*x.shape[:-1], Cout)
+        ctx.has_bias, ctx.has_R = bias is not None, R is not None
+        ctx.shapes = (x1.shape, x2.shape if x2 is not None else None, R.shape if R is not None else None)
+        ctx.gather = (rows_dst, rows_src)
+        ctx.save_for_backward(a1, a2, gidx, Wc, H, Y if (R is not None or st is not None and not ctx.has_bn) else None)
+        return Y.view(*lead, Cout)
 
     @staticmethod
     def backward(ctx, gy):
-        x2, Wc, H = ctx.saved_tensors
+        a1, a2, gidx, Wc, H, Y = ctx.saved_tensors
         g2 = ops.as2d(gy)
-        Cout, Cin = Wc.shape
-        need_x = ctx.needs_input_grad[0]
-        dx = torch.empty_like(x2) if need_x else None
+        Cout = Wc.shape[0]
+        dev = g2.device
+        nig = ctx.needs_input_grad
+        rows_dst, rows_src = ctx.gather
+        M = g2.shape[0]
+        dR = None
+        slope = ctx.slope
+        if ctx.has_R:                          # out = lrelu(V + R): dS feeds both the residual and the BN branch (slope 1)
+            g2 = ops.lrelu_bwd(g2, Y, slope)
+            dR, slope = g2, 1.0
+        dX1 = torch.empty((M, a1.shape[1]), dtype=torch.float32, device=dev) if nig[0] else None
+        dX2 = torch.empty_like(a2) if (a2 is not None and nig[1]) else None
         dW = torch.zeros_like(Wc)
         dgamma = dbeta = dbias = None
+        st = ctx.st
         if ctx.has_bn:
-            dgamma = torch.zeros(Cout, device=g2.device)
-            dbeta = torch.zeros(Cout, device=g2.device)
-            ops.bn_backward_prepare(g2, H, ctx.st, ctx.slope, dgamma, dbeta)
-            ops.linear_bwd(g2, H, ctx.st, ctx.slope, x2, Wc, dX1=dx, dW=dW)
+            dgamma, dbeta = torch.zeros(Cout, device=dev), torch.zeros(Cout, device=dev)
+            ops.bn_backward_prepare(g2, H, st, slope, dgamma, dbeta)
         else:
-            dbias = torch.zeros(Cout, device=g2.device) if ctx.has_bias else None
-            if ctx.slope != 1.0:       # activation without BN: fixed affine (scale 1), k1 = k2 = 0
-                ctx.st.k1.zero_(); ctx.st.k2.zero_()
-                ops.linear_bwd(g2, H, ctx.st, ctx.slope, x2, Wc, dX1=dx, dW=dW, dbias=dbias)
+            dbias = torch.zeros(Cout, device=dev) if ctx.has_bias else None
+            if st is not None and slope != 1.0:
+                st.k1.zero_(); st.k2.zero_()   # activation without BN: fixed affine (scale 1)
             else:
-                ops.linear_bwd(g2, H, None, 1.0, x2, Wc, dX1=dx, dW=dW, dbias=dbias)
-        nig = ctx.needs_input_grad
-        return (dx.view(ctx.x_shape) if need_x else None), (dW if nig[1] else None), (dbias if nig[2] else None), \
-            (dgamma if nig[3] else None), (dbeta if nig[4] else None), None, None, None
+                st = None
+        ops.linear_bwd(g2, H, st, slope, a1, Wc, idx1=gidx, rows_dst=rows_dst, rows_src=rows_src, X2=a2, dX1=dX1, dX2=dX2, dW=dW,
+                       dbias=dbias)
+        s1, s2, sR = ctx.shapes
+        if dX1 is not None and gidx is not None:           # gradient wrt gathered rows → scatter onto the source rows
+            full = torch.zeros((s1[0] * s1[1], s1[2]), dtype=torch.float32, device=dev)
+            ops.scatter_add_rows(dX1, gidx, full, s1[0], rows_dst, rows_src)
+            dX1 = full
+        return (dX1.view(s1) if dX1 is not None else None, dX2.view(s2) if dX2 is not None else None, None,
+                dR.view(sR) if (dR is not None and nig[3]) else None, dW if nig[4] else None, dbias if nig[5] else None,
+                dgamma if nig[6] else None, dbeta if nig[7] else None, None, None, None)
 
 
 class MLP(nn.Module):
@@ -123,15 +152,21 @@ class MLP(nn.Module):
     def slope(self):
         return _slope_of(self.activation)
 
-    def forward(self, x, *args, **kwargs):
-        slope = self.slope
-        fused = slope if slope is not None else 1.0
+    def forward(self, x, *args, x2=None, gather_idx=None, residual=None, slope=None, **kwargs):
+        """x2: second input segment (the reference's torch.cat([x, x2], -1) without the copy); gather_idx: [B,N,1] row
+        gather applied to x (Upsampling.upsampling); residual / slope: fused `leaky_relu(mlp(x) + residual, slope)`."""
+        own = self.slope
+        fused = own if own is not None else 1.0
+        if residual is not None:
+            assert own == 1.0 and slope is not None, "a fused residual needs an activation-free MLP and an explicit slope"
+            fused = slope
         if self.bn is not None:
             bnm = self.bn.batch_norm
-            y = _LinearBNAct.apply(x, self.lin.weight, None, bnm.weight, bnm.bias, bnm, self.training or not bnm.track_running_stats, fused)
+            y = _LinearBNAct.apply(x, x2, gather_idx, residual, self.lin.weight, None, bnm.weight, bnm.bias, bnm,
+                                   self.training or not bnm.track_running_stats, fused)
         else:
-            y = _LinearBNAct.apply(x, self.lin.weight, self.lin.bias, None, None, None, False, fused)
-        if slope is None:
+            y = _LinearBNAct.apply(x, x2, gather_idx, residual, self.lin.weight, self.lin.bias, None, None, None, False, fused)
+        if own is None:
             y = self.activation(y)
         return y
 

@@ -629,7 +629,7 @@ int crfconv_linear_bwd(const float* dY, const float* H, const float* act_ref, co
     const int Ktot = C1 + C2;
     const int gprec = precision == 2 ? 1 : precision;    // precision seen by the generic (TF32) kernels
     if (dX1 || dX2) {
-        if (idx1 && dX1) return CRF_ERR_UNSUPPORTED;   // gathered inputs: scatter the gradient with crfconv_scatter_add_rows
+        // with idx1, dX1 is the gradient wrt the GATHERED rows [M, C1]; scatter it with crfconv_scatter_add_rows
         lin::DgradArgs a{dY, H, bn, W, dX1, C1, acc1, dX2, C2, acc2, M, Cout};
         int rc = CRF_OK;
         if (!(lin::use_fast(M) && lin::try_dgrad2(a, precision, st, &rc)))

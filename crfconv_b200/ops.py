@@ -245,3 +245,78 @@ def crf_step_bwd(Hy, scale_y, z, xprev, nbr, Cm, Minv, g, Gz, gprev, Gy, m_out, 
         rc = L.crfconv_crf_step_bwd(_p(Hy), _p(scale_y), _p(z), _p(xprev), _p(nbr), _p(Cm), _p(Minv), _p(g), _p(Gz), _p(gprev), _p(Gy),
                                     _p(m_out), _p(v_out), _p(h_out), int(gz_acc), B, N, K, z.shape[1], _lib.stream_ptr())
     _lib.check(rc, "crf_step_bwd")
+
+
+# ------------------------------------------------------------------------- point-conv gather / aggregation
+def relpos(support, centres, idx):
+    """support [B,Ns,3], centres [B,Nq,3], idx [B,Nq,K] → rel [B·Nq·K, 3]."""
+    L = _lib.lib()
+    B, Ns, _ = support.shape
+    Nq, K = idx.shape[1], idx.shape[2]
+    rel = torch.empty((B * Nq * K, 3), dtype=torch.float32, device=support.device)
+    with _call("relpos", 1, _nbytes(support, centres, idx, rel)):
+        rc = L.crfconv_relpos(_p(support), _p(centres), _p(idx), _p(rel), B, Ns, Nq, K, _lib.stream_ptr())
+    _lib.check(rc, "relpos")
+    return rel
+
+
+def pointconv_aggregate_fwd(x, H2, bn: BN, idx, B, Ns, Nq, K):
+    L = _lib.lib()
+    C = x.shape[1]
+    out = torch.empty((B * Nq, C), dtype=torch.float32, device=x.device)
+    with _call(f"pointconv_aggregate_fwd[{C}]", 1, _nbytes(x, H2, idx, out)):
+        rc = L.crfconv_pointconv_aggregate_fwd(_p(x), _p(H2), _p(bn.scale), _p(bn.shift), _p(idx), _p(out), B, Ns, Nq, K, C, _lib.stream_ptr())
+    _lib.check(rc, "pointconv_aggregate_fwd")
+    return out
+
+
+def pointconv_aggregate_bwd(x, H2, bn: BN, idx, g, dx, B, Ns, Nq, K):
+    L = _lib.lib()
+    C = x.shape[1]
+    dWgt = torch.empty_like(H2)
+    with _call(f"pointconv_aggregate_bwd[{C}]", 1, _nbytes(x, H2, idx, g, dWgt, dx)):
+        rc = L.crfconv_pointconv_aggregate_bwd(_p(x), _p(H2), _p(bn.scale), _p(bn.shift), _p(idx), _p(g), _p(dWgt), _p(dx), B, Ns, Nq, K, C,
+                                               _lib.stream_ptr())
+    _lib.check(rc, "pointconv_aggregate_bwd")
+    return dWgt
+
+
+def gather_max_fwd(x, idx, B, Ns, Nq, K):
+    L = _lib.lib()
+    C = x.shape[1]
+    out = torch.empty((B * Nq, C), dtype=torch.float32, device=x.device)
+    arg = torch.empty((B * Nq, C), dtype=torch.int32, device=x.device)
+    with _call(f"gather_max_fwd[{C}]", 1, _nbytes(x, idx, out, arg)):
+        rc = L.crfconv_gather_max_fwd(_p(x), _p(idx), _p(out), _p(arg), B, Ns, Nq, K, C, _lib.stream_ptr())
+    _lib.check(rc, "gather_max_fwd")
+    return out, arg
+
+
+def gather_max_bwd(g, arg, dx):
+    L = _lib.lib()
+    with _call(f"gather_max_bwd[{g.shape[1]}]", 1, _nbytes(g, arg, dx)):
+        rc = L.crfconv_gather_max_bwd(_p(g), _p(arg), _p(dx), g.shape[0], g.shape[1], _lib.stream_ptr())
+    _lib.check(rc, "gather_max_bwd")
+
+
+def lrelu_bwd(g, out, slope):
+    L = _lib.lib()
+    dS = torch.empty_like(out)
+    with _call("lrelu_bwd", 1, _nbytes(g, out, dS)):
+        rc = L.crfconv_lrelu_bwd(_p(g), _p(out), float(slope), _p(dS), out.numel(), _lib.stream_ptr())
+    _lib.check(rc, "lrelu_bwd")
+    return dS
+
+
+def add_inplace(y, x):
+    L = _lib.lib()
+    with _call("add_inplace", 1, _nbytes(y, y, x)):
+        rc = L.crfconv_add_inplace(_p(y), _p(x), y.numel(), _lib.stream_ptr())
+    _lib.check(rc, "add_inplace")
+
+
+def scatter_add_rows(src, idx, dst, B, Nq, Ns):
+    L = _lib.lib()
+    with _call(f"scatter_add_rows[{src.shape[1]}]", 1, _nbytes(src, idx, dst)):
+        rc = L.crfconv_scatter_add_rows(_p(src), _p(idx), _p(dst), B, Nq, Ns, src.shape[1], _lib.stream_ptr())
+    _lib.check(rc, "scatter_add_rows")

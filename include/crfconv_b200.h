@@ -135,6 +135,31 @@ int crfconv_crf_step_bwd(const float* Hy, const float* scale_y, const float* z, 
                          const float* Cm, const float* Minv, const float* g, float* Gz, float* gprev, float* Gy, float* m_out,
                          float* v_out, float* h_out, int gz_acc, int64_t B, int64_t N, int K, int F, void* stream);
 
+/* ------------------------------------------------------- neighbour gather / point-conv aggregation
+ * Replaces PointConv.gather_neighbors / _compute_weights / forward (models/point_conv_big.py:25-58),
+ * ResNetBBlock.max_pooling (:74-77) and the backward of Upsampling.upsampling (:97-101).  idx [B,Nq,K] i64 indexes the
+ * Ns support points of the same cloud.  C % 4 == 0. */
+
+/* rel[(b·Nq+i)·K+k, 0:3] = centres[b,i] − support[b, idx[b,i,k]]   (point_conv_big.py:40) */
+int crfconv_relpos(const float* support, const float* centres, const int64_t* idx, float* rel, int64_t B, int64_t Ns, int64_t Nq, int K,
+                   void* stream);
+/* out[b,i,:] = Σ_k (H2[e,:]*scale + shift) ⊙ x[b, idx[b,i,k], :]   — (w * x).sum(2) with weight_nn's last BatchNorm fused (:56-57) */
+int crfconv_pointconv_aggregate_fwd(const float* x, const float* H2, const float* scale, const float* shift, const int64_t* idx, float* out,
+                                    int64_t B, int64_t Ns, int64_t Nq, int K, int C, void* stream);
+/* dWgt[e,:] = g[b,i,:] ⊙ x[src,:];  dx[src,:] += w[e,:] ⊙ g[b,i,:]  (dx may be NULL; zero-initialised by the caller) */
+int crfconv_pointconv_aggregate_bwd(const float* x, const float* H2, const float* scale, const float* shift, const int64_t* idx,
+                                    const float* g, float* dWgt, float* dx, int64_t B, int64_t Ns, int64_t Nq, int K, int C, void* stream);
+/* out[b,i,:] = max_k x[b, idx[b,i,k], :];  arg = flat source row of the first maximum (for the backward scatter) */
+int crfconv_gather_max_fwd(const float* x, const int64_t* idx, float* out, int32_t* arg, int64_t B, int64_t Ns, int64_t Nq, int K, int C,
+                           void* stream);
+int crfconv_gather_max_bwd(const float* g, const int32_t* arg, float* dx, int64_t rows, int C, void* stream);
+/* dS = g · (out > 0 ? 1 : slope)  — backward of F.leaky_relu(x + residual) (point_conv_big.py:88) */
+int crfconv_lrelu_bwd(const float* g, const float* out, float slope, float* dS, int64_t numel, void* stream);
+/* y += x */
+int crfconv_add_inplace(float* y, const float* x, int64_t numel, void* stream);
+/* dst[b·Ns + idx[b,m], :] += src[b·Nq + m, :]  — backward of a K=1 row gather (point_conv_big.py:97-101) */
+int crfconv_scatter_add_rows(const float* src, const int64_t* idx, float* dst, int64_t B, int64_t Nq, int64_t Ns, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,6 +79,8 @@ class PointConv(nn.Module):                             # point_conv_big.py:8-58
 
 
 class ResNetBBlock(nn.Module):                          # point_conv_big.py:61-88
+    negative_slope = 0.01                               # F.leaky_relu default (:88); a class attribute so tests can remove the kink
+
     def __init__(self, in_channels, out_channels):
         super().__init__()
         hidden = out_channels // 4
@@ -92,7 +94,7 @@ class ResNetBBlock(nn.Module):                          # point_conv_big.py:61-8
         if not torch.is_tensor(pos):                                               # strided block: max over neighbours (:74-77,81-82)
             residual = take_rows(residual, neighbor_idx).max(dim=2)[0]
         x = self.lin_out(self.point_conv(self.lin_in(x), pos, neighbor_idx))
-        return F.leaky_relu(x + residual)                                          # default slope 0.01 (:88)
+        return F.leaky_relu(x + residual, self.negative_slope)                    # default slope 0.01 (:88)
 
 
 class Upsampling(nn.Module):                            # point_conv_big.py:91-107
