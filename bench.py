@@ -154,8 +154,8 @@ def run_gpu(args, rank, local_rank, world):
     layer = ContinuousGaussianCRFConv(CU, CP, CP, steps=1).to(dev).train()
     with torch.no_grad():
         layer.c.add_(0.1 * torch.randn_like(layer.c))
-    params = [p for p in layer.parameters()]
-    flat_grad = torch.zeros(sum(p.numel() for p in params), device=dev)
+    from crfconv_b200.distributed import FlatGradients
+    fg = FlatGradients(layer)          # all parameter gradients are views of ONE contiguous buffer → one all-reduce, no copies
 
     in_bytes = B * (4 * ((N_POINTS // RATIO) * CU + N_POINTS * CP) + 8 * N_POINTS * (K_NBR + 1))
     nsets = max(2, -(-2 * L2_BYTES // max(in_bytes, 1)))     # rotate enough input sets that a step never finds its inputs in L2
@@ -168,15 +168,10 @@ def run_gpu(args, rank, local_rank, world):
 
     def step(i):
         s = sets[i % nsets]
+        fg.zero()
         out = layer(s["unary"], s["pairwise"], s["up_idx"], s["neighbor_idx"])
         out.backward(cot)
-        if world > 1:
-            off = 0
-            for p in params:                      # grads land in one flat fp32 buffer → ONE all-reduce
-                flat_grad[off:off + p.numel()].copy_(p.grad.reshape(-1)); off += p.numel()
-            dist.all_reduce(flat_grad)
-        for p in params:
-            p.grad = None
+        fg.all_reduce()                           # no-op at world == 1
         s["unary"].grad = None
         s["pairwise"].grad = None
 
@@ -220,16 +215,11 @@ def run_gpu(args, rank, local_rank, world):
         p = h["pairwise"].to(dev, non_blocking=True).requires_grad_(True)
         up = h["up_idx"].to(dev, non_blocking=True)
         nb = h["neighbor_idx"].to(dev, non_blocking=True)
+        fg.zero()
         out = layer(u, p, up, nb)
         out.backward(cot)
-        if world > 1:
-            off = 0
-            for q in params:
-                flat_grad[off:off + q.numel()].copy_(q.grad.reshape(-1)); off += q.numel()
-            dist.all_reduce(flat_grad)
+        fg.all_reduce()
         loss_host.copy_(out.detach().sum().reshape(1), non_blocking=True)
-        for q in params:
-            q.grad = None
         torch.cuda.current_stream().synchronize()      # the caller reads the loss on the host every step
 
     for i in range(3):

@@ -1,0 +1,85 @@
+"""Batch-sharded data parallelism for the hot path: the clouds of a batch are independent in every stage
+(kNN, subsampling, gather, conv, CRF), so each rank (one process per GPU) takes a contiguous slice of the batch and the only
+exchange is ONE all-reduce of the parameter gradients per step — NCCL over NVLink/NVSwitch on the GPU box, gloo in the
+CPU tests.  All parameter gradients live in one contiguous fp32 buffer (``p.grad`` are views into it), so the collective
+needs no bucketing and no staging copies (3.28 MB for the full PointConvResNet, 54 KB for one CRF layer: latency-bound).
+
+BatchNorm statistics stay per-rank (standard DDP semantics); running statistics are not synchronised.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(batch_size: int, rank: int, world_size: int):
+    """Contiguous slice [lo, hi) of the batch owned by `rank`; remainders go to the lowest ranks."""
+    base, rem = divmod(batch_size, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(tensors, rank: int, world_size: int):
+    """Slices every [B, ...] tensor of a (possibly nested) list / tuple / dict / namespace-like structure along dim 0."""
+    def rec(x):
+        if torch.is_tensor(x):
+            lo, hi = shard_range(x.shape[0], rank, world_size)
+            return x[lo:hi]
+        if isinstance(x, dict):
+            return {k: rec(v) for k, v in x.items()}
+        if isinstance(x, (list, tuple)):
+            return type(x)(rec(v) for v in x)
+        if hasattr(x, "__dict__"):
+            import copy
+            y = copy.copy(x)
+            for k, v in vars(x).items():
+                setattr(y, k, rec(v))
+            return y
+        return x
+    return rec(tensors)
+
+
+class FlatGradients:
+    """Owns one contiguous gradient buffer for all parameters of `module`; ``all_reduce()`` is a single collective."""
+
+    def __init__(self, module: torch.nn.Module):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        if not self.params:
+            raise ValueError("module has no trainable parameters")
+        dev = self.params[0].device
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
+        self._bind()
+
+    def _bind(self):
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)      # autograd accumulates in place into these views
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+        if any(p.grad is None or p.grad.data_ptr() < self.flat.data_ptr() for p in self.params):
+            self._bind()                                            # someone called zero_grad(set_to_none=True)
+
+    def all_reduce(self, average: bool = True):
+        """Sums the flat buffer over the ranks (one collective); divides by world size if `average`."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            if average:
+                self.flat.div_(dist.get_world_size())
+        return self.flat
+
+
+def init_from_env(backend: str | None = None):
+    """torchrun-style initialisation (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT). Returns (rank, local_rank, world)."""
+    import os
+    rank, local_rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend)
+    return rank, local_rank, world

@@ -1,0 +1,79 @@
+"""CPU, world_size = 2, gloo: host-side logic of the batch-sharded data parallelism — shard ranges, flat
+gradient buffer, ONE all-reduce — checked against the single-process result.  A plain torch module stands in for the CUDA
+layers (which need a GPU); BatchNorm-free so that sharded and unsharded gradients are identical by linearity."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from crfconv_b200.distributed import FlatGradients, shard_batch, shard_range
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _model():
+    torch.manual_seed(0)
+    return torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.Tanh(), torch.nn.Linear(16, 3))
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        model = _model()
+        fg = FlatGradients(model)
+        g = torch.Generator().manual_seed(1)
+        x, y = torch.randn(5, 40, 6, generator=g), torch.randn(5, 40, 3, generator=g)      # 5 clouds over 2 ranks: ragged shards
+        xs, ys = shard_batch((x, y), rank, world)
+        fg.zero()
+        ((model(xs) - ys) ** 2).sum().backward()          # sum-loss ⇒ summed shard gradients == full-batch gradient
+        before = fg.flat.clone()
+        out = fg.all_reduce(average=False)
+        assert out.data_ptr() == fg.flat.data_ptr()
+        assert all(p.grad.data_ptr() >= fg.flat.data_ptr() for p in model.parameters())   # grads are views of the flat buffer
+        q.put((rank, xs.shape[0], before, fg.flat.clone()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_ranges_cover_the_batch_exactly():
+    for B in (1, 2, 5, 6, 16, 17):
+        for W in (1, 2, 4, 8):
+            r = [shard_range(B, k, W) for k in range(W)]
+            assert r[0][0] == 0 and r[-1][1] == B and all(r[i][1] == r[i + 1][0] for i in range(W - 1))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.timeout(120)
+def test_flat_gradient_allreduce_matches_single_process():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=100) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[1] for r in res] == [3, 2]
+    # single-process reference on the whole batch
+    model = _model()
+    g = torch.Generator().manual_seed(1)
+    x, y = torch.randn(5, 40, 6, generator=g), torch.randn(5, 40, 3, generator=g)
+    ((model(x) - y) ** 2).sum().backward()
+    ref = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    for _, _, before, after in res:
+        assert torch.allclose(after, ref, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(res[0][2] + res[1][2], ref, rtol=1e-5, atol=1e-5)
+    assert not torch.allclose(res[0][2], ref, rtol=1e-3, atol=1e-3)        # a shard alone is NOT the full gradient

@@ -110,3 +110,15 @@ def test_large_sampled_brute_force(nn):
     got = nn.knn(pts, pts, 16)
     sample = np.random.default_rng(1).choice(1000000, 300, replace=False)
     assert np.array_equal(got[sample], on.knn(pts, pts[sample], 16))
+
+
+def test_gpu_multiscale_builder_matches_reference_pipeline():
+    """N1: the collate-time pyramid (s3dis_dataset.py:416-449) built on the device equals the CPU restatement driven by the
+    oracle kNN, level by level, bit for bit (same randperm stream)."""
+    from crfconv_b200.multiscale import build_multiscale
+    pos = synthetic.room_cloud(2, 8192, 30)
+    ref = synthetic.build_multiscale(pos, on.knn_batch, num_scales=5, K=16, seed=7)
+    got = build_multiscale(torch.from_numpy(pos).cuda(), generator=torch.Generator().manual_seed(7))
+    for a, b in zip(got, ref):
+        for k in ("pos", "neighbor_idx", "sub_idx", "up_idx"):
+            assert torch.equal(getattr(a, k).cpu(), getattr(b, k)), k
