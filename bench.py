@@ -166,7 +166,7 @@ def run_gpu(args, rank, local_rank, world):
         s["pairwise"].requires_grad_(True)
     cot = torch.ones(B, N_POINTS, CP, device=dev)
 
-    def step(i):
+    def eager_step(i):
         s = sets[i % nsets]
         fg.zero()
         out = layer(s["unary"], s["pairwise"], s["up_idx"], s["neighbor_idx"])
@@ -174,6 +174,39 @@ def run_gpu(args, rank, local_rank, world):
         fg.all_reduce()                           # no-op at world == 1
         s["unary"].grad = None
         s["pairwise"].grad = None
+
+    # The ~50 kernel launches of one fwd+bwd are captured ONCE per input set into a CUDA graph and replayed: with ≈1.4 ms of GPU
+    # work per step the Python/ctypes launch path (≈1.8 ms per step) would otherwise be the bottleneck.  The gradient all-reduce
+    # stays outside the graph.
+    graphs, launches_per_step = [], 0
+    if args.graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(3):
+                eager_step(i)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for k in range(nsets):
+            s = sets[k]
+            g = torch.cuda.CUDAGraph()
+            ops.COUNTERS["launches"] = 0
+            with torch.cuda.graph(g):
+                fg.zero()
+                out = layer(s["unary"], s["pairwise"], s["up_idx"], s["neighbor_idx"])
+                out.backward(cot)
+            launches_per_step = ops.COUNTERS["launches"]
+            s["unary"].grad = None
+            s["pairwise"].grad = None
+            graphs.append(g)
+
+    def step(i):
+        if graphs:
+            graphs[i % nsets].replay()
+            fg.all_reduce()
+            ops.COUNTERS["launches"] += launches_per_step
+        else:
+            eager_step(i)
 
     def barrier():
         if world > 1:
@@ -209,25 +242,68 @@ def run_gpu(args, rank, local_rank, world):
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
     loss_host = torch.zeros(1).pin_memory()
 
-    def e2e_step(i):
-        h = host[i % 2]
-        u = h["unary"].to(dev, non_blocking=True).requires_grad_(True)
-        p = h["pairwise"].to(dev, non_blocking=True).requires_grad_(True)
-        up = h["up_idx"].to(dev, non_blocking=True)
-        nb = h["neighbor_idx"].to(dev, non_blocking=True)
-        fg.zero()
-        out = layer(u, p, up, nb)
-        out.backward(cot)
-        fg.all_reduce()
-        loss_host.copy_(out.detach().sum().reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the caller reads the loss on the host every step
+    # Two device-side staging buffers: the H2D copy of step i+1 runs on a copy stream while step i computes (the inputs of
+    # every step still cross PCIe inside the timed region); fwd+bwd of each buffer is a captured CUDA graph when --graph.
+    copy_stream = torch.cuda.Stream()
+    stage = [{k: torch.empty_like(v, device=dev) for k, v in host[0].items()} for _ in range(2)]
+    for st_ in stage:
+        st_["unary"].requires_grad_(True)
+        st_["pairwise"].requires_grad_(True)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
+    loss_dev = [torch.zeros(1, device=dev) for _ in range(2)]
 
-    for i in range(3):
-        e2e_step(i)
+    def fwd_bwd(j):
+        st_ = stage[j]
+        fg.zero()
+        out = layer(st_["unary"], st_["pairwise"], st_["up_idx"], st_["neighbor_idx"])
+        out.backward(cot)
+        loss_dev[j].copy_(out.detach().sum().reshape(1))
+        st_["unary"].grad = None
+        st_["pairwise"].grad = None
+
+    e2e_graphs = []
+    if args.graph:
+        for j in range(2):
+            for k, v in host[j].items():
+                stage[j][k].data.copy_(v)
+            torch.cuda.synchronize()
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph):
+                fwd_bwd(j)
+            e2e_graphs.append(gph)
+
+    def upload(i):
+        j = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done[j])                     # the previous user of this staging buffer has finished
+            for k, v in host[j].items():
+                stage[j][k].data.copy_(v, non_blocking=True)
+            ready[j].record(copy_stream)
+
+    def e2e_run(n):
+        cur = torch.cuda.current_stream()
+        for j in range(2):
+            done[j].record(cur)
+        upload(0)
+        for i in range(n):
+            j = i % 2
+            if i + 1 < n:
+                upload(i + 1)
+            cur.wait_event(ready[j])
+            if e2e_graphs:
+                e2e_graphs[j].replay()
+            else:
+                fwd_bwd(j)
+            fg.all_reduce()
+            loss_host.copy_(loss_dev[j], non_blocking=True)
+            done[j].record(cur)
+            cur.synchronize()                                   # the caller reads the loss on the host every step
+
+    e2e_run(3)
     barrier()
     e0.record()
-    for i in range(args.steps):
-        e2e_step(i)
+    e2e_run(args.steps)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
@@ -244,7 +320,7 @@ def run_gpu(args, rank, local_rank, world):
 
     # ---- per-kernel instrumented pass (CUDA events around every C-ABI launch on the launching stream)
     peaks, peak_src = measured_peaks()
-    prof = ops.profile_calls(lambda: step(0), repeats=3)
+    prof = ops.profile_calls(lambda: eager_step(0), repeats=3)
     total_k = sum(v["ms"] for v in prof.values())
     top = max(prof.items(), key=lambda kv: kv[1]["ms"])
     kernels = {k: {"ms_per_step": round(v["ms"], 4), "calls_per_step": v["calls"], "share": round(v["ms"] / total_k, 4),
@@ -279,6 +355,7 @@ def run_gpu(args, rank, local_rank, world):
             "config": {"workload": f"single ContinuousGaussianCRFConv(128,64,64,steps=1) fwd+bwd, N=40960, Nc=10240, K=16, "
                                    f"{B} clouds per GPU per step (SURVEY.md §8 S1 / BASELINE configs[0] shape on the GPU)",
                        "clouds_per_gpu": B, "precision": "3xTF32 tensor-core contractions, fp32 elsewhere" if ops.PRECISION == 0 else "TF32",
+                       "launch": "one CUDA graph per input set, replayed" if args.graph else "eager (per-kernel launches from Python)",
                        "l2": f"rotating {nsets} input sets of {in_bytes / 2**20:.0f} MiB each (> {L2_BYTES / 2**20:.0f} MiB L2)",
                        "parallelism": f"dp{world}: clouds sharded, one NCCL all-reduce of the flat gradient" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -298,6 +375,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--clouds", type=int, default=6, help="clouds per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every kernel from Python instead of replaying CUDA graphs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -309,7 +387,7 @@ def main():
         # launched without torchrun: re-launch under torch.distributed.run, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", str(29500 + os.getpid() % 2000), os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps),
-               "--warmup", str(args.warmup), "--clouds", str(args.clouds)]
+               "--warmup", str(args.warmup), "--clouds", str(args.clouds)] + ([] if args.graph else ["--no-graph"])
         sys.exit(subprocess.call(cmd))
     run_gpu(args, rank, local_rank, world)
 

@@ -246,6 +246,103 @@ __global__ void __launch_bounds__(256) step_bwd_kernel(const StepArgs a) {
     if (valid) *reinterpret_cast<float4*>(a.v_out + p * F + c0) = v;
 }
 
+// Single-gather variant for the common neighbourhood size (K-1 = KN known at compile time): every neighbour row is fetched
+// ONCE; y_j slices, distances and <q, x_j> stay in registers between the softmax pass and the scatter pass.  The generic
+// kernel above re-gathers in its second pass; ncu shows it L1TEX-throughput bound (82 %), so transactions are what to cut.
+template <int F, int KN>
+__global__ void __launch_bounds__(128) step_bwd_reg_kernel(const StepArgs a) {
+    constexpr int LP = F / 4, PPW = 32 / LP;
+    __shared__ __align__(16) float CsT[F * F];   // transposed copies: out[c] = Σ_k v[k]·Mat[c][k] becomes a row-vector product
+    __shared__ __align__(16) float MsT[F * F];
+    __shared__ __align__(16) float Cs[F * F];
+    for (int i = threadIdx.x; i < F * F; i += blockDim.x) {
+        const int r = i / F, c = i % F;
+        Cs[i] = a.Cm[i];
+        CsT[c * F + r] = a.Cm[i];
+        MsT[c * F + r] = a.Minv[i];
+    }
+    __syncthreads();
+    const int lane = lane_id();
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t p = warp * PPW + lane / LP;
+    const bool valid = p < a.total;
+    if (!valid) p = a.total - 1;
+    const int c0 = (lane % LP) * 4;
+    const int64_t base = (p / a.N) * a.N;
+    const float4 sc = ld4(a.scale_y + c0);
+    const float4 yi = mul4(ld4(a.Hy + p * F + c0), sc);
+
+    float full[F];
+    const float4 gi = ld4(a.g + p * F + c0);
+    gather_full<F>(gi, full, lane);
+    const float4 h = rowvec_mat<F>(full, MsT, c0);       // h = g·Minvᵀ
+    gather_full<F>(h, full, lane);
+    const float4 q = rowvec_mat<F>(full, CsT, c0);       // q = h·Cᵀ
+
+    int rj[KN];
+    float4 dfj[KN];
+    float dj[KN], gsj[KN];
+    const int64_t* nb = a.nbr + p * a.K + 1;
+#pragma unroll
+    for (int k = 0; k < KN; ++k) rj[k] = (int)__ldg(nb + k);
+    float mx = -INFINITY;
+    float4 xj[KN];
+#pragma unroll
+    for (int k = 0; k < KN; ++k) {                       // all gathers issued back to back
+        const int64_t row = base + rj[k];
+        dfj[k] = ld4(a.Hy + row * F + c0);
+        xj[k] = ld4(a.xprev + row * F + c0);
+    }
+#pragma unroll
+    for (int k = 0; k < KN; ++k) {
+        dfj[k] = sub4(yi, mul4(dfj[k], sc));
+        dj[k] = group_sum<LP>(dot4(dfj[k], dfj[k]));
+        gsj[k] = group_sum<LP>(dot4(q, xj[k]));
+        mx = fmaxf(mx, -dj[k]);
+    }
+    float l = 0.f, tacc = 0.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < KN; ++k) {
+        const float pj = __expf(-dj[k] - mx);
+        dj[k] = pj;                                      // reuse the slot for the unnormalised weight
+        l += pj;
+        tacc = fmaf(pj, gsj[k], tacc);
+        acc.x = fmaf(pj, xj[k].x, acc.x); acc.y = fmaf(pj, xj[k].y, acc.y);
+        acc.z = fmaf(pj, xj[k].z, acc.z); acc.w = fmaf(pj, xj[k].w, acc.w);
+    }
+    const float inv_l = 1.0f / l;
+    const float sdot = tacc * inv_l;
+    const float4 msg = make_float4(acc.x * inv_l, acc.y * inv_l, acc.z * inv_l, acc.w * inv_l);
+    float4 gyi = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < KN; ++k) {
+        const float s_ = dj[k] * inv_l;
+        const float ga2 = 2.0f * s_ * (gsj[k] - sdot);
+        const float4 df = dfj[k];
+        gyi.x -= ga2 * df.x; gyi.y -= ga2 * df.y; gyi.z -= ga2 * df.z; gyi.w -= ga2 * df.w;
+        if (valid) {
+            const int64_t row = base + rj[k];
+            red_add_v4(a.Gy + row * F + c0, make_float4(ga2 * df.x, ga2 * df.y, ga2 * df.z, ga2 * df.w));
+            red_add_v4(a.gprev + row * F + c0, make_float4(s_ * q.x, s_ * q.y, s_ * q.z, s_ * q.w));
+        }
+    }
+    if (valid) {
+        red_add_v4(a.Gy + p * F + c0, gyi);
+        float* gz = a.Gz + p * F + c0;
+        float4 o = h;
+        if (a.gz_acc) { const float4 old = *reinterpret_cast<float4*>(gz); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+        *reinterpret_cast<float4*>(gz) = o;
+        *reinterpret_cast<float4*>(a.h_out + p * F + c0) = h;
+        *reinterpret_cast<float4*>(a.m_out + p * F + c0) = msg;
+    }
+    gather_full<F>(msg, full, lane);
+    float4 v = rowvec_mat<F>(full, Cs, c0);
+    const float4 zi = ld4(a.z + p * F + c0);
+    v.x += zi.x; v.y += zi.y; v.z += zi.z; v.w += zi.w;
+    if (valid) *reinterpret_cast<float4*>(a.v_out + p * F + c0) = v;
+}
+
 // ---- F×F compatibility algebra (single CTA, double precision in a global scratch of 3·F·F doubles)
 // Cm = cᵀc ; Minv = (I + Cm)^{-1} by Gauss-Jordan (I + cᵀc is SPD with eigenvalues >= 1: no pivoting needed).
 __global__ void __launch_bounds__(256) compat_fwd_kernel(const float* __restrict__ c, float* __restrict__ Cm, float* __restrict__ Minv,
@@ -401,6 +498,13 @@ int crfconv_crf_step_bwd(const float* Hy, const float* scale_y, const float* z, 
         constexpr int FF = decltype(f)::value;
         constexpr int PPW = 32 / (FF / 4);
         const int64_t warps = ceil_div(a.total, PPW);
+        if constexpr (FF <= 16) {
+            if (K == 16) {      // the reference's neighbourhood size everywhere (kernel_size = 16): single-gather register kernel
+                mf::step_bwd_reg_kernel<FF, 15><<<(unsigned)ceil_div(warps, 4), 128, 0, (cudaStream_t)stream>>>(a);
+                CRF_LAUNCH_CHECK();
+                return CRF_OK;
+            }
+        }
         mf::step_bwd_kernel<FF><<<(unsigned)ceil_div(warps, 8), 256, 0, (cudaStream_t)stream>>>(a);
         CRF_LAUNCH_CHECK();
         return CRF_OK;

@@ -172,8 +172,9 @@ __global__ void __launch_bounds__(kThreads) fwd_kernel(const FwdArgs a) {
     if (a.stats) {
         __syncthreads();
         if (tid < BN && n0 + tid < a.Cout) {
-            atomicAdd(a.stats + n0 + tid, (double)s_sum[tid]);
-            atomicAdd(a.stats + a.Cout + n0 + tid, (double)s_sq[tid]);
+            double* st = a.stats + (size_t)(blockIdx.x % kStatSlots) * 2 * a.Cout;
+            atomicAdd(st + n0 + tid, (double)s_sum[tid]);
+            atomicAdd(st + a.Cout + n0 + tid, (double)s_sq[tid]);
         }
     }
 }
@@ -181,16 +182,31 @@ __global__ void __launch_bounds__(kThreads) fwd_kernel(const FwdArgs a) {
 // ------------------------------------------------------------------------------- BatchNorm bookkeeping
 // Training: batch statistics from Σ / Σ² → scale/shift (+ saved mean / invstd, running-stat update with momentum and
 // unbiased variance, exactly nn.BatchNorm1d).  Eval: scale/shift from the running statistics.
-__global__ void bn_finalize_fwd_kernel(const double* __restrict__ stats, double count, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(128) bn_finalize_fwd_kernel(const double* __restrict__ stats, double count, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, float eps, float momentum, int training,
                                        float* running_mean, float* running_var, float* __restrict__ scale,
                                        float* __restrict__ shift, float* __restrict__ mean_out, float* __restrict__ invstd_out, int C) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    // one CTA per channel: sums the kStatSlots partial (Σ, Σ²) pairs in a fixed order, then the BatchNorm bookkeeping
+    __shared__ double r1[4], r2[4];
+    const int c = blockIdx.x;
+    double s1 = 0.0, s2 = 0.0;
+    if (training) {
+        for (int p = threadIdx.x; p < kStatSlots; p += blockDim.x) {
+            s1 += stats[(size_t)p * 2 * C + c];
+            s2 += stats[(size_t)p * 2 * C + C + c];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+        if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = s1; r2[threadIdx.x >> 5] = s2; }
+        __syncthreads();
+        s1 = r1[0] + r1[1] + r1[2] + r1[3];
+        s2 = r2[0] + r2[1] + r2[2] + r2[3];
+    }
+    if (threadIdx.x != 0) return;
     float mean, invstd;
     if (training) {
-        const double mu = stats[c] / count;
-        double var = stats[C + c] / count - mu * mu;
+        const double mu = s1 / count;
+        double var = s2 / count - mu * mu;
         if (var < 0.0) var = 0.0;
         mean = (float)mu;
         invstd = (float)(1.0 / sqrt(var + (double)eps));
@@ -252,16 +268,30 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
         const float4 sc = __ldg(reinterpret_cast<const float4*>(bn.scale + c)), sh = __ldg(reinterpret_cast<const float4*>(bn.shift + c));
         const float4 mu = __ldg(reinterpret_cast<const float4*>(bn.mean + c)), is = __ldg(reinterpret_cast<const float4*>(bn.invstd + c));
         const bool has_ref = bn.act_ref != nullptr;
-        for (int64_t m = (int64_t)blockIdx.x * rows_per_it + rslot; m < M; m += (int64_t)gridDim.x * rows_per_it) {
-            const float4 dy = __ldg(reinterpret_cast<const float4*>(dY + m * C + c));
-            const float4 h = __ldg(reinterpret_cast<const float4*>(H + m * C + c));
-            float4 rf = make_float4(0, 0, 0, 0);
-            if (has_ref) rf = __ldg(reinterpret_cast<const float4*>(bn.act_ref + m * C + c));
-            const float d0 = bn_dv(dy.x, h.x, rf.x, has_ref, sc.x, sh.x, bn.slope), d1 = bn_dv(dy.y, h.y, rf.y, has_ref, sc.y, sh.y, bn.slope);
-            const float d2 = bn_dv(dy.z, h.z, rf.z, has_ref, sc.z, sh.z, bn.slope), d3 = bn_dv(dy.w, h.w, rf.w, has_ref, sc.w, sh.w, bn.slope);
-            s1[0] += d0; s1[1] += d1; s1[2] += d2; s1[3] += d3;
-            s2[0] += d0 * (h.x - mu.x) * is.x; s2[1] += d1 * (h.y - mu.y) * is.y;
-            s2[2] += d2 * (h.z - mu.z) * is.z; s2[3] += d3 * (h.w - mu.w) * is.w;
+        // 4 rows per thread per trip: 8-12 independent 128-bit loads in flight per thread (the kernel is pure streaming)
+        constexpr int U = 4;
+        const int64_t stride = (int64_t)gridDim.x * rows_per_it;
+        for (int64_t m0 = (int64_t)blockIdx.x * rows_per_it + rslot; m0 < M; m0 += U * stride) {
+            float4 dy[U], h[U], rf[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t m = m0 + u * stride;
+                if (m < M) {
+                    dy[u] = __ldg(reinterpret_cast<const float4*>(dY + m * C + c));
+                    h[u] = __ldg(reinterpret_cast<const float4*>(H + m * C + c));
+                    rf[u] = has_ref ? __ldg(reinterpret_cast<const float4*>(bn.act_ref + m * C + c)) : make_float4(0, 0, 0, 0);
+                } else {
+                    dy[u] = make_float4(0, 0, 0, 0); h[u] = mu; rf[u] = make_float4(0, 0, 0, 0);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const float d0 = bn_dv(dy[u].x, h[u].x, rf[u].x, has_ref, sc.x, sh.x, bn.slope), d1 = bn_dv(dy[u].y, h[u].y, rf[u].y, has_ref, sc.y, sh.y, bn.slope);
+                const float d2 = bn_dv(dy[u].z, h[u].z, rf[u].z, has_ref, sc.z, sh.z, bn.slope), d3 = bn_dv(dy[u].w, h[u].w, rf[u].w, has_ref, sc.w, sh.w, bn.slope);
+                s1[0] += d0; s1[1] += d1; s1[2] += d2; s1[3] += d3;
+                s2[0] += d0 * (h[u].x - mu.x) * is.x; s2[1] += d1 * (h[u].y - mu.y) * is.y;
+                s2[2] += d2 * (h[u].z - mu.z) * is.z; s2[3] += d3 * (h[u].w - mu.w) * is.w;
+            }
         }
     }
 #pragma unroll
@@ -273,20 +303,41 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
         float tot = 0.0f;
         for (int r = 0; r < rows_per_it; ++r) tot += red[(r * tpr + cs) * 8 + e];
         const int c = cs * 4 + (e & 3);
-        atomicAdd(sums + (e < 4 ? 0 : C) + c, (double)tot);
+        atomicAdd(sums + (size_t)(blockIdx.x % kStatSlots) * 2 * C + (e < 4 ? 0 : C) + c, (double)tot);
     }
 }
 
 // k1 = s1/M, k2 = s2/M; dγ += s2, dβ += s1.
-__global__ void bn_finalize_bwd_kernel(const double* __restrict__ sums, double count, float* __restrict__ k1, float* __restrict__ k2,
+__global__ void __launch_bounds__(128) bn_finalize_bwd_kernel(const double* __restrict__ sums, double count, float* __restrict__ k1, float* __restrict__ k2,
                                        float* dgamma, float* dbeta, int C) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    const double s1 = sums[c], s2 = sums[C + c];
+    __shared__ double r1[4], r2[4];
+    const int c = blockIdx.x;
+    double s1 = 0.0, s2 = 0.0;
+    for (int p = threadIdx.x; p < kStatSlots; p += blockDim.x) {
+        s1 += sums[(size_t)p * 2 * C + c];
+        s2 += sums[(size_t)p * 2 * C + C + c];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = s1; r2[threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    s1 = r1[0] + r1[1] + r1[2] + r1[3];
+    s2 = r2[0] + r2[1] + r2[2] + r2[3];
     k1[c] = (float)(s1 / count);
     k2[c] = (float)(s2 / count);
     if (dgamma) dgamma[c] += (float)s2;
     if (dbeta) dbeta[c] += (float)s1;
+}
+
+// dW[i] += Σ_slots scratch[slot][i]   (fixed order ⇒ deterministic for a given launch configuration)
+__global__ void __launch_bounds__(256) grad_slots_reduce_kernel(const float* __restrict__ scratch, float* dW, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.f;
+#pragma unroll 8
+    for (int p = 0; p < kGradSlots; ++p) s += scratch[(size_t)p * n + i];
+    dW[i] += s;
 }
 
 // dH for 4 consecutive channels starting at c (c % 4 == 0, c + 3 < C).
@@ -499,7 +550,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const WgradArgs a) {
         for (int e = 0; e < 4; ++e) {
             const int co = co0 + wr + g + (e >= 2 ? 8 : 0);
             const int k = k0 + wc + nt * 8 + 2 * t + (e & 1);
-            if (co < a.Cout && k < Ktot) atomicAdd(a.dW + (int64_t)co * Ktot + k, acc[nt][e]);
+            if (co < a.Cout && k < Ktot) atomicAdd(a.dW + a.slot_stride * (blockIdx.x % kGradSlots) + (int64_t)co * Ktot + k, acc[nt][e]);
         }
     }
     if (a.dbias && blockIdx.z == 0 && tid < 64 && co0 + tid < a.Cout) atomicAdd(a.dbias + co0 + tid, bsum);
@@ -558,6 +609,7 @@ int crfconv_linear_fwd(const float* X1, int C1, const float* scale1, const float
     cudaStream_t st = (cudaStream_t)stream;
     if (lin::use_fast(M)) {
         int rc2 = CRF_OK;
+        if (lin::try_narrow_fwd(a, st, &rc2)) return rc2;
         if (lin::try_fwd2(a, precision, st, &rc2)) return rc2;
     }
     if (precision == 2) precision = 1;     // generic kernels: single-pass TF32 stands in for single-pass bf16
@@ -575,7 +627,7 @@ int crfconv_bn_finalize_fwd(const double* stats, int64_t count, const float* gam
                             int training, float* running_mean, float* running_var, float* scale, float* shift, float* mean,
                             float* invstd, int C, void* stream) {
     if (C <= 0 || !scale || !shift || (training && !stats) || (!training && (!running_mean || !running_var))) return CRF_ERR_INVALID_ARG;
-    lin::bn_finalize_fwd_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
+    lin::bn_finalize_fwd_kernel<<<(unsigned)C, 128, 0, (cudaStream_t)stream>>>(
         stats, (double)count, gamma, beta, eps, momentum, training, running_mean, running_var, scale, shift, mean, invstd, C);
     CRF_LAUNCH_CHECK();
     return CRF_OK;
@@ -608,7 +660,7 @@ int crfconv_bn_bwd_reduce(const float* dY, const float* H, const float* act_ref,
 
 int crfconv_bn_finalize_bwd(const double* sums, int64_t count, float* k1, float* k2, float* dgamma, float* dbeta, int C, void* stream) {
     if (C <= 0 || !sums || !k1 || !k2) return CRF_ERR_INVALID_ARG;
-    lin::bn_finalize_bwd_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, (double)count, k1, k2, dgamma, dbeta, C);
+    lin::bn_finalize_bwd_kernel<<<(unsigned)C, 128, 0, (cudaStream_t)stream>>>(sums, (double)count, k1, k2, dgamma, dbeta, C);
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }
@@ -620,7 +672,7 @@ int crfconv_linear_bwd(const float* dY, const float* H, const float* act_ref, co
                        const float* mean, const float* invstd, const float* k1, const float* k2, float slope,
                        const float* X1, int C1, const float* scale1, const float* shift1, float slope1, const int64_t* idx1,
                        int64_t rows_dst, int64_t rows_src, const float* X2, int C2, const float* W, float* dX1, int acc1,
-                       float* dX2, int acc2, float* dW, float* dbias, int64_t M, int Cout, int precision, void* stream) {
+                       float* dX2, int acc2, float* dW, float* dbias, float* dW_scratch, int64_t M, int Cout, int precision, void* stream) {
     if (M < 0 || Cout <= 0 || C1 < 0 || C2 < 0 || C1 + C2 <= 0 || !dY || !W) return CRF_ERR_INVALID_ARG;
     if (M == 0) return CRF_OK;
     if (scale && (Cout & 3)) return CRF_ERR_UNSUPPORTED;
@@ -628,6 +680,22 @@ int crfconv_linear_bwd(const float* dY, const float* H, const float* act_ref, co
     lin::BnBwd bn{scale, shift, mean, invstd, k1, k2, act_ref, slope};
     const int Ktot = C1 + C2;
     const int gprec = precision == 2 ? 1 : precision;    // precision seen by the generic (TF32) kernels
+    // weight-gradient partial slots: CTAs add into dW_scratch[slot] (zero-initialised by the caller), reduced into dW afterwards
+    float* wdst = (dW && dW_scratch) ? dW_scratch : dW;
+    const int64_t wstride = (dW && dW_scratch) ? (int64_t)Cout * Ktot : 0;
+    auto reduce_slots = [&]() -> int {
+        if (dW && dW_scratch) {
+            lin::grad_slots_reduce_kernel<<<(unsigned)ceil_div((int64_t)Cout * Ktot, 256), 256, 0, st>>>(dW_scratch, dW, Cout * Ktot);
+            CRF_LAUNCH_CHECK();
+        }
+        return CRF_OK;
+    };
+    if (lin::use_fast(M)) {                               // hidden-width layers: one fused dgrad + wgrad CUDA-core kernel
+        lin::DgradArgs d{dY, H, bn, W, dX1, C1, acc1, dX2, C2, acc2, M, Cout};
+        lin::WgradArgs w{dY, H, bn, X1, C1, scale1, shift1, slope1, idx1, rows_dst, rows_src, X2, C2, wdst, dbias, M, Cout, 0, wstride};
+        int rc2 = CRF_OK;
+        if (lin::try_narrow_bwd(d, dW ? &w : nullptr, st, &rc2)) return rc2 != CRF_OK ? rc2 : reduce_slots();
+    }
     if (dX1 || dX2) {
         // with idx1, dX1 is the gradient wrt the GATHERED rows [M, C1]; scatter it with crfconv_scatter_add_rows
         lin::DgradArgs a{dY, H, bn, W, dX1, C1, acc1, dX2, C2, acc2, M, Cout};
@@ -644,10 +712,10 @@ int crfconv_linear_bwd(const float* dY, const float* H, const float* act_ref, co
         if (rc != CRF_OK) return rc;
     }
     if (dW) {
-        lin::WgradArgs a{dY, H, bn, X1, C1, scale1, shift1, slope1, idx1, rows_dst, rows_src, X2, C2, dW, dbias, M, Cout, 0};
+        lin::WgradArgs a{dY, H, bn, X1, C1, scale1, shift1, slope1, idx1, rows_dst, rows_src, X2, C2, wdst, dbias, M, Cout, 0, wstride};
         if (lin::use_fast(M)) {
             int rc2 = CRF_OK;
-            if (lin::try_wgrad2(a, precision, st, &rc2)) return rc2;
+            if (lin::try_wgrad2(a, precision, st, &rc2)) return rc2 != CRF_OK ? rc2 : reduce_slots();
         }
         const int ty = (int)ceil_div(Cout, 64), tz = (int)ceil_div(Ktot, 64);
         int64_t splits = std::max<int64_t>(1, std::min<int64_t>(ceil_div(M, 256), (int64_t)(2 * kNumSMs) / (ty * tz) + 1));
@@ -657,6 +725,7 @@ int crfconv_linear_bwd(const float* dY, const float* H, const float* act_ref, co
         if (gprec == 0) lin::wgrad_kernel<true><<<grid, lin::kThreads, 0, st>>>(a);
         else lin::wgrad_kernel<false><<<grid, lin::kThreads, 0, st>>>(a);
         CRF_LAUNCH_CHECK();
+        return reduce_slots();
     }
     return CRF_OK;
 }

@@ -167,8 +167,9 @@ __global__ void __launch_bounds__(kThreads, 2) fwd2_kernel(const FwdArgs a, cons
     if (a.stats) {
         __syncthreads();
         if (tid < BN && tid < a.Cout) {
-            atomicAdd(a.stats + tid, (double)s_sum[tid]);
-            atomicAdd(a.stats + a.Cout + tid, (double)s_sq[tid]);
+            double* st = a.stats + (size_t)(blockIdx.x % kStatSlots) * 2 * a.Cout;
+            atomicAdd(st + tid, (double)s_sum[tid]);
+            atomicAdd(st + a.Cout + tid, (double)s_sq[tid]);
         }
     }
 }
@@ -199,9 +200,8 @@ __global__ void __launch_bounds__(kThreads, 2) fwd2t_kernel(const FwdArgs a, con
     const int nch1 = (a.C1 + BK - 1) / BK, nch2 = (a.C2 + BK - 1) / BK, nch = nch1 + nch2;
     const int Kpad = nch * BK, WS = Kpad + 4;
     float* As = reinterpret_cast<float*>(smem_raw);                       // [NSTT][BM][AST]
-    uint32_t* Wh = reinterpret_cast<uint32_t*>(As + NSTT * BM * AST);     // [BN][WS] tf32 hi
-    uint32_t* Wl = Wh + BN * WS;                                          //          tf32 lo
-    float* s_sc = reinterpret_cast<float*>(Wl + BN * WS);
+    float* Wf = As + NSTT * BM * AST;                                     // [BN][WS] fp32
+    float* s_sc = Wf + BN * WS;
     float* s_sh = s_sc + Kpad;
     float* s_sum = s_sh + Kpad;
     float* s_sq = s_sum + BN;
@@ -213,10 +213,7 @@ __global__ void __launch_bounds__(kThreads, 2) fwd2t_kernel(const FwdArgs a, con
         int col = -1;
         if (c < nch1) { if (c * BK + kk < a.C1) col = c * BK + kk; }
         else if ((c - nch1) * BK + kk < a.C2) col = a.C1 + (c - nch1) * BK + kk;
-        const float wv = (col >= 0 && n < a.Cout) ? __ldg(a.W + (int64_t)n * Ktot + col) : 0.f;
-        const uint32_t hi = tf32_of(wv);
-        Wh[n * WS + k] = hi;
-        Wl[n * WS + k] = tf32_of(wv - __uint_as_float(hi));
+        Wf[n * WS + k] = (col >= 0 && n < a.Cout) ? __ldg(a.W + (int64_t)n * Ktot + col) : 0.f;
     }
     for (int k = tid; k < Kpad; k += kThreads) {
         float sc = 1.f, sh = 0.f;
@@ -246,8 +243,10 @@ __global__ void __launch_bounds__(kThreads, 2) fwd2t_kernel(const FwdArgs a, con
             cp_async16(dst + r * AST + 4 * c4, X + srow * C + (ok ? col : 0), ok);
         }
     };
-    if (Q > 0) issue(0);
-    cp_async_commit();
+    for (int s = 0; s < NSTT - 1; ++s) {
+        if (s < Q) issue(s);
+        cp_async_commit();
+    }
 
     float acc[BN / 8][4];
 #pragma unroll
@@ -256,9 +255,9 @@ __global__ void __launch_bounds__(kThreads, 2) fwd2t_kernel(const FwdArgs a, con
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
     for (int q = 0; q < Q; ++q) {
-        cp_async_wait<0>();
+        cp_async_wait<NSTT - 2>();
         __syncthreads();
-        if (q + 1 < Q) issue(q + 1);
+        if (q + NSTT - 1 < Q) issue(q + NSTT - 1);
         cp_async_commit();
         const int ti = q / nch, c = q % nch;
         const float* At = As + (q % NSTT) * BM * AST;
@@ -283,9 +282,12 @@ __global__ void __launch_bounds__(kThreads, 2) fwd2t_kernel(const FwdArgs a, con
 #pragma unroll
                 for (int nt = 0; nt < BN / 8; ++nt) {
                     const int wi = (nt * 8 + g) * WS + wb;
-                    mma_tf32(acc[nt], al, Wh[wi], Wh[wi + 4]);
-                    mma_tf32(acc[nt], ah, Wl[wi], Wl[wi + 4]);
-                    mma_tf32(acc[nt], ah, Wh[wi], Wh[wi + 4]);
+                    const float w0 = Wf[wi], w1 = Wf[wi + 4];
+                    const uint32_t bh0 = tf32_of(w0), bh1 = tf32_of(w1);
+                    const uint32_t bl0 = tf32_of(w0 - __uint_as_float(bh0)), bl1 = tf32_of(w1 - __uint_as_float(bh1));
+                    mma_tf32(acc[nt], al, bh0, bh1);
+                    mma_tf32(acc[nt], ah, bl0, bl1);
+                    mma_tf32(acc[nt], ah, bh0, bh1);
                 }
             }
         }
@@ -324,15 +326,16 @@ __global__ void __launch_bounds__(kThreads, 2) fwd2t_kernel(const FwdArgs a, con
     if (a.stats) {
         __syncthreads();
         if (tid < BN && tid < a.Cout) {
-            atomicAdd(a.stats + tid, (double)s_sum[tid]);
-            atomicAdd(a.stats + a.Cout + tid, (double)s_sq[tid]);
+            double* st = a.stats + (size_t)(blockIdx.x % kStatSlots) * 2 * a.Cout;
+            atomicAdd(st + tid, (double)s_sum[tid]);
+            atomicAdd(st + a.Cout + tid, (double)s_sq[tid]);
         }
     }
 }
 
 template <int BN>
 size_t fwd2t_smem(int Kpad) {
-    return (size_t)NSTT * 128 * AST * 4 + (size_t)2 * BN * (Kpad + 4) * 4 + (size_t)2 * Kpad * 4 + (size_t)2 * BN * 4;
+    return (size_t)NSTT * 128 * AST * 4 + (size_t)BN * (Kpad + 4) * 4 + (size_t)2 * Kpad * 4 + (size_t)2 * BN * 4;
 }
 
 template <int BN>
@@ -652,7 +655,7 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad2_kernel(const WgradArgs a, 
         for (int e = 0; e < 4; ++e) {
             const int co = wco * 16 + g + (e >= 2 ? 8 : 0);
             const int k = (wci * NT + nt) * 8 + 2 * t + (e & 1);
-            if (co < C && k < Ktot) atomicAdd(a.dW + (int64_t)co * Ktot + k, acc[nt][e]);
+            if (co < C && k < Ktot) atomicAdd(a.dW + a.slot_stride * (blockIdx.x % kGradSlots) + (int64_t)co * Ktot + k, acc[nt][e]);
         }
     }
 }
@@ -736,7 +739,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_small_kernel(const WgradArgs a
 #pragma unroll
         for (int j = 0; j < 4; ++j) atomicAdd(&red[(a0 + i) * F + b0 + j], acc[i][j]);
     __syncthreads();
-    for (int i = tid; i < F * F; i += kThreads) atomicAdd(a.dW + i, red[i]);
+    for (int i = tid; i < F * F; i += kThreads) atomicAdd(a.dW + a.slot_stride * (blockIdx.x % kGradSlots) + i, red[i]);
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

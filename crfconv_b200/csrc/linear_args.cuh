@@ -46,12 +46,16 @@ struct WgradArgs {
     float* dbias;         // [Cout] or null: += Σ_m dH
     int64_t M; int Cout;
     int64_t rows_per_cta;
+    int64_t slot_stride;  // 0, or Cout·Ktot when dW points at [kGradSlots][Cout·Ktot] partial slots
 };
 
 // fast-path launchers (linear2.cu); return true when the shape was handled
 bool try_fwd2(const FwdArgs& a, int precision, cudaStream_t st, int* rc);
 bool try_dgrad2(const DgradArgs& a, int precision, cudaStream_t st, int* rc);
 bool try_wgrad2(const WgradArgs& a, int precision, cudaStream_t st, int* rc);
+// CUDA-core kernels for hidden-width layers (linear_narrow.cu); w == nullptr ⇒ dgrad only
+bool try_narrow_fwd(const FwdArgs& a, cudaStream_t st, int* rc);
+bool try_narrow_bwd(const DgradArgs& d, const WgradArgs* w, cudaStream_t st, int* rc);
 
 }  // namespace lin
 }  // namespace crf

@@ -11,6 +11,8 @@ from . import _lib
 
 # 0 = 3xTF32 (fp32-grade, default: matches the fp32 reference to ~1e-6), 1 = single-pass TF32
 PRECISION = int(os.environ.get("CRFCONV_PRECISION", "0"))
+STAT_SLOTS = 512     # include/crfconv_b200.h: CRFCONV_STAT_SLOTS
+GRAD_SLOTS = 32      # CRFCONV_GRAD_SLOTS
 
 
 COUNTERS = {"launches": 0}       # number of crfconv_b200 kernels launched (bench.py's gpu_launches)
@@ -84,7 +86,7 @@ class BN:
 
     def __init__(self, C, device, stats=None):
         self.C = C
-        self.stats = stats if stats is not None else torch.zeros(2 * C, dtype=torch.float64, device=device)   # must be zeroed
+        self.stats = stats if stats is not None else torch.zeros(STAT_SLOTS * 2 * C, dtype=torch.float64, device=device)   # zeroed
         buf = torch.empty(6, C, dtype=torch.float32, device=device)
         self.scale, self.shift, self.mean, self.invstd, self.k1, self.k2 = buf.unbind(0)
         self.count = 0
@@ -150,10 +152,10 @@ def bn_act_fwd(H, bn: BN, slope, R=None, out=None):
 
 def bn_backward_prepare(dY, H, bn: BN, slope, dgamma, dbeta, act_ref=None, sums=None):
     """Reduces Σ dV and Σ dV·Ĥ, accumulates dγ / dβ and fills bn.k1 / bn.k2 for the on-the-fly dH transform.
-    `sums` (optional) = zero-initialised f64 scratch of 2·C entries."""
+    `sums` (optional) = zero-initialised f64 scratch of STAT_SLOTS·2·C entries."""
     L = _lib.lib()
     if sums is None:
-        sums = torch.zeros(2 * bn.C, dtype=torch.float64, device=H.device)
+        sums = torch.zeros(STAT_SLOTS * 2 * bn.C, dtype=torch.float64, device=H.device)
     with _call(f"bn_bwd_reduce[{bn.C}]", 1, _nbytes(dY, H, act_ref)):
         rc = L.crfconv_bn_bwd_reduce(_p(dY), _p(H), _p(act_ref), _p(bn.scale), _p(bn.shift), _p(bn.mean), _p(bn.invstd), float(slope),
                                      _p(sums), H.shape[0], bn.C, _lib.stream_ptr())
@@ -167,29 +169,33 @@ def bn_backward_prepare(dY, H, bn: BN, slope, dgamma, dbeta, act_ref=None, sums=
 
 
 def linear_bwd(dY, H, bn, slope, X1, W, *, scale1=None, shift1=None, slope1=1.0, idx1=None, rows_dst=0, rows_src=0, X2=None,
-               dX1=None, acc1=False, dX2=None, acc2=False, dW=None, dbias=None, act_ref=None):
+               dX1=None, acc1=False, dX2=None, acc2=False, dW=None, dbias=None, act_ref=None, scratch=None):
     """bn = BN (after bn_backward_prepare) or None for a plain Linear."""
     L = _lib.lib()
     C1 = X1.shape[1]
     C2 = X2.shape[1] if X2 is not None else 0
     M, Cout = dY.shape
     b = bn
+    if dW is not None and Cout * (C1 + C2) > 1024:
+        scratch = None      # wide outputs: a CTA's adds are spread over >1024 addresses, direct atomics are cheaper than a reduce pass
+    elif dW is not None and scratch is None:
+        scratch = torch.zeros(GRAD_SLOTS * Cout * (C1 + C2), dtype=torch.float32, device=dY.device)
     nb = _nbytes(dY, H if b else None, act_ref, X1 if dW is not None else None, X2 if dW is not None else None, dX1, dX2,
                  dX1 if acc1 else None, dX2 if acc2 else None)
     with _call(f"linear_bwd[{Cout}<-{C1 + C2}]" + ("" if dW is not None else ":dgrad") + ("" if (dX1 is not None or dX2 is not None) else ":wgrad"),
-               int(dW is not None) + int(dX1 is not None or dX2 is not None), nb):
+               int(dW is not None) + int(scratch is not None) + int(dX1 is not None or dX2 is not None), nb):
         rc = _linear_bwd_call(L, dY, H, act_ref, b, slope, X1, C1, scale1, shift1, slope1, idx1, rows_dst, rows_src, X2, C2, W, dX1, acc1,
-                              dX2, acc2, dW, dbias, M, Cout)
+                              dX2, acc2, dW, dbias, scratch, M, Cout)
     _lib.check(rc, "linear_bwd")
 
 
 def _linear_bwd_call(L, dY, H, act_ref, b, slope, X1, C1, scale1, shift1, slope1, idx1, rows_dst, rows_src, X2, C2, W, dX1, acc1, dX2, acc2,
-                     dW, dbias, M, Cout):
+                     dW, dbias, scratch, M, Cout):
     return L.crfconv_linear_bwd(_p(dY), _p(H), _p(act_ref), _p(b.scale) if b else None, _p(b.shift) if b else None,
                               _p(b.mean) if b else None, _p(b.invstd) if b else None, _p(b.k1) if b else None,
                               _p(b.k2) if b else None, float(slope),
                               _p(X1), C1, _p(scale1), _p(shift1), float(slope1), _p(idx1), int(rows_dst), int(rows_src), _p(X2), C2,
-                              _p(W), _p(dX1), int(acc1), _p(dX2), int(acc2), _p(dW), _p(dbias), int(M), int(Cout), PRECISION,
+                              _p(W), _p(dX1), int(acc1), _p(dX2), int(acc2), _p(dW), _p(dbias), _p(scratch), int(M), int(Cout), PRECISION,
                               _lib.stream_ptr())
 
 

@@ -74,9 +74,13 @@ int crfconv_grid_subsample_host(const float* points, int64_t N, const float* fea
  * generic 3xTF32 kernels otherwise), 0 = generic only, 1 = fast whenever the shape allows.  Returns the previous mode. */
 int crfconv_set_fast_path(int mode);
 
+#define CRFCONV_STAT_SLOTS 512 /* Σ/Σ² buffers (`stats`, `sums`) are [CRFCONV_STAT_SLOTS][2·C] doubles, zero-initialised by the caller */
+#define CRFCONV_GRAD_SLOTS 32
+
 /* Y[M,Cout] = [ lrelu(X1*scale1 + shift1, slope1) | X2 ] · Wᵀ (+ bias).  scale1 == NULL ⇒ X1 is used as is.
  * idx1 != NULL ⇒ X1 rows are gathered: source row of output row m is (m / rows_dst) * rows_src + idx1[m]
- * (point_conv_big.py:97-101).  stats != NULL ⇒ stats[0:Cout] += Σ_rows Y, stats[Cout:2Cout] += Σ_rows Y² (f64). */
+ * (point_conv_big.py:97-101).  stats != NULL ⇒ Σ_rows Y and Σ_rows Y² (f64) are accumulated into the slotted
+ * partial buffer stats[CRFCONV_STAT_SLOTS][2·Cout] (CTA b adds into slot b % SLOTS); crfconv_bn_finalize_fwd sums the slots. */
 int crfconv_linear_fwd(const float* X1, int C1, const float* scale1, const float* shift1, float slope1, const int64_t* idx1,
                        int64_t rows_dst, int64_t rows_src, const float* X2, int C2, const float* W, const float* bias, float* Y,
                        double* stats, int64_t M, int Cout, int precision, void* stream);
@@ -92,23 +96,24 @@ int crfconv_bn_finalize_fwd(const double* stats, int64_t count, const float* gam
 int crfconv_bn_act_fwd(const float* H, const float* scale, const float* shift, const float* R, float slope, float* Y, int64_t M,
                        int C, void* stream);
 
-/* BatchNorm backward reductions: sums[0:C] += Σ dV, sums[C:2C] += Σ dV·Ĥ, dV = dY·lrelu'(pre), Ĥ = (H−mean)·invstd,
+/* BatchNorm backward reductions into sums[CRFCONV_STAT_SLOTS][2·C]: [0:C] += Σ dV, [C:2C] += Σ dV·Ĥ, dV = dY·lrelu'(pre), Ĥ = (H−mean)·invstd,
  * pre = act_ref ? act_ref : H*scale+shift. */
 int crfconv_bn_bwd_reduce(const float* dY, const float* H, const float* act_ref, const float* scale, const float* shift,
                           const float* mean, const float* invstd, float slope, double* sums, int64_t M, int C, void* stream);
 
-/* k1 = sums[0:C]/count, k2 = sums[C:2C]/count; dgamma += sums[C:2C], dbeta += sums[0:C] (either may be NULL). */
+/* Sums the slots: k1 = Σ dV / count, k2 = Σ dV·Ĥ / count; dgamma += Σ dV·Ĥ, dbeta += Σ dV (either may be NULL). */
 int crfconv_bn_finalize_bwd(const double* sums, int64_t count, float* k1, float* k2, float* dgamma, float* dbeta, int C, void* stream);
 
 /* Backward of crfconv_linear_fwd.  dY is the gradient wrt the layer's activation output; the BN(+LeakyReLU) backward
  * dH = scale·(dV − k1 − Ĥ·k2) is applied on the fly (scale == NULL ⇒ no BN, dH = dY).  Produces dX1 [M,C1] / dX2 [M,C2]
  * (gradients wrt the post-prologue inputs; NULL ⇒ skipped; acc ⇒ +=), dW [Cout,C1+C2] += dHᵀ·[prologue(X1)|X2],
- * dbias += Σ dH (NULL ⇒ skipped). */
+ * dbias += Σ dH (NULL ⇒ skipped).  dW_scratch (optional): CRFCONV_GRAD_SLOTS·Cout·(C1+C2) zero-initialised floats; when given,
+ * CTAs accumulate into per-slot partial copies that a follow-up kernel sums into dW (same-address atomics serialise in L2). */
 int crfconv_linear_bwd(const float* dY, const float* H, const float* act_ref, const float* scale, const float* shift,
                        const float* mean, const float* invstd, const float* k1, const float* k2, float slope,
                        const float* X1, int C1, const float* scale1, const float* shift1, float slope1, const int64_t* idx1,
                        int64_t rows_dst, int64_t rows_src, const float* X2, int C2, const float* W, float* dX1, int acc1,
-                       float* dX2, int acc2, float* dW, float* dbias, int64_t M, int Cout, int precision, void* stream);
+                       float* dX2, int acc2, float* dW, float* dbias, float* dW_scratch, int64_t M, int Cout, int precision, void* stream);
 
 /* ------------------------------------------------------------------------ continuous-CRF mean-field
  * Replaces the body of ContinuousGaussianCRFConv.forward, models/continuous_crf_conv_big.py:56-72 (and its autograd

@@ -53,7 +53,8 @@ def test_linear_fwd_and_bwd(ops, fast, M, C1, C2, Cout):
             A = torch.cat([A, X2.double()], 1)
         Href = A @ W.double().t()
         assert rel(H, Href) < ftol
-        assert rel(bn.stats[:Cout], Href.sum(0)) < 1e-4 and rel(bn.stats[Cout:], (Href ** 2).sum(0)) < 1e-4
+        st = bn.stats.view(-1, 2 * Cout).sum(0)                 # slotted partial sums (CRFCONV_STAT_SLOTS)
+        assert rel(st[:Cout], Href.sum(0)) < 1e-4 and rel(st[Cout:], (Href ** 2).sum(0)) < 1e-4
         ops.bn_finalize_fwd(bn, M, gamma, beta, 1e-5, 0.1, True, None, None)
         mu, var = Href.mean(0), Href.var(0, unbiased=False)
         assert rel(bn.mean, mu) < 1e-4 and rel(bn.invstd, (var + 1e-5).rsqrt()) < 1e-4
