@@ -155,7 +155,9 @@ def run_gpu(args, rank, local_rank, world):
     with torch.no_grad():
         layer.c.add_(0.1 * torch.randn_like(layer.c))
     from crfconv_b200.distributed import FlatGradients
-    fg = FlatGradients(layer)          # all parameter gradients are views of ONE contiguous buffer → one all-reduce, no copies
+    # bind=False: autograd adopts the gradient tensors the fused layer returns — views of ONE flat allocation — so there is no
+    # accumulate kernel per parameter, and the all-reduce runs in place on that allocation (one collective, no copies)
+    fg = FlatGradients(layer, bind=False)
 
     in_bytes = B * (4 * ((N_POINTS // RATIO) * CU + N_POINTS * CP) + 8 * N_POINTS * (K_NBR + 1))
     nsets = max(2, -(-2 * L2_BYTES // max(in_bytes, 1)))     # rotate enough input sets that a step never finds its inputs in L2

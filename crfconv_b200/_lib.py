@@ -29,8 +29,9 @@ SIGNATURES = {
     "crfconv_bn_bwd_reduce": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _i64, _int, _vp]),
     "crfconv_bn_finalize_bwd": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _int, _vp]),
     "crfconv_linear_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32,
-                                  _vp, _int, _vp, _vp, _f32, _vp, _i64, _i64, _vp, _int, _vp, _vp, _int, _vp, _int, _vp, _vp, _vp,
+                                  _vp, _int, _vp, _vp, _f32, _vp, _i64, _i64, _vp, _int, _vp, _vp, _int, _vp, _int, _vp, _vp, _vp, _i64,
                                   _i64, _int, _int, _vp]),
+    "crfconv_grad_slots_reduce": (_int, [_vp, _vp, _i64, _i64, _vp]),
     "crfconv_relpos": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
     "crfconv_pointconv_aggregate_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _vp]),
     "crfconv_pointconv_aggregate_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _vp]),

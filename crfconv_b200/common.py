@@ -42,8 +42,10 @@ def _slope_of(activation):
     return None
 
 
-def bn_forward_state(C, device, count, bn_module, training, stats=None):
-    """Allocates the per-call BN scratch; returns (state, finalize) where finalize() must run after the producing GEMM."""
+def bn_forward_state(C, device, count, bn_module, training, stats=None, defer_counters=None):
+    """Allocates the per-call BN scratch; returns (state, finalize) where finalize() must run after the producing GEMM.
+    `defer_counters` (a list): collect the num_batches_tracked buffers instead of bumping each with its own kernel; the caller
+    bumps them all with one torch._foreach_add_."""
     st = ops.BN(C, device, stats)
 
     def finalize():
@@ -51,7 +53,10 @@ def bn_forward_state(C, device, count, bn_module, training, stats=None):
                             bn_module.momentum if bn_module.momentum is not None else 0.1, training,
                             bn_module.running_mean, bn_module.running_var)
         if training and bn_module.track_running_stats and bn_module.num_batches_tracked is not None:
-            bn_module.num_batches_tracked.add_(1)
+            if defer_counters is not None:
+                defer_counters.append(bn_module.num_batches_tracked)
+            else:
+                bn_module.num_batches_tracked.add_(1)
     return st, finalize
 
 

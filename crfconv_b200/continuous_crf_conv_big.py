@@ -46,16 +46,17 @@ class _CRFConvFunction(torch.autograd.Function):
         def tr(bn):
             return training or not bn.track_running_stats
 
-        fstats = ops.Flat(ops.STAT_SLOTS * 2 * (4 * F + 2 * Co), torch.float64, dev)
+        fstats = ops.Flat(ops.STAT_SLOTS * 2 * (4 * F + 2 * Co), torch.float32, dev)
+        nbt = []
 
         # unary_nn / pairwise_nn, layer 1 and 2 (:58-59)
-        s1u, fin = bn_forward_state(F, dev, Mc, bns[0], tr(bns[0]), fstats.take(ops.STAT_SLOTS * 2 * F))
+        s1u, fin = bn_forward_state(F, dev, Mc, bns[0], tr(bns[0]), fstats.take(ops.STAT_SLOTS * 2 * F), nbt)
         H1u = ops.linear_fwd(U, W1u, stats=s1u.stats); fin()
-        s1p, fin = bn_forward_state(F, dev, M, bns[2], tr(bns[2]), fstats.take(ops.STAT_SLOTS * 2 * F))
+        s1p, fin = bn_forward_state(F, dev, M, bns[2], tr(bns[2]), fstats.take(ops.STAT_SLOTS * 2 * F), nbt)
         H1p = ops.linear_fwd(P, W1p, stats=s1p.stats); fin()
-        s2u, fin = bn_forward_state(F, dev, Mc, bns[1], tr(bns[1]), fstats.take(ops.STAT_SLOTS * 2 * F))
+        s2u, fin = bn_forward_state(F, dev, Mc, bns[1], tr(bns[1]), fstats.take(ops.STAT_SLOTS * 2 * F), nbt)
         H2u = ops.linear_fwd(H1u, W2u, scale1=s1u.scale, shift1=s1u.shift, slope1=sl[0], stats=s2u.stats); fin()
-        s2p, fin = bn_forward_state(F, dev, M, bns[3], tr(bns[3]), fstats.take(ops.STAT_SLOTS * 2 * F))
+        s2p, fin = bn_forward_state(F, dev, M, bns[3], tr(bns[3]), fstats.take(ops.STAT_SLOTS * 2 * F), nbt)
         H2p = ops.linear_fwd(H1p, W2p, scale1=s1p.scale, shift1=s1p.shift, slope1=sl[2], stats=s2p.stats); fin()
         # mean field (:60-72)
         cc = c.detach().contiguous().float()
@@ -65,11 +66,13 @@ class _CRFConvFunction(torch.autograd.Function):
         for _ in range(steps):
             xs.append(ops.crf_step_fwd(H2p, s2p.scale, z, xs[-1], nbr, Cm, Minv, B, N, K))
         # out_nn, fusion_nn (:74-76)
-        so, fin = bn_forward_state(Co, dev, M, bns[4], tr(bns[4]), fstats.take(ops.STAT_SLOTS * 2 * Co))
+        so, fin = bn_forward_state(Co, dev, M, bns[4], tr(bns[4]), fstats.take(ops.STAT_SLOTS * 2 * Co), nbt)
         H3 = ops.linear_fwd(xs[-1], Wo, stats=so.stats); fin()
-        sf, fin = bn_forward_state(Co, dev, M, bns[5], tr(bns[5]), fstats.take(ops.STAT_SLOTS * 2 * Co))
+        sf, fin = bn_forward_state(Co, dev, M, bns[5], tr(bns[5]), fstats.take(ops.STAT_SLOTS * 2 * Co), nbt)
         Hf = ops.linear_fwd(H3, Wf, scale1=so.scale, shift1=so.shift, slope1=sl[4], X2=P, stats=sf.stats); fin()
         out = ops.bn_act_fwd(Hf, sf, sl[5])
+        if nbt:
+            torch._foreach_add_(nbt, 1)                  # six num_batches_tracked counters, one launch
 
         ctx.dims = (B, N, Nc, K, F, Co, Cu, Cp, steps)
         ctx.bn = (s1u, s2u, s1p, s2p, so, sf)
@@ -90,33 +93,52 @@ class _CRFConvFunction(torch.autograd.Function):
 
         wl = (("1u", W1u), ("2u", W2u), ("1p", W1p), ("2p", W2p), ("o", Wo), ("f", Wf))
         cl = (("1u", F), ("2u", F), ("1p", F), ("2p", F), ("o", Co), ("f", Co))
-        small = ops.Flat(sum(w.numel() for _, w in wl) + 2 * sum(n for _, n in cl) + 3 * F * F, torch.float32, dev)
-        sums = ops.Flat(ops.STAT_SLOTS * 2 * sum(n for _, n in cl), torch.float64, dev)
-        wscr = ops.Flat(ops.GRAD_SLOTS * (sum(w.numel() for _, w in wl) + 2 * steps * F * F), torch.float32, dev)   # dW partial slots
-        big = ops.Flat((steps + 1) * M * F + Mc * F, torch.float32, dev)       # scatter targets: Gy, gprev per step, Gu
-        zeros = small.take
-        dW = {k: small.take(*w.shape) for k, w in wl}
-        dg = {k: small.take(n) for k, n in cl}
-        db = {k: small.take(n) for k, n in cl}
+        n_small = sum(w.numel() for _, w in wl) + 2 * sum(n for _, n in cl) + 3 * F * F
+        n_sums = ops.STAT_SLOTS * 2 * sum(n for _, n in cl)
+        n_big = (steps + 1) * M * F + Mc * F
+        # ONE zero-filled allocation: [small grads | weight-grad partial slots | BN-backward Σ slots | scatter targets]
+        flat = ops.Flat(n_small * (1 + ops.GRAD_SLOTS) + n_sums + n_big, torch.float32, dev)
+        small = flat.take(n_small)
+        wscr = flat.take(ops.GRAD_SLOTS * n_small)          # slot pitch n_small: same layout as `small`, folded by one reduce at the end
+        sums = ops.Flat.__new__(ops.Flat); sums.buf, sums.off = flat.take(n_sums), 0
+        big = ops.Flat.__new__(ops.Flat); big.buf, big.off = flat.take(n_big), 0
+        cursor = [0]
 
+        def take_small(*shape):
+            n = 1
+            for d in shape:
+                n *= int(d)
+            v = small[cursor[0]:cursor[0] + n].view(*shape)
+            cursor[0] += n
+            return v
+
+        def scr(t):                                          # partial-slot region that mirrors the small-gradient view `t`
+            return wscr[(t.data_ptr() - small.data_ptr()) // 4:]
+
+        zeros = take_small
+        GC, GM = take_small(F, F), take_small(F, F)         # first in the layout: folded on their own before the c-gradient algebra
+        dW = {k: take_small(*w.shape) for k, w in wl}
+        dg = {k: take_small(n) for k, n in cl}
+        db = {k: take_small(n) for k, n in cl}
         # fusion_nn
         ops.bn_backward_prepare(g2, Hf, sf, sl[5], dg["f"], db["f"], sums=sums.take(ops.STAT_SLOTS * 2 * Co))
         dO = torch.empty((M, Co), dtype=torch.float32, device=dev)
         dP = torch.empty((M, Cp), dtype=torch.float32, device=dev)
-        ops.linear_bwd(g2, Hf, sf, sl[5], H3, Wf, scale1=so.scale, shift1=so.shift, slope1=sl[4], X2=P, dX1=dO, dX2=dP, dW=dW["f"], scratch=wscr.take(ops.GRAD_SLOTS * Wf.numel()))
+        ops.linear_bwd(g2, Hf, sf, sl[5], H3, Wf, scale1=so.scale, shift1=so.shift, slope1=sl[4], X2=P, dX1=dO, dX2=dP, dW=dW["f"], scratch=scr(dW["f"]), scratch_stride=n_small)
         # out_nn
         ops.bn_backward_prepare(dO, H3, so, sl[4], dg["o"], db["o"], sums=sums.take(ops.STAT_SLOTS * 2 * Co))
         g = torch.empty((M, F), dtype=torch.float32, device=dev)
-        ops.linear_bwd(dO, H3, so, sl[4], xs[-1], Wo, dX1=g, dW=dW["o"], scratch=wscr.take(ops.GRAD_SLOTS * Wo.numel()))
+        ops.linear_bwd(dO, H3, so, sl[4], xs[-1], Wo, dX1=g, dW=dW["o"], scratch=scr(dW["o"]), scratch_stride=n_small)
         # mean-field steps, last to first
-        Gy, GC, GM = big.take(M, F), zeros(F, F), zeros(F, F)
+        Gy = big.take(M, F)
         Gz, m_out, v_out, h_out = (torch.empty((M, F), dtype=torch.float32, device=dev) for _ in range(4))
         for t in range(steps, 0, -1):
             gprev = big.take(M, F)
             ops.crf_step_bwd(H2p, s2p.scale, z, xs[t - 1], nbr, Cm, Minv, g, Gz, gprev, Gy, m_out, v_out, h_out, t != steps, B, N, K)
-            ops.linear_bwd(m_out, None, None, 1.0, h_out, GC, dW=GC, scratch=wscr.take(ops.GRAD_SLOTS * F * F))      # GC += mᵀ·h
-            ops.linear_bwd(v_out, None, None, 1.0, g, GM, dW=GM, scratch=wscr.take(ops.GRAD_SLOTS * F * F))          # GM += vᵀ·g
+            ops.linear_bwd(m_out, None, None, 1.0, h_out, GC, dW=GC, scratch=scr(GC), scratch_stride=n_small)      # GC += mᵀ·h
+            ops.linear_bwd(v_out, None, None, 1.0, g, GM, dW=GM, scratch=scr(GM), scratch_stride=n_small)          # GM += vᵀ·g
             g = gprev
+        ops.grad_slots_reduce(wscr, small, 2 * F * F, n_small)    # fold the GC / GM partial slots
         Gc = zeros(F, F)
         ops.crf_compat_bwd(cc, Minv, GC, GM, Gc)
         Gu = big.take(Mc, F)
@@ -127,18 +149,19 @@ class _CRFConvFunction(torch.autograd.Function):
         # unary_nn
         ops.bn_backward_prepare(Gu, H2u, s2u, 1.0, dg["2u"], db["2u"], sums=sums.take(ops.STAT_SLOTS * 2 * F))
         dA = torch.empty((Mc, F), dtype=torch.float32, device=dev)
-        ops.linear_bwd(Gu, H2u, s2u, 1.0, H1u, W2u, scale1=s1u.scale, shift1=s1u.shift, slope1=sl[0], dX1=dA, dW=dW["2u"], scratch=wscr.take(ops.GRAD_SLOTS * W2u.numel()))
+        ops.linear_bwd(Gu, H2u, s2u, 1.0, H1u, W2u, scale1=s1u.scale, shift1=s1u.shift, slope1=sl[0], dX1=dA, dW=dW["2u"], scratch=scr(dW["2u"]), scratch_stride=n_small)
         ops.bn_backward_prepare(dA, H1u, s1u, sl[0], dg["1u"], db["1u"], sums=sums.take(ops.STAT_SLOTS * 2 * F))
         dU = torch.empty((Mc, Cu), dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
-        ops.linear_bwd(dA, H1u, s1u, sl[0], U, W1u, dX1=dU, dW=dW["1u"], scratch=wscr.take(ops.GRAD_SLOTS * W1u.numel()))
+        ops.linear_bwd(dA, H1u, s1u, sl[0], U, W1u, dX1=dU, dW=dW["1u"], scratch=scr(dW["1u"]), scratch_stride=n_small)
         # pairwise_nn (its input gradient accumulates onto the fusion_nn branch)
         ops.bn_backward_prepare(Gy, H2p, s2p, 1.0, dg["2p"], db["2p"], sums=sums.take(ops.STAT_SLOTS * 2 * F))
         dA = torch.empty((M, F), dtype=torch.float32, device=dev)
-        ops.linear_bwd(Gy, H2p, s2p, 1.0, H1p, W2p, scale1=s1p.scale, shift1=s1p.shift, slope1=sl[2], dX1=dA, dW=dW["2p"], scratch=wscr.take(ops.GRAD_SLOTS * W2p.numel()))
+        ops.linear_bwd(Gy, H2p, s2p, 1.0, H1p, W2p, scale1=s1p.scale, shift1=s1p.shift, slope1=sl[2], dX1=dA, dW=dW["2p"], scratch=scr(dW["2p"]), scratch_stride=n_small)
         ops.bn_backward_prepare(dA, H1p, s1p, sl[2], dg["1p"], db["1p"], sums=sums.take(ops.STAT_SLOTS * 2 * F))
         need_p = ctx.needs_input_grad[1]
-        ops.linear_bwd(dA, H1p, s1p, sl[2], P, W1p, dX1=dP if need_p else None, acc1=True, dW=dW["1p"], scratch=wscr.take(ops.GRAD_SLOTS * W1p.numel()))
+        ops.linear_bwd(dA, H1p, s1p, sl[2], P, W1p, dX1=dP if need_p else None, acc1=True, dW=dW["1p"], scratch=scr(dW["1p"]), scratch_stride=n_small)
 
+        ops.grad_slots_reduce(wscr[2 * F * F:], small[2 * F * F:], n_small - 2 * F * F, n_small)   # all weight gradients, one launch
         grads = []
         for k in ("1u", "2u", "1p", "2p", "o", "f"):
             grads += [dW[k], dg[k], db[k]]

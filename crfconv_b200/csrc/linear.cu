@@ -172,9 +172,9 @@ __global__ void __launch_bounds__(kThreads) fwd_kernel(const FwdArgs a) {
     if (a.stats) {
         __syncthreads();
         if (tid < BN && n0 + tid < a.Cout) {
-            double* st = a.stats + (size_t)(blockIdx.x % kStatSlots) * 2 * a.Cout;
-            atomicAdd(st + n0 + tid, (double)s_sum[tid]);
-            atomicAdd(st + a.Cout + n0 + tid, (double)s_sq[tid]);
+            float* st = a.stats + (size_t)(blockIdx.x % kStatSlots) * 2 * a.Cout;
+            atomicAdd(st + n0 + tid, s_sum[tid]);
+            atomicAdd(st + a.Cout + n0 + tid, s_sq[tid]);
         }
     }
 }
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kThreads) fwd_kernel(const FwdArgs a) {
 // ------------------------------------------------------------------------------- BatchNorm bookkeeping
 // Training: batch statistics from Σ / Σ² → scale/shift (+ saved mean / invstd, running-stat update with momentum and
 // unbiased variance, exactly nn.BatchNorm1d).  Eval: scale/shift from the running statistics.
-__global__ void __launch_bounds__(128) bn_finalize_fwd_kernel(const double* __restrict__ stats, double count, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(128) bn_finalize_fwd_kernel(const float* __restrict__ stats, double count, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, float eps, float momentum, int training,
                                        float* running_mean, float* running_var, float* __restrict__ scale,
                                        float* __restrict__ shift, float* __restrict__ mean_out, float* __restrict__ invstd_out, int C) {
@@ -192,8 +192,8 @@ __global__ void __launch_bounds__(128) bn_finalize_fwd_kernel(const double* __re
     double s1 = 0.0, s2 = 0.0;
     if (training) {
         for (int p = threadIdx.x; p < kStatSlots; p += blockDim.x) {
-            s1 += stats[(size_t)p * 2 * C + c];
-            s2 += stats[(size_t)p * 2 * C + C + c];
+            s1 += (double)stats[(size_t)p * 2 * C + c];
+            s2 += (double)stats[(size_t)p * 2 * C + C + c];
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
@@ -255,7 +255,7 @@ __device__ __forceinline__ float bn_dv(float dy, float h, float ref, bool has_re
 
 // s1[c] = Σ_rows dV, s2[c] = Σ_rows dV·Ĥ (double atomics).  C % 4 == 0, C <= 1024.
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ dY, const float* __restrict__ H, BnBwd bn,
-                                                            double* __restrict__ sums, int64_t M, int C) {
+                                                            float* __restrict__ sums, int64_t M, int C) {
     __shared__ float red[256 * 8];
     const int C4 = C >> 2;
     const int tpr = C4;                           // threads per row
@@ -303,19 +303,19 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
         float tot = 0.0f;
         for (int r = 0; r < rows_per_it; ++r) tot += red[(r * tpr + cs) * 8 + e];
         const int c = cs * 4 + (e & 3);
-        atomicAdd(sums + (size_t)(blockIdx.x % kStatSlots) * 2 * C + (e < 4 ? 0 : C) + c, (double)tot);
+        atomicAdd(sums + (size_t)(blockIdx.x % kStatSlots) * 2 * C + (e < 4 ? 0 : C) + c, tot);
     }
 }
 
 // k1 = s1/M, k2 = s2/M; dγ += s2, dβ += s1.
-__global__ void __launch_bounds__(128) bn_finalize_bwd_kernel(const double* __restrict__ sums, double count, float* __restrict__ k1, float* __restrict__ k2,
+__global__ void __launch_bounds__(128) bn_finalize_bwd_kernel(const float* __restrict__ sums, double count, float* __restrict__ k1, float* __restrict__ k2,
                                        float* dgamma, float* dbeta, int C) {
     __shared__ double r1[4], r2[4];
     const int c = blockIdx.x;
     double s1 = 0.0, s2 = 0.0;
     for (int p = threadIdx.x; p < kStatSlots; p += blockDim.x) {
-        s1 += sums[(size_t)p * 2 * C + c];
-        s2 += sums[(size_t)p * 2 * C + C + c];
+        s1 += (double)sums[(size_t)p * 2 * C + c];
+        s2 += (double)sums[(size_t)p * 2 * C + C + c];
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
@@ -331,12 +331,12 @@ __global__ void __launch_bounds__(128) bn_finalize_bwd_kernel(const double* __re
 }
 
 // dW[i] += Σ_slots scratch[slot][i]   (fixed order ⇒ deterministic for a given launch configuration)
-__global__ void __launch_bounds__(256) grad_slots_reduce_kernel(const float* __restrict__ scratch, float* dW, int n) {
+__global__ void __launch_bounds__(256) grad_slots_reduce_kernel(const float* __restrict__ scratch, float* dW, int n, int64_t stride) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float s = 0.f;
 #pragma unroll 8
-    for (int p = 0; p < kGradSlots; ++p) s += scratch[(size_t)p * n + i];
+    for (int p = 0; p < kGradSlots; ++p) s += scratch[(size_t)p * stride + i];
     dW[i] += s;
 }
 
@@ -600,7 +600,7 @@ int crfconv_set_fast_path(int mode) {
 // precision: 0 = 3xTF32 (fp32-grade), 1 = single-pass TF32.
 int crfconv_linear_fwd(const float* X1, int C1, const float* scale1, const float* shift1, float slope1, const int64_t* idx1,
                        int64_t rows_dst, int64_t rows_src, const float* X2, int C2, const float* W, const float* bias, float* Y,
-                       double* stats, int64_t M, int Cout, int precision, void* stream) {
+                       float* stats, int64_t M, int Cout, int precision, void* stream) {
     if (M < 0 || Cout <= 0 || C1 < 0 || C2 < 0 || C1 + C2 <= 0) return CRF_ERR_INVALID_ARG;
     if (M == 0) return CRF_OK;
     if ((C1 > 0 && !X1) || (C2 > 0 && !X2) || !W || !Y) return CRF_ERR_INVALID_ARG;
@@ -623,7 +623,7 @@ int crfconv_linear_fwd(const float* X1, int C1, const float* scale1, const float
     });
 }
 
-int crfconv_bn_finalize_fwd(const double* stats, int64_t count, const float* gamma, const float* beta, float eps, float momentum,
+int crfconv_bn_finalize_fwd(const float* stats, int64_t count, const float* gamma, const float* beta, float eps, float momentum,
                             int training, float* running_mean, float* running_var, float* scale, float* shift, float* mean,
                             float* invstd, int C, void* stream) {
     if (C <= 0 || !scale || !shift || (training && !stats) || (!training && (!running_mean || !running_var))) return CRF_ERR_INVALID_ARG;
@@ -647,20 +647,30 @@ int crfconv_bn_act_fwd(const float* H, const float* scale, const float* shift, c
 
 // sums[0:C] += Σ dV, sums[C:2C] += Σ dV·Ĥ with dV = dY·lrelu'(pre), pre = act_ref ? act_ref : H*scale+shift.
 int crfconv_bn_bwd_reduce(const float* dY, const float* H, const float* act_ref, const float* scale, const float* shift,
-                          const float* mean, const float* invstd, float slope, double* sums, int64_t M, int C, void* stream) {
+                          const float* mean, const float* invstd, float slope, float* sums, int64_t M, int C, void* stream) {
     if (M < 0 || C <= 0 || (C & 3) || C > 1024 || (256 % (C / 4)) != 0) return CRF_ERR_UNSUPPORTED;
     if (M == 0) return CRF_OK;
     lin::BnBwd bn{scale, shift, mean, invstd, nullptr, nullptr, act_ref, slope};
     const int rows_per_it = 256 / (C / 4);
-    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(M, rows_per_it * 8), (int64_t)kNumSMs * 8);
+    static const int mult = [] { const char* e = getenv("CRFCONV_REDUCE_CTAS_PER_SM"); return e ? std::max(1, atoi(e)) : 8; }();
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(M, rows_per_it * 8), (int64_t)kNumSMs * mult);
     lin::bn_bwd_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dY, H, bn, sums, M, C);
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }
 
-int crfconv_bn_finalize_bwd(const double* sums, int64_t count, float* k1, float* k2, float* dgamma, float* dbeta, int C, void* stream) {
+int crfconv_bn_finalize_bwd(const float* sums, int64_t count, float* k1, float* k2, float* dgamma, float* dbeta, int C, void* stream) {
     if (C <= 0 || !sums || !k1 || !k2) return CRF_ERR_INVALID_ARG;
     lin::bn_finalize_bwd_kernel<<<(unsigned)C, 128, 0, (cudaStream_t)stream>>>(sums, (double)count, k1, k2, dgamma, dbeta, C);
+    CRF_LAUNCH_CHECK();
+    return CRF_OK;
+}
+
+// dW[i] += Σ_slots scratch[slot·stride + i], i < n  — one call can fold the partial slots of many layers that share a flat layout.
+int crfconv_grad_slots_reduce(const float* scratch, float* dW, int64_t n, int64_t stride, void* stream) {
+    if (n < 0 || !scratch || !dW || stride < n) return CRF_ERR_INVALID_ARG;
+    if (n == 0) return CRF_OK;
+    lin::grad_slots_reduce_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(scratch, dW, (int)n, stride);
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }
@@ -672,7 +682,8 @@ int crfconv_linear_bwd(const float* dY, const float* H, const float* act_ref, co
                        const float* mean, const float* invstd, const float* k1, const float* k2, float slope,
                        const float* X1, int C1, const float* scale1, const float* shift1, float slope1, const int64_t* idx1,
                        int64_t rows_dst, int64_t rows_src, const float* X2, int C2, const float* W, float* dX1, int acc1,
-                       float* dX2, int acc2, float* dW, float* dbias, float* dW_scratch, int64_t M, int Cout, int precision, void* stream) {
+                       float* dX2, int acc2, float* dW, float* dbias, float* dW_scratch, int64_t dW_scratch_stride, int64_t M, int Cout, int precision,
+                       void* stream) {
     if (M < 0 || Cout <= 0 || C1 < 0 || C2 < 0 || C1 + C2 <= 0 || !dY || !W) return CRF_ERR_INVALID_ARG;
     if (M == 0) return CRF_OK;
     if (scale && (Cout & 3)) return CRF_ERR_UNSUPPORTED;
@@ -682,10 +693,10 @@ int crfconv_linear_bwd(const float* dY, const float* H, const float* act_ref, co
     const int gprec = precision == 2 ? 1 : precision;    // precision seen by the generic (TF32) kernels
     // weight-gradient partial slots: CTAs add into dW_scratch[slot] (zero-initialised by the caller), reduced into dW afterwards
     float* wdst = (dW && dW_scratch) ? dW_scratch : dW;
-    const int64_t wstride = (dW && dW_scratch) ? (int64_t)Cout * Ktot : 0;
+    const int64_t wstride = (dW && dW_scratch) ? (dW_scratch_stride > 0 ? dW_scratch_stride : (int64_t)Cout * Ktot) : 0;
     auto reduce_slots = [&]() -> int {
-        if (dW && dW_scratch) {
-            lin::grad_slots_reduce_kernel<<<(unsigned)ceil_div((int64_t)Cout * Ktot, 256), 256, 0, st>>>(dW_scratch, dW, Cout * Ktot);
+        if (dW && dW_scratch && dW_scratch_stride <= 0) {      // stride given ⇒ the caller reduces all its layers at once
+            lin::grad_slots_reduce_kernel<<<(unsigned)ceil_div((int64_t)Cout * Ktot, 256), 256, 0, st>>>(dW_scratch, dW, Cout * Ktot, (int64_t)Cout * Ktot);
             CRF_LAUNCH_CHECK();
         }
         return CRF_OK;

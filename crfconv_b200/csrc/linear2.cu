@@ -167,9 +167,9 @@ __global__ void __launch_bounds__(kThreads, 2) fwd2_kernel(const FwdArgs a, cons
     if (a.stats) {
         __syncthreads();
         if (tid < BN && tid < a.Cout) {
-            double* st = a.stats + (size_t)(blockIdx.x % kStatSlots) * 2 * a.Cout;
-            atomicAdd(st + tid, (double)s_sum[tid]);
-            atomicAdd(st + a.Cout + tid, (double)s_sq[tid]);
+            float* st = a.stats + (size_t)(blockIdx.x % kStatSlots) * 2 * a.Cout;
+            atomicAdd(st + tid, s_sum[tid]);
+            atomicAdd(st + a.Cout + tid, s_sq[tid]);
         }
     }
 }
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, 2) fwd2_kernel(const FwdArgs a, cons
 // as between two fp32 implementations.  Double-buffered (the tf32 (hi, lo) copy of W is twice the
 // size of the bf16 one); row stride 36 ≡ 4 (mod 32) ⇒ conflict-free scalar fragment loads at (g, t).
 constexpr int AST = 36;
-constexpr int NSTT = 2;
+template <int BN> struct FwdT { static constexpr int NS = BN <= 16 ? 3 : 4; static constexpr int CTAS = BN <= 16 ? 3 : 2; };   // ring depth, CTAs/SM
 
 __device__ __forceinline__ uint32_t tf32_of(float x) {
     uint32_t r;
@@ -194,8 +194,8 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 }
 
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 2) fwd2t_kernel(const FwdArgs a, const int ntiles) {
-    constexpr int BM = 128;
+__global__ void __launch_bounds__(kThreads, FwdT<BN>::CTAS) fwd2t_kernel(const FwdArgs a, const int ntiles) {
+    constexpr int BM = 128, NSTT = FwdT<BN>::NS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nch1 = (a.C1 + BK - 1) / BK, nch2 = (a.C2 + BK - 1) / BK, nch = nch1 + nch2;
     const int Kpad = nch * BK, WS = Kpad + 4;
@@ -326,16 +326,16 @@ __global__ void __launch_bounds__(kThreads, 2) fwd2t_kernel(const FwdArgs a, con
     if (a.stats) {
         __syncthreads();
         if (tid < BN && tid < a.Cout) {
-            double* st = a.stats + (size_t)(blockIdx.x % kStatSlots) * 2 * a.Cout;
-            atomicAdd(st + tid, (double)s_sum[tid]);
-            atomicAdd(st + a.Cout + tid, (double)s_sq[tid]);
+            float* st = a.stats + (size_t)(blockIdx.x % kStatSlots) * 2 * a.Cout;
+            atomicAdd(st + tid, s_sum[tid]);
+            atomicAdd(st + a.Cout + tid, s_sq[tid]);
         }
     }
 }
 
 template <int BN>
 size_t fwd2t_smem(int Kpad) {
-    return (size_t)NSTT * 128 * AST * 4 + (size_t)BN * (Kpad + 4) * 4 + (size_t)2 * Kpad * 4 + (size_t)2 * BN * 4;
+    return (size_t)FwdT<BN>::NS * 128 * AST * 4 + (size_t)BN * (Kpad + 4) * 4 + (size_t)2 * Kpad * 4 + (size_t)2 * BN * 4;
 }
 
 template <int BN>
@@ -350,6 +350,7 @@ template <int BN, bool X3, bool REF>
 __global__ void __launch_bounds__(kThreads, (BN >= 128 || REF) ? 1 : 2) dgrad2_kernel(const DgradArgs a, const int ntiles) {
     constexpr int WC = BN >= 64 ? 2 : 1, WR = 8 / WC, BM = 16 * WR, NT = BN / WC / 8;
     constexpr int NTILE = REF ? 3 : 2;                       // staged tiles per stage: dY, H (, act_ref)
+    constexpr int NST = BN >= 64 ? 3 : 2;                    // shadows the file-level ring depth: 128-row tiles take 2 stages
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int C = a.Cout, nch = (C + BK - 1) / BK, Kpad = nch * BK, WS2 = (Kpad + 8) / 2, Ktot = a.C1 + a.C2;
     float* St = reinterpret_cast<float*>(smem_raw);                          // [NST][NTILE][BM][AS]
@@ -487,8 +488,8 @@ __global__ void __launch_bounds__(kThreads, (BN >= 128 || REF) ? 1 : 2) dgrad2_k
 
 template <int BN, bool REF>
 size_t dgrad2_smem(int Kpad) {
-    constexpr int WC = BN >= 64 ? 2 : 1, BM = 16 * (8 / WC), NTILE = REF ? 3 : 2;
-    return (size_t)NST * NTILE * BM * AS * 4 + (size_t)2 * BN * ((Kpad + 8) / 2) * 4 + (size_t)Kpad * 16;
+    constexpr int WC = BN >= 64 ? 2 : 1, BM = 16 * (8 / WC), NTILE = REF ? 3 : 2, NSTD = BN >= 64 ? 3 : 2;
+    return (size_t)NSTD * NTILE * BM * AS * 4 + (size_t)2 * BN * ((Kpad + 8) / 2) * 4 + (size_t)Kpad * 16;
 }
 
 // ===================================================================================================== wgrad
@@ -770,7 +771,7 @@ bool try_fwd2(const FwdArgs& a, int precision, cudaStream_t st, int* rc) {
         if (precision == 0) {            // fp32-grade forward (3xTF32)
             const size_t smem = fwd2t_smem<BN>(Kpad);
             CRF_SET_SMEM((fwd2t_kernel<BN>), smem);
-            fwd2t_kernel<BN><<<grid, kThreads, smem, st>>>(a, ntiles);
+            fwd2t_kernel<BN><<<std::min(ntiles, FwdT<BN>::CTAS * kNumSMs), kThreads, smem, st>>>(a, ntiles);
         } else {
             const size_t smem = fwd2_smem<BN>(Kpad);
             if (precision == 3) { CRF_SET_SMEM((fwd2_kernel<BN, true>), smem); fwd2_kernel<BN, true><<<grid, kThreads, smem, st>>>(a, ntiles); }

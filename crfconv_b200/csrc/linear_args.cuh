@@ -13,7 +13,7 @@ struct FwdArgs {
     const float* W;                               // [Cout, C1 + C2] row-major (nn.Linear.weight)
     const float* bias;                            // [Cout] or null
     float* Y;                                     // [M, Cout]
-    double* stats;                                // [2*Cout]: Σ, Σ² over rows (or null)
+    float* stats;                                 // [kStatSlots][2*Cout] partial Σ, Σ² over rows (or null)
     int64_t M; int Cout;
 };
 

@@ -122,9 +122,9 @@ __global__ void __launch_bounds__(TR) fwd_kernel(const FwdArgs a, const int ntil
     if (a.stats) {
         __syncthreads();
         if (tid < CO && tid < a.Cout) {
-            double* st = a.stats + (size_t)(blockIdx.x % kStatSlots) * 2 * a.Cout;
-            atomicAdd(st + tid, (double)s_sum[tid]);
-            atomicAdd(st + a.Cout + tid, (double)s_sq[tid]);
+            float* st = a.stats + (size_t)(blockIdx.x % kStatSlots) * 2 * a.Cout;
+            atomicAdd(st + tid, s_sum[tid]);
+            atomicAdd(st + a.Cout + tid, s_sq[tid]);
         }
     }
 }

@@ -40,15 +40,23 @@ def shard_batch(tensors, rank: int, world_size: int):
 
 
 class FlatGradients:
-    """Owns one contiguous gradient buffer for all parameters of `module`; ``all_reduce()`` is a single collective."""
+    """One contiguous gradient buffer for all parameters of `module`; ``all_reduce()`` is a single collective.
 
-    def __init__(self, module: torch.nn.Module):
+    bind=True  : ``p.grad`` are pre-bound views of the buffer and autograd accumulates into them (works for any module).
+    bind=False : ``p.grad`` is left to autograd (call ``zero()`` → grads set to None, so autograd *adopts* the tensors the
+                 backward returns, with no accumulate kernels).  If all adopted gradients already live in one storage — the
+                 fused CRF layer returns views of a single flat allocation — that storage is all-reduced in place; otherwise
+                 they are packed with one foreach-copy, reduced and copied back."""
+
+    def __init__(self, module: torch.nn.Module, bind: bool = True):
         self.params = [p for p in module.parameters() if p.requires_grad]
         if not self.params:
             raise ValueError("module has no trainable parameters")
+        self.bind = bind
         dev = self.params[0].device
         self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
-        self._bind()
+        if bind:
+            self._bind()
 
     def _bind(self):
         off = 0
@@ -57,17 +65,49 @@ class FlatGradients:
             off += p.numel()
 
     def zero(self):
+        if not self.bind:
+            for p in self.params:
+                p.grad = None
+            return
         self.flat.zero_()
         if any(p.grad is None or p.grad.data_ptr() < self.flat.data_ptr() for p in self.params):
             self._bind()                                            # someone called zero_grad(set_to_none=True)
 
+    def _shared_span(self):
+        """If every gradient is a contiguous view of the same storage, returns a 1-D tensor covering their span."""
+        gs = [p.grad for p in self.params]
+        if any(g is None or not g.is_contiguous() or g.dtype != torch.float32 for g in gs):
+            return None
+        base = gs[0].untyped_storage().data_ptr()
+        if any(g.untyped_storage().data_ptr() != base for g in gs):
+            return None
+        lo = min(g.storage_offset() for g in gs)
+        hi = max(g.storage_offset() + g.numel() for g in gs)
+        if hi - lo > 4 * sum(g.numel() for g in gs):                 # mostly foreign data in between: pack instead
+            return None
+        return torch.as_strided(gs[0], (hi - lo,), (1,), lo)
+
     def all_reduce(self, average: bool = True):
-        """Sums the flat buffer over the ranks (one collective); divides by world size if `average`."""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-            if average:
-                self.flat.div_(dist.get_world_size())
-        return self.flat
+        """Sums the gradients over the ranks with ONE collective; divides by world size if `average`."""
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        if world == 1:
+            return self.flat if self.bind else None
+        if self.bind:
+            buf = self.flat
+        else:
+            buf = self._shared_span()
+            if buf is None:
+                gs = [p.grad.reshape(-1) for p in self.params]
+                torch._foreach_copy_(list(self.flat.split([g.numel() for g in gs])), gs)
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+                if average:
+                    self.flat.div_(world)
+                torch._foreach_copy_(gs, list(self.flat.split([g.numel() for g in gs])))
+                return self.flat
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        if average:
+            buf.div_(world)
+        return buf
 
 
 def init_from_env(backend: str | None = None):

@@ -11,7 +11,7 @@ from . import _lib
 
 # 0 = 3xTF32 (fp32-grade, default: matches the fp32 reference to ~1e-6), 1 = single-pass TF32
 PRECISION = int(os.environ.get("CRFCONV_PRECISION", "0"))
-STAT_SLOTS = 512     # include/crfconv_b200.h: CRFCONV_STAT_SLOTS
+STAT_SLOTS = 64      # include/crfconv_b200.h: CRFCONV_STAT_SLOTS
 GRAD_SLOTS = 32      # CRFCONV_GRAD_SLOTS
 
 
@@ -81,12 +81,12 @@ def as2d(x):
 
 
 class BN:
-    """Per-BatchNorm scratch: f64 Σ/Σ² accumulators, fused affine (scale, shift), saved mean/invstd, backward k1/k2."""
+    """Per-BatchNorm scratch: slotted f32 Σ/Σ² partial accumulators, fused affine (scale, shift), saved mean/invstd, backward k1/k2."""
     __slots__ = ("C", "stats", "scale", "shift", "mean", "invstd", "k1", "k2", "count", "training")
 
     def __init__(self, C, device, stats=None):
         self.C = C
-        self.stats = stats if stats is not None else torch.zeros(STAT_SLOTS * 2 * C, dtype=torch.float64, device=device)   # zeroed
+        self.stats = stats if stats is not None else torch.zeros(STAT_SLOTS * 2 * C, dtype=torch.float32, device=device)   # zeroed
         buf = torch.empty(6, C, dtype=torch.float32, device=device)
         self.scale, self.shift, self.mean, self.invstd, self.k1, self.k2 = buf.unbind(0)
         self.count = 0
@@ -113,6 +113,12 @@ def linear_fwd(X1, W, *, scale1=None, shift1=None, slope1=1.0, idx1=None, rows_d
 def _linear_fwd_call(L, X1, C1, scale1, shift1, slope1, idx1, rows_dst, rows_src, X2, C2, W, bias, Y, stats, M, Cout):
     return L.crfconv_linear_fwd(_p(X1), C1, _p(scale1), _p(shift1), float(slope1), _p(idx1), int(rows_dst), int(rows_src), _p(X2), C2,
                               _p(W), _p(bias), _p(Y), _p(stats), int(M), int(Cout), PRECISION, _lib.stream_ptr())
+
+
+def grad_slots_reduce(scratch, dW_flat, n, stride):
+    L = _lib.lib()
+    COUNTERS["launches"] += 1
+    _lib.check(L.crfconv_grad_slots_reduce(_p(scratch), _p(dW_flat), int(n), int(stride), _lib.stream_ptr()), "grad_slots_reduce")
 
 
 class Flat:
@@ -155,7 +161,7 @@ def bn_backward_prepare(dY, H, bn: BN, slope, dgamma, dbeta, act_ref=None, sums=
     `sums` (optional) = zero-initialised f64 scratch of STAT_SLOTS·2·C entries."""
     L = _lib.lib()
     if sums is None:
-        sums = torch.zeros(STAT_SLOTS * 2 * bn.C, dtype=torch.float64, device=H.device)
+        sums = torch.zeros(STAT_SLOTS * 2 * bn.C, dtype=torch.float32, device=H.device)
     with _call(f"bn_bwd_reduce[{bn.C}]", 1, _nbytes(dY, H, act_ref)):
         rc = L.crfconv_bn_bwd_reduce(_p(dY), _p(H), _p(act_ref), _p(bn.scale), _p(bn.shift), _p(bn.mean), _p(bn.invstd), float(slope),
                                      _p(sums), H.shape[0], bn.C, _lib.stream_ptr())
@@ -169,33 +175,33 @@ def bn_backward_prepare(dY, H, bn: BN, slope, dgamma, dbeta, act_ref=None, sums=
 
 
 def linear_bwd(dY, H, bn, slope, X1, W, *, scale1=None, shift1=None, slope1=1.0, idx1=None, rows_dst=0, rows_src=0, X2=None,
-               dX1=None, acc1=False, dX2=None, acc2=False, dW=None, dbias=None, act_ref=None, scratch=None):
+               dX1=None, acc1=False, dX2=None, acc2=False, dW=None, dbias=None, act_ref=None, scratch=None, scratch_stride=0):
     """bn = BN (after bn_backward_prepare) or None for a plain Linear."""
     L = _lib.lib()
     C1 = X1.shape[1]
     C2 = X2.shape[1] if X2 is not None else 0
     M, Cout = dY.shape
     b = bn
-    if dW is not None and Cout * (C1 + C2) > 1024:
+    if dW is not None and Cout * (C1 + C2) > 1024 and scratch_stride == 0:
         scratch = None      # wide outputs: a CTA's adds are spread over >1024 addresses, direct atomics are cheaper than a reduce pass
     elif dW is not None and scratch is None:
         scratch = torch.zeros(GRAD_SLOTS * Cout * (C1 + C2), dtype=torch.float32, device=dY.device)
     nb = _nbytes(dY, H if b else None, act_ref, X1 if dW is not None else None, X2 if dW is not None else None, dX1, dX2,
                  dX1 if acc1 else None, dX2 if acc2 else None)
     with _call(f"linear_bwd[{Cout}<-{C1 + C2}]" + ("" if dW is not None else ":dgrad") + ("" if (dX1 is not None or dX2 is not None) else ":wgrad"),
-               int(dW is not None) + int(scratch is not None) + int(dX1 is not None or dX2 is not None), nb):
+               int(dW is not None) + int(scratch is not None and scratch_stride == 0) + int(dX1 is not None or dX2 is not None), nb):
         rc = _linear_bwd_call(L, dY, H, act_ref, b, slope, X1, C1, scale1, shift1, slope1, idx1, rows_dst, rows_src, X2, C2, W, dX1, acc1,
-                              dX2, acc2, dW, dbias, scratch, M, Cout)
+                              dX2, acc2, dW, dbias, scratch, scratch_stride, M, Cout)
     _lib.check(rc, "linear_bwd")
 
 
 def _linear_bwd_call(L, dY, H, act_ref, b, slope, X1, C1, scale1, shift1, slope1, idx1, rows_dst, rows_src, X2, C2, W, dX1, acc1, dX2, acc2,
-                     dW, dbias, scratch, M, Cout):
+                     dW, dbias, scratch, scratch_stride, M, Cout):
     return L.crfconv_linear_bwd(_p(dY), _p(H), _p(act_ref), _p(b.scale) if b else None, _p(b.shift) if b else None,
                               _p(b.mean) if b else None, _p(b.invstd) if b else None, _p(b.k1) if b else None,
                               _p(b.k2) if b else None, float(slope),
                               _p(X1), C1, _p(scale1), _p(shift1), float(slope1), _p(idx1), int(rows_dst), int(rows_src), _p(X2), C2,
-                              _p(W), _p(dX1), int(acc1), _p(dX2), int(acc2), _p(dW), _p(dbias), _p(scratch), int(M), int(Cout), PRECISION,
+                              _p(W), _p(dX1), int(acc1), _p(dX2), int(acc2), _p(dW), _p(dbias), _p(scratch), int(scratch_stride), int(M), int(Cout), PRECISION,
                               _lib.stream_ptr())
 
 

@@ -74,21 +74,21 @@ int crfconv_grid_subsample_host(const float* points, int64_t N, const float* fea
  * generic 3xTF32 kernels otherwise), 0 = generic only, 1 = fast whenever the shape allows.  Returns the previous mode. */
 int crfconv_set_fast_path(int mode);
 
-#define CRFCONV_STAT_SLOTS 512 /* Σ/Σ² buffers (`stats`, `sums`) are [CRFCONV_STAT_SLOTS][2·C] doubles, zero-initialised by the caller */
+#define CRFCONV_STAT_SLOTS 64 /* Σ/Σ² buffers (`stats`, `sums`) are [CRFCONV_STAT_SLOTS][2·C] floats (per-slot partials of <= 4 CTAs; summed in f64 by the finalize calls), zero-initialised by the caller */
 #define CRFCONV_GRAD_SLOTS 32
 
 /* Y[M,Cout] = [ lrelu(X1*scale1 + shift1, slope1) | X2 ] · Wᵀ (+ bias).  scale1 == NULL ⇒ X1 is used as is.
  * idx1 != NULL ⇒ X1 rows are gathered: source row of output row m is (m / rows_dst) * rows_src + idx1[m]
- * (point_conv_big.py:97-101).  stats != NULL ⇒ Σ_rows Y and Σ_rows Y² (f64) are accumulated into the slotted
+ * (point_conv_big.py:97-101).  stats != NULL ⇒ Σ_rows Y and Σ_rows Y² are accumulated into the slotted
  * partial buffer stats[CRFCONV_STAT_SLOTS][2·Cout] (CTA b adds into slot b % SLOTS); crfconv_bn_finalize_fwd sums the slots. */
 int crfconv_linear_fwd(const float* X1, int C1, const float* scale1, const float* shift1, float slope1, const int64_t* idx1,
                        int64_t rows_dst, int64_t rows_src, const float* X2, int C2, const float* W, const float* bias, float* Y,
-                       double* stats, int64_t M, int Cout, int precision, void* stream);
+                       float* stats, int64_t M, int Cout, int precision, void* stream);
 
 /* nn.BatchNorm1d bookkeeping (momentum, eps, biased variance for normalisation, unbiased for running_var).
  * training: scale = γ·istd, shift = β − μ·scale from Σ/Σ², running stats updated in place (may be NULL);
  * eval: from running statistics.  mean / invstd (saved for backward) may be NULL. */
-int crfconv_bn_finalize_fwd(const double* stats, int64_t count, const float* gamma, const float* beta, float eps, float momentum,
+int crfconv_bn_finalize_fwd(const float* stats, int64_t count, const float* gamma, const float* beta, float eps, float momentum,
                             int training, float* running_mean, float* running_var, float* scale, float* shift, float* mean,
                             float* invstd, int C, void* stream);
 
@@ -99,21 +99,25 @@ int crfconv_bn_act_fwd(const float* H, const float* scale, const float* shift, c
 /* BatchNorm backward reductions into sums[CRFCONV_STAT_SLOTS][2·C]: [0:C] += Σ dV, [C:2C] += Σ dV·Ĥ, dV = dY·lrelu'(pre), Ĥ = (H−mean)·invstd,
  * pre = act_ref ? act_ref : H*scale+shift. */
 int crfconv_bn_bwd_reduce(const float* dY, const float* H, const float* act_ref, const float* scale, const float* shift,
-                          const float* mean, const float* invstd, float slope, double* sums, int64_t M, int C, void* stream);
+                          const float* mean, const float* invstd, float slope, float* sums, int64_t M, int C, void* stream);
 
 /* Sums the slots: k1 = Σ dV / count, k2 = Σ dV·Ĥ / count; dgamma += Σ dV·Ĥ, dbeta += Σ dV (either may be NULL). */
-int crfconv_bn_finalize_bwd(const double* sums, int64_t count, float* k1, float* k2, float* dgamma, float* dbeta, int C, void* stream);
+int crfconv_bn_finalize_bwd(const float* sums, int64_t count, float* k1, float* k2, float* dgamma, float* dbeta, int C, void* stream);
 
 /* Backward of crfconv_linear_fwd.  dY is the gradient wrt the layer's activation output; the BN(+LeakyReLU) backward
  * dH = scale·(dV − k1 − Ĥ·k2) is applied on the fly (scale == NULL ⇒ no BN, dH = dY).  Produces dX1 [M,C1] / dX2 [M,C2]
  * (gradients wrt the post-prologue inputs; NULL ⇒ skipped; acc ⇒ +=), dW [Cout,C1+C2] += dHᵀ·[prologue(X1)|X2],
- * dbias += Σ dH (NULL ⇒ skipped).  dW_scratch (optional): CRFCONV_GRAD_SLOTS·Cout·(C1+C2) zero-initialised floats; when given,
+ * dbias += Σ dH (NULL ⇒ skipped).  dW_scratch (optional): CRFCONV_GRAD_SLOTS slots of zero-initialised floats (pitch Cout·(C1+C2), or dW_scratch_stride); when given,
  * CTAs accumulate into per-slot partial copies that a follow-up kernel sums into dW (same-address atomics serialise in L2). */
 int crfconv_linear_bwd(const float* dY, const float* H, const float* act_ref, const float* scale, const float* shift,
                        const float* mean, const float* invstd, const float* k1, const float* k2, float slope,
                        const float* X1, int C1, const float* scale1, const float* shift1, float slope1, const int64_t* idx1,
                        int64_t rows_dst, int64_t rows_src, const float* X2, int C2, const float* W, float* dX1, int acc1,
-                       float* dX2, int acc2, float* dW, float* dbias, float* dW_scratch, int64_t M, int Cout, int precision, void* stream);
+                       float* dX2, int acc2, float* dW, float* dbias, float* dW_scratch, int64_t dW_scratch_stride, int64_t M, int Cout,
+                       int precision, void* stream);
+/* dW[i] += Σ_slots scratch[slot·stride + i] for i < n.  With dW_scratch_stride > 0 crfconv_linear_bwd only accumulates into the
+ * slots (slot pitch = stride floats) and the caller folds all layers that share one flat gradient layout with ONE call here. */
+int crfconv_grad_slots_reduce(const float* scratch, float* dW, int64_t n, int64_t stride, void* stream);
 
 /* ------------------------------------------------------------------------ continuous-CRF mean-field
  * Replaces the body of ContinuousGaussianCRFConv.forward, models/continuous_crf_conv_big.py:56-72 (and its autograd
