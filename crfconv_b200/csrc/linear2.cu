@@ -67,14 +67,15 @@ __global__ void __launch_bounds__(kThreads, 2) fwd2_kernel(const FwdArgs a, cons
     const int Q = my_tiles * nch;
     const int c4 = tid & 7, r0 = tid >> 3;
 
-    auto issue = [&](int q) {
-        const int ti = q / nch, c = q % nch;
+    int iq_t = 0, iq_c = 0, iq_s = 0;          // next chunk to issue: (tile, chunk, stage) counters instead of div/mod
+    auto issue = [&]() {
+        const int ti = iq_t, c = iq_c;
         const int64_t m0 = ((int64_t)blockIdx.x + (int64_t)ti * gridDim.x) * BM;
         const bool seg1 = c < nch1;
         const float* X = seg1 ? a.X1 : a.X2;
         const int C = seg1 ? a.C1 : a.C2;
         const int col = (seg1 ? c : c - nch1) * BK + 4 * c4;
-        float* dst = As + (q % NST) * BM * AS;
+        float* dst = As + iq_s * BM * AS;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int r = r0 + 32 * j;
@@ -84,10 +85,12 @@ __global__ void __launch_bounds__(kThreads, 2) fwd2_kernel(const FwdArgs a, cons
             if (ok && seg1 && a.idx1) srow = (m / a.rows_dst) * a.rows_src + __ldg(a.idx1 + m);
             cp_async16(dst + r * AS + 4 * c4, X + srow * C + (ok ? col : 0), ok);
         }
+        if (++iq_c == nch) { iq_c = 0; ++iq_t; }
+        if (++iq_s == NST) iq_s = 0;
     };
 
     for (int s = 0; s < NST - 1; ++s) {
-        if (s < Q) issue(s);
+        if (s < Q) issue();
         cp_async_commit();
     }
 
@@ -97,14 +100,14 @@ __global__ void __launch_bounds__(kThreads, 2) fwd2_kernel(const FwdArgs a, cons
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
+    int ti = 0, c = 0, cs = 0;
     for (int q = 0; q < Q; ++q) {
         cp_async_wait<NST - 2>();
         __syncthreads();
-        if (q + NST - 1 < Q) issue(q + NST - 1);
+        if (q + NST - 1 < Q) issue();
         cp_async_commit();
 
-        const int ti = q / nch, c = q % nch;
-        const float* At = As + (q % NST) * BM * AS;
+        const float* At = As + cs * BM * AS;
         const bool seg1 = c < nch1;
         const int kvalid = seg1 ? min(BK, a.C1 - c * BK) : min(BK, a.C2 - (c - nch1) * BK);
         const float slope = (seg1 && a.scale1) ? a.slope1 : 1.0f;
@@ -162,6 +165,8 @@ __global__ void __launch_bounds__(kThreads, 2) fwd2_kernel(const FwdArgs a, cons
                 }
             }
         }
+        if (++c == nch) { c = 0; ++ti; }
+        if (++cs == NST) cs = 0;
     }
     cp_async_wait<0>();
     if (a.stats) {
@@ -185,6 +190,13 @@ __device__ __forceinline__ uint32_t tf32_of(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
+}
+// (hi, lo) tf32 split by TRUNCATION: cvt.rna.tf32 costs ~4 integer instructions on this part (SASS: IMAD/LOP3 sequences), which
+// made operand conversion — not the tensor pipe — the bound of the 3xTF32 forward (ncu: 14.6 issued instructions per mma).
+// hi = top 19 bits, lo = top 19 bits of the exact remainder: |a − hi − lo| <= 2^-20 |a|, i.e. products good to ≈1e-6.
+__device__ __forceinline__ void split_trunc(float v, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(v) & 0xffffe000u;
+    lo = __float_as_uint(v - __uint_as_float(hi)) & 0xffffe000u;
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(
@@ -225,14 +237,15 @@ __global__ void __launch_bounds__(kThreads, FwdT<BN>::CTAS) fwd2t_kernel(const F
     const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int Q = my_tiles * nch;
     const int c4 = tid & 7, r0 = tid >> 3;
-    auto issue = [&](int q) {
-        const int ti = q / nch, c = q % nch;
+    int iq_t = 0, iq_c = 0, iq_s = 0;          // (tile, chunk, stage) of the next chunk to issue — counters, no div/mod in the loop
+    auto issue = [&]() {
+        const int ti = iq_t, c = iq_c;
         const int64_t m0 = ((int64_t)blockIdx.x + (int64_t)ti * gridDim.x) * BM;
         const bool seg1 = c < nch1;
         const float* X = seg1 ? a.X1 : a.X2;
         const int C = seg1 ? a.C1 : a.C2;
         const int col = (seg1 ? c : c - nch1) * BK + 4 * c4;
-        float* dst = As + (q % NSTT) * BM * AST;
+        float* dst = As + iq_s * BM * AST;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int r = r0 + 32 * j;
@@ -242,9 +255,11 @@ __global__ void __launch_bounds__(kThreads, FwdT<BN>::CTAS) fwd2t_kernel(const F
             if (ok && seg1 && a.idx1) srow = (m / a.rows_dst) * a.rows_src + __ldg(a.idx1 + m);
             cp_async16(dst + r * AST + 4 * c4, X + srow * C + (ok ? col : 0), ok);
         }
+        if (++iq_c == nch) { iq_c = 0; ++iq_t; }
+        if (++iq_s == NSTT) iq_s = 0;
     };
     for (int s = 0; s < NSTT - 1; ++s) {
-        if (s < Q) issue(s);
+        if (s < Q) issue();
         cp_async_commit();
     }
 
@@ -254,13 +269,13 @@ __global__ void __launch_bounds__(kThreads, FwdT<BN>::CTAS) fwd2t_kernel(const F
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
+    int ti = 0, c = 0, cs = 0;                 // (tile, chunk, stage) being computed
     for (int q = 0; q < Q; ++q) {
         cp_async_wait<NSTT - 2>();
         __syncthreads();
-        if (q + NSTT - 1 < Q) issue(q + NSTT - 1);
+        if (q + NSTT - 1 < Q) issue();
         cp_async_commit();
-        const int ti = q / nch, c = q % nch;
-        const float* At = As + (q % NSTT) * BM * AST;
+        const float* At = As + cs * BM * AST;
         const bool seg1 = c < nch1;
         const int kvalid = seg1 ? min(BK, a.C1 - c * BK) : min(BK, a.C2 - (c - nch1) * BK);
         const float slope = (seg1 && a.scale1) ? a.slope1 : 1.0f;
@@ -275,16 +290,16 @@ __global__ void __launch_bounds__(kThreads, FwdT<BN>::CTAS) fwd2t_kernel(const F
                     const int kk = kb + t + ((i & 2) ? 4 : 0);
                     float v = At[row * AST + kk];
                     v = lrelu(fmaf(v, s_sc[c * BK + kk], s_sh[c * BK + kk]), slope);
-                    ah[i] = tf32_of(v);
-                    al[i] = tf32_of(v - __uint_as_float(ah[i]));
+                    split_trunc(v, ah[i], al[i]);
                 }
                 const int wb = c * BK + kb + t;
 #pragma unroll
                 for (int nt = 0; nt < BN / 8; ++nt) {
                     const int wi = (nt * 8 + g) * WS + wb;
                     const float w0 = Wf[wi], w1 = Wf[wi + 4];
-                    const uint32_t bh0 = tf32_of(w0), bh1 = tf32_of(w1);
-                    const uint32_t bl0 = tf32_of(w0 - __uint_as_float(bh0)), bl1 = tf32_of(w1 - __uint_as_float(bh1));
+                    uint32_t bh0, bl0, bh1, bl1;
+                    split_trunc(w0, bh0, bl0);
+                    split_trunc(w1, bh1, bl1);
                     mma_tf32(acc[nt], al, bh0, bh1);
                     mma_tf32(acc[nt], ah, bl0, bl1);
                     mma_tf32(acc[nt], ah, bh0, bh1);
@@ -321,6 +336,8 @@ __global__ void __launch_bounds__(kThreads, FwdT<BN>::CTAS) fwd2t_kernel(const F
                 }
             }
         }
+        if (++c == nch) { c = 0; ++ti; }
+        if (++cs == NSTT) cs = 0;
     }
     cp_async_wait<0>();
     if (a.stats) {
@@ -387,11 +404,12 @@ __global__ void __launch_bounds__(kThreads, (BN >= 128 || REF) ? 1 : 2) dgrad2_k
     constexpr int RPP = kThreads / 8;                      // rows covered per pass of 256 threads (8 float4 per 32-float row)
     const int c4 = tid & 7, r0 = tid >> 3;
 
-    auto issue = [&](int q) {
-        const int ti = q / nch, c = q % nch;
+    int iq_t = 0, iq_c = 0, iq_s = 0;
+    auto issue = [&]() {
+        const int ti = iq_t, c = iq_c;
         const int64_t m0 = ((int64_t)blockIdx.x + (int64_t)ti * gridDim.x) * BM;
         const int col = c * BK + 4 * c4;
-        float* dst = St + (q % NST) * NTILE * BM * AS;
+        float* dst = St + iq_s * NTILE * BM * AS;
 #pragma unroll
         for (int j = 0; j < BM / RPP; ++j) {
             const int r = r0 + RPP * j;
@@ -402,9 +420,11 @@ __global__ void __launch_bounds__(kThreads, (BN >= 128 || REF) ? 1 : 2) dgrad2_k
             if (!plain) cp_async16(dst + BM * AS + r * AS + 4 * c4, a.H + off, ok);
             if (REF) cp_async16(dst + 2 * BM * AS + r * AS + 4 * c4, a.bn.act_ref + off, ok);
         }
+        if (++iq_c == nch) { iq_c = 0; ++iq_t; }
+        if (++iq_s == NST) iq_s = 0;
     };
     for (int s = 0; s < NST - 1; ++s) {
-        if (s < Q) issue(s);
+        if (s < Q) issue();
         cp_async_commit();
     }
     float acc[NT][4];
@@ -414,13 +434,13 @@ __global__ void __launch_bounds__(kThreads, (BN >= 128 || REF) ? 1 : 2) dgrad2_k
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     const float slope = a.bn.slope;
 
+    int ti = 0, c = 0, cs = 0;
     for (int q = 0; q < Q; ++q) {
         cp_async_wait<NST - 2>();
         __syncthreads();
-        if (q + NST - 1 < Q) issue(q + NST - 1);
+        if (q + NST - 1 < Q) issue();
         cp_async_commit();
-        const int ti = q / nch, c = q % nch;
-        const float* Dt = St + (q % NST) * NTILE * BM * AS;
+        const float* Dt = St + cs * NTILE * BM * AS;
         const float* Ht = Dt + BM * AS;
         const float* Rt = Dt + 2 * BM * AS;
         const int kvalid = min(BK, C - c * BK);
@@ -482,6 +502,8 @@ __global__ void __launch_bounds__(kThreads, (BN >= 128 || REF) ? 1 : 2) dgrad2_k
                 }
             }
         }
+        if (++c == nch) { c = 0; ++ti; }
+        if (++cs == NST) cs = 0;
     }
     cp_async_wait<0>();
 }
