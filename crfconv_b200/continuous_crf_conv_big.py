@@ -19,6 +19,19 @@ from . import ops
 from .common import MLP, bn_forward_state
 
 
+_SIDE = {}
+
+
+def _side_stream(dev):
+    """Second stream per device: the unary and pairwise MLP chains are independent until the upsample, and at hidden width
+    each of their kernels is latency-bound (≈300 persistent CTAs, little work each), so the two chains run concurrently
+    (forward and backward).  Captured CUDA graphs keep the fork/join as parallel branches."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
+
+
 def _mlp_params(m: MLP):
     return m.lin.weight, m.bn.batch_norm.weight, m.bn.batch_norm.bias
 
@@ -49,18 +62,27 @@ class _CRFConvFunction(torch.autograd.Function):
         fstats = ops.Flat(ops.STAT_SLOTS * 2 * (4 * F + 2 * Co), torch.float32, dev)
         nbt = []
 
-        # unary_nn / pairwise_nn, layer 1 and 2 (:58-59)
-        s1u, fin = bn_forward_state(F, dev, Mc, bns[0], tr(bns[0]), fstats.take(ops.STAT_SLOTS * 2 * F), nbt)
-        H1u = ops.linear_fwd(U, W1u, stats=s1u.stats); fin()
-        s1p, fin = bn_forward_state(F, dev, M, bns[2], tr(bns[2]), fstats.take(ops.STAT_SLOTS * 2 * F), nbt)
-        H1p = ops.linear_fwd(P, W1p, stats=s1p.stats); fin()
-        s2u, fin = bn_forward_state(F, dev, Mc, bns[1], tr(bns[1]), fstats.take(ops.STAT_SLOTS * 2 * F), nbt)
-        H2u = ops.linear_fwd(H1u, W2u, scale1=s1u.scale, shift1=s1u.shift, slope1=sl[0], stats=s2u.stats); fin()
-        s2p, fin = bn_forward_state(F, dev, M, bns[3], tr(bns[3]), fstats.take(ops.STAT_SLOTS * 2 * F), nbt)
-        H2p = ops.linear_fwd(H1p, W2p, scale1=s1p.scale, shift1=s1p.shift, slope1=sl[2], stats=s2p.stats); fin()
+        # unary_nn / pairwise_nn, layer 1 and 2 (:58-59) — two independent chains on two streams; every buffer is allocated on the
+        # main stream first, the side stream only launches kernels
+        s1u, fin1u = bn_forward_state(F, dev, Mc, bns[0], tr(bns[0]), fstats.take(ops.STAT_SLOTS * 2 * F), nbt)
+        s2u, fin2u = bn_forward_state(F, dev, Mc, bns[1], tr(bns[1]), fstats.take(ops.STAT_SLOTS * 2 * F), nbt)
+        s1p, fin1p = bn_forward_state(F, dev, M, bns[2], tr(bns[2]), fstats.take(ops.STAT_SLOTS * 2 * F), nbt)
+        s2p, fin2p = bn_forward_state(F, dev, M, bns[3], tr(bns[3]), fstats.take(ops.STAT_SLOTS * 2 * F), nbt)
+        H1u, H2u = torch.empty((Mc, F), dtype=torch.float32, device=dev), torch.empty((Mc, F), dtype=torch.float32, device=dev)
+        main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+        fork, join = torch.cuda.Event(), torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            ops.linear_fwd(U, W1u, stats=s1u.stats, out=H1u); fin1u()
+            ops.linear_fwd(H1u, W2u, scale1=s1u.scale, shift1=s1u.shift, slope1=sl[0], stats=s2u.stats, out=H2u); fin2u()
+            join.record(side)
+        H1p = ops.linear_fwd(P, W1p, stats=s1p.stats); fin1p()
+        H2p = ops.linear_fwd(H1p, W2p, scale1=s1p.scale, shift1=s1p.shift, slope1=sl[2], stats=s2p.stats); fin2p()
         # mean field (:60-72)
         cc = c.detach().contiguous().float()
         Cm, Minv = ops.crf_compat_fwd(cc)
+        main.wait_event(join)
         z = ops.crf_upsample_fwd(H2u, s2u, up, B, N, Nc)
         xs = [z]
         for _ in range(steps):
@@ -146,13 +168,20 @@ class _CRFConvFunction(torch.autograd.Function):
             ops.crf_upsample_bwd(Gz, g, up, Gu, B, N, Nc)      # dL/dz = Σ_t h^t + g^0
         else:
             ops.crf_upsample_bwd(g, None, up, Gu, B, N, Nc)
-        # unary_nn
-        ops.bn_backward_prepare(Gu, H2u, s2u, 1.0, dg["2u"], db["2u"], sums=sums.take(ops.STAT_SLOTS * 2 * F))
-        dA = torch.empty((Mc, F), dtype=torch.float32, device=dev)
-        ops.linear_bwd(Gu, H2u, s2u, 1.0, H1u, W2u, scale1=s1u.scale, shift1=s1u.shift, slope1=sl[0], dX1=dA, dW=dW["2u"], scratch=scr(dW["2u"]), scratch_stride=n_small)
-        ops.bn_backward_prepare(dA, H1u, s1u, sl[0], dg["1u"], db["1u"], sums=sums.take(ops.STAT_SLOTS * 2 * F))
+        # unary_nn — on the side stream, concurrently with the pairwise_nn chain below (buffers allocated here, on the main stream)
+        dAu = torch.empty((Mc, F), dtype=torch.float32, device=dev)
         dU = torch.empty((Mc, Cu), dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
-        ops.linear_bwd(dA, H1u, s1u, sl[0], U, W1u, dX1=dU, dW=dW["1u"], scratch=scr(dW["1u"]), scratch_stride=n_small)
+        sums_2u, sums_1u = sums.take(ops.STAT_SLOTS * 2 * F), sums.take(ops.STAT_SLOTS * 2 * F)
+        main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+        fork, join = torch.cuda.Event(), torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            ops.bn_backward_prepare(Gu, H2u, s2u, 1.0, dg["2u"], db["2u"], sums=sums_2u)
+            ops.linear_bwd(Gu, H2u, s2u, 1.0, H1u, W2u, scale1=s1u.scale, shift1=s1u.shift, slope1=sl[0], dX1=dAu, dW=dW["2u"], scratch=scr(dW["2u"]), scratch_stride=n_small)
+            ops.bn_backward_prepare(dAu, H1u, s1u, sl[0], dg["1u"], db["1u"], sums=sums_1u)
+            ops.linear_bwd(dAu, H1u, s1u, sl[0], U, W1u, dX1=dU, dW=dW["1u"], scratch=scr(dW["1u"]), scratch_stride=n_small)
+            join.record(side)
         # pairwise_nn (its input gradient accumulates onto the fusion_nn branch)
         ops.bn_backward_prepare(Gy, H2p, s2p, 1.0, dg["2p"], db["2p"], sums=sums.take(ops.STAT_SLOTS * 2 * F))
         dA = torch.empty((M, F), dtype=torch.float32, device=dev)
@@ -161,6 +190,7 @@ class _CRFConvFunction(torch.autograd.Function):
         need_p = ctx.needs_input_grad[1]
         ops.linear_bwd(dA, H1p, s1p, sl[2], P, W1p, dX1=dP if need_p else None, acc1=True, dW=dW["1p"], scratch=scr(dW["1p"]), scratch_stride=n_small)
 
+        main.wait_event(join)
         ops.grad_slots_reduce(wscr[2 * F * F:], small[2 * F * F:], n_small - 2 * F * F, n_small)   # all weight gradients, one launch
         grads = []
         for k in ("1u", "2u", "1p", "2p", "o", "f"):
