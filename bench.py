@@ -56,7 +56,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -68,8 +68,8 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
+        time.sleep(0.05)
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -216,12 +216,19 @@ def run_gpu(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
-        step(i)
-    barrier()
+    # clocks are sampled (20 ms period) from before the warm-up to the end of the timed region: same load throughout; the warm-up
+    # runs for at least 0.5 s so that nvidia-smi is up and several samples land under load
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    t_w = time.perf_counter()
+    i = 0
+    while i < max(args.warmup, 3) or time.perf_counter() - t_w < 0.5:
+        step(i)
+        i += 1
+        if i % 16 == 0:
+            torch.cuda.synchronize()
+    barrier()
     ops.COUNTERS["launches"] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -330,8 +337,14 @@ def run_gpu(args, rank, local_rank, world):
                    "algo_bytes_per_step": v["bytes"], "achieved_gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None}
                for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
     top_ach = top[1]["bytes"] / (top[1]["ms"] * 1e-3) / 1e9
+    traffic = None
+    try:      # DRAM bytes (read + write) per launch of the same call, from the committed `ncu --set full` capture (profiles/)
+        met = json.load(open(os.path.join(ROOT, "profiles", "ncu_r01_metrics.json")))
+        traffic = met["calls"].get(top[0], {}).get("traffic_bytes")
+    except Exception:
+        pass
     roofline = {"kernel": top[0], "bound": "hbm", "achieved": round(top_ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": round(top_ach / peaks["hbm_gbs"], 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(top_ach / peaks["hbm_gbs"], 4), "traffic": traffic, "peak_source": peak_src,
                 "share_of_step": round(top[1]["ms"] / total_k, 4),
                 "note": "achieved = algorithmic bytes of this kernel's calls in one step / their CUDA-event time"}
     step_ach = ALGO_BYTES_PER_CLOUD * B / (ms_step * 1e-3) / 1e9
@@ -374,7 +387,7 @@ def run_gpu(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--clouds", type=int, default=6, help="clouds per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])

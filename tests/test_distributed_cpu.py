@@ -40,6 +40,14 @@ def _worker(rank, world, port, q):
         out = fg.all_reduce(average=False)
         assert out.data_ptr() == fg.flat.data_ptr()
         assert all(p.grad.data_ptr() >= fg.flat.data_ptr() for p in model.parameters())   # grads are views of the flat buffer
+        # adopt mode (bind=False): autograd owns the gradient tensors; they are packed, reduced with ONE collective, copied back
+        fa = FlatGradients(model, bind=False)
+        fa.zero()
+        assert all(p.grad is None for p in model.parameters())
+        ((model(xs) - ys) ** 2).sum().backward()
+        fa.all_reduce(average=False)
+        adopted = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+        assert torch.allclose(adopted, fg.flat, rtol=1e-5, atol=1e-5)
         q.put((rank, xs.shape[0], before, fg.flat.clone()))
     finally:
         dist.destroy_process_group()
