@@ -256,6 +256,9 @@ __device__ __forceinline__ void scan_range(int s, int e, float qx, float qy, flo
     }
 }
 
+// SELF = queries are the support points themselves (same buffer): queries are then taken in CELL order from the sorted records,
+// so the warps of a CTA search neighbouring cells and share their point ranges through L1; results go to the original row.
+template <bool SELF>
 __global__ void __launch_bounds__(256) query_kernel(const float4* __restrict__ sorted_all,
                                                     const int* __restrict__ cell_start_all,
                                                     const Grid* __restrict__ grids, const float* __restrict__ edges,
@@ -271,8 +274,16 @@ __global__ void __launch_bounds__(256) query_kernel(const float4* __restrict__ s
     const float* lo_edge = edges + (size_t)b * 2 * kEdgeStride;
     const float* hi_edge = lo_edge + kEdgeStride;
 
-    const float* qp = queries + ((size_t)b * Q + q) * 3;
-    const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
+    float qx, qy, qz;
+    int out_row = q;
+    if (SELF) {
+        const float4 me = __ldg(sorted + q);
+        qx = me.x; qy = me.y; qz = me.z;
+        out_row = __float_as_int(me.w);
+    } else {
+        const float* qp = queries + ((size_t)b * Q + q) * 3;
+        qx = __ldg(qp); qy = __ldg(qp + 1); qz = __ldg(qp + 2);
+    }
     const int cx = cell_coord(qx, g.lo[0], g.inv[0], g.n[0]);
     const int cy = cell_coord(qy, g.lo[1], g.inv[1], g.n[1]);
     const int cz = cell_coord(qz, g.lo[2], g.inv[2], g.n[2]);
@@ -324,7 +335,7 @@ __global__ void __launch_bounds__(256) query_kernel(const float4* __restrict__ s
     }
     if (lane < K) {
         // K > N: unfilled slots keep 0, the observable behaviour of the reference's cpp_knn_omp (knn_.cxx:59,65-67)
-        out[((size_t)b * Q + q) * K + lane] = (t.i == 0x7fffffff) ? 0 : (int64_t)t.i;
+        out[((size_t)b * Q + out_row) * K + lane] = (t.i == 0x7fffffff) ? 0 : (int64_t)t.i;
     }
 }
 
@@ -383,8 +394,12 @@ int crfconv_knn_batch(const float* pts, int64_t B, int64_t N, const float* queri
     knn::count_kernel<<<dim3((unsigned)ceil_div(N, 256), (unsigned)B), 256, 0, st>>>(pts, grids, cell_of, cell_start, (int)N, cap);
     knn::scan_kernel<<<(unsigned)B, 1024, 0, st>>>(cell_start, grids, cap);
     knn::scatter_kernel<<<dim3((unsigned)ceil_div(N, 256), (unsigned)B), 256, 0, st>>>(pts, cell_of, cell_start, cursor, sorted, (int)N, cap);
-    knn::query_kernel<<<dim3((unsigned)ceil_div(Q, 8), (unsigned)B), 256, 0, st>>>(sorted, cell_start, grids, edges, queries, out_idx,
-                                                                                   (int)N, (int)Q, (int)K, cap);
+    if (queries == pts && Q == N)
+        knn::query_kernel<true><<<dim3((unsigned)ceil_div(Q, 8), (unsigned)B), 256, 0, st>>>(sorted, cell_start, grids, edges, queries, out_idx,
+                                                                                         (int)N, (int)Q, (int)K, cap);
+    else
+        knn::query_kernel<false><<<dim3((unsigned)ceil_div(Q, 8), (unsigned)B), 256, 0, st>>>(sorted, cell_start, grids, edges, queries, out_idx,
+                                                                                          (int)N, (int)Q, (int)K, cap);
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }
