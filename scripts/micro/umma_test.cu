@@ -1,0 +1,205 @@
+// Bring-up test for the tcgen05 path: D[128,N] = A[128,K] · B[N,K]^T with kind::tf32, operands written to shared memory by
+// CUDA cores in the K-major SWIZZLE_128B canonical layout, accumulator in TMEM, read back with tcgen05.ld.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o scripts/micro/umma_test scripts/micro/umma_test.cu
+// Every wait is bounded (trap after ~1e7 polls) so a wrong descriptor cannot hang the box.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+    for (uint32_t i = 0; i < (1u << 24); ++i)
+        if (mbar_try_wait(bar, parity)) return;
+    printf("mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+    __trap();
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"): rows are 128 bytes, 8-row groups are 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);          // start address
+    d |= (uint64_t)0 << 16;                          // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: 8 rows × 128 B
+    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    return d;
+}
+
+// instruction descriptor: D = f32, A = B = tf32, both K-major, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// element (r, k) of a K-major SW128 slab of 32 floats per row
+__device__ __forceinline__ uint32_t sw128_off(int r, int k) { return (uint32_t)(r * 128 + ((((k >> 2) ^ (r & 7)) << 4) | ((k & 3) << 2))); }
+
+template <int N, int KSLABS, bool X3>
+__global__ void __launch_bounds__(128) umma_test_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D) {
+    constexpr int K = 32 * KSLABS;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // [A hi slabs][A lo slabs][B hi slabs][B lo slabs]
+    uint8_t* a_hi = smem;
+    uint8_t* a_lo = a_hi + KSLABS * 128 * 128;
+    uint8_t* b_hi = a_lo + KSLABS * 128 * 128;
+    uint8_t* b_lo = b_hi + KSLABS * N * 128;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(64));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // operands → swizzled shared memory, split into tf32 hi + remainder lo
+    for (int i = tid; i < 128 * K; i += 128) {
+        const int r = i / K, k = i % K;
+        const float x = A[i];
+        const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+        const uint32_t off = (k / 32) * (128 * 128) + sw128_off(r, k % 32);
+        *(float*)(a_hi + off) = X3 ? hi : x;
+        *(float*)(a_lo + off) = x - hi;
+    }
+    for (int i = tid; i < N * K; i += 128) {
+        const int r = i / K, k = i % K;
+        const float x = B[i];
+        const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+        const uint32_t off = (k / 32) * (N * 128) + sw128_off(r, k % 32);
+        *(float*)(b_hi + off) = X3 ? hi : x;
+        *(float*)(b_lo + off) = x - hi;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes → visible to the tensor core's async proxy
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base;
+
+    if (tid == 0) {
+        constexpr uint32_t idesc = make_idesc(128, N);
+        uint32_t acc = 0;
+        for (int s = 0; s < KSLABS; ++s) {
+            for (int k8 = 0; k8 < 4; ++k8) {
+                const uint32_t ao = s * 128 * 128 + k8 * 32, bo = s * N * 128 + k8 * 32;
+                const uint64_t ah = make_desc(smem_u32(a_hi + ao)), al = make_desc(smem_u32(a_lo + ao));
+                const uint64_t bh = make_desc(smem_u32(b_hi + bo)), bl = make_desc(smem_u32(b_lo + bo));
+                if (X3) {
+                    umma_tf32(tmem, al, bh, idesc, acc); acc = 1;
+                    umma_tf32(tmem, ah, bl, idesc, acc);
+                }
+                umma_tf32(tmem, ah, bh, idesc, acc); acc = 1;
+            }
+        }
+        umma_commit(&bar);
+    }
+    mbar_wait_bounded(&bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // warp w reads TMEM lanes 32w .. 32w+31 (one accumulator row per thread)
+    const int row = warp * 32 + (tid & 31);
+    for (int c = 0; c < N; c += 16) {
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) D[row * N + c + i] = v[i];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64));
+}
+
+template <int N, int KSLABS, bool X3>
+static int run(const char* name, bool exact_inputs) {
+    constexpr int K = 32 * KSLABS;
+    std::vector<float> A(128 * K), B(N * K), D(128 * N), ref(128 * N);
+    srand(1234);
+    for (auto& x : A) x = exact_inputs ? (float)((rand() % 17) - 8) * 0.25f : (float)rand() / RAND_MAX * 2.f - 1.f;
+    for (auto& x : B) x = exact_inputs ? (float)((rand() % 17) - 8) * 0.5f : (float)rand() / RAND_MAX * 2.f - 1.f;
+    double amax = 0;
+    for (int i = 0; i < 128; ++i)
+        for (int j = 0; j < N; ++j) {
+            double s = 0;
+            for (int k = 0; k < K; ++k) s += (double)A[i * K + k] * (double)B[j * K + k];
+            ref[i * N + j] = (float)s;
+            amax = fmax(amax, fabs(s));
+        }
+    float *dA, *dB, *dD;
+    cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dB, B.size() * 4); cudaMalloc(&dD, D.size() * 4);
+    cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemset(dD, 0xff, D.size() * 4);
+    const size_t smem = 2 * KSLABS * 128 * 128 + 2 * KSLABS * N * 128 + 1024;
+    auto kern = umma_test_kernel<N, KSLABS, X3>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<1, 128, smem>>>(dA, dB, dD);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("%s: CUDA error %s\n", name, cudaGetErrorString(e)); return 1; }
+    cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+    double err = 0;
+    int bad = 0;
+    for (int i = 0; i < 128 * N; ++i) {
+        const double d = fabs((double)D[i] - (double)ref[i]);
+        if (!(d <= 1e30)) { ++bad; continue; }
+        err = fmax(err, d);
+    }
+    printf("%s: N=%d K=%d x3=%d  max|err|=%.3e (max|ref|=%.3e, rel %.3e) nan=%d   D[0..3]=%g %g %g %g  ref=%g %g %g %g\n", name, N, K, (int)X3,
+           err, amax, err / amax, bad, D[0], D[1], D[2], D[3], ref[0], ref[1], ref[2], ref[3]);
+    cudaFree(dA); cudaFree(dB); cudaFree(dD);
+    return 0;
+}
+
+int main() {
+    int rc = 0;
+    rc |= run<64, 1, false>("exact  ", true);
+    rc |= run<64, 2, false>("exact2 ", true);
+    rc |= run<16, 1, false>("exactN16", true);
+    rc |= run<64, 4, false>("tf32x1 ", false);
+    rc |= run<64, 4, true>("tf32x3 ", false);
+    rc |= run<16, 4, true>("tf32x3 N16", false);
+    return rc;
+}
