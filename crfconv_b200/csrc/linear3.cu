@@ -1,0 +1,302 @@
+// Third-generation Linear forward for sm_100a: the contraction runs on the 5th-generation tensor cores (tcgen05.mma,
+// kind::tf32, 128×N×8 per instruction) with the accumulator in TMEM.  Same contract as the other forward kernels
+// (linear_args.cuh FwdArgs): Y = [ lrelu(X1·scale1+shift1) | X2 ] · Wᵀ (+bias), optional row gather on segment 1, BatchNorm
+// Σ/Σ² partials in the epilogue.  fp32 parity comes from 3xTF32: every operand is split into tf32 hi + remainder lo and three
+// MMAs accumulate hi·hi + hi·lo + lo·hi in fp32 (measured 1.7e-6 relative, scripts/micro/umma_test.cu).
+//
+// One persistent CTA per SM, 17 warps with fixed roles, rows streamed in 128-row tiles:
+//   warps 5..16  producers : 6 groups of 2 warps; a group owns every 6th [128 rows × 32 columns] slab: coalesced 128-bit global
+//                            loads into registers, BatchNorm+LeakyReLU prologue, hi/lo split, stores into a 3-slot shared-memory
+//                            ring in the swizzled K-major operand layout, then fence.proxy.async + mbarrier arrive (the tensor
+//                            core reads shared memory through the async proxy);
+//   warp 4       issuer    : one thread waits for a slab, issues its ≤12 MMAs against the CTA-resident split weights and
+//                            tcgen05.commit's the slot back to the producers; after a tile's last slab it commits the accumulator;
+//   warps 0..3   epilogue  : tcgen05.ld of the [128 × N] accumulator (one row per thread), bias, staging in shared memory,
+//                            coalesced stores, per-column Σ/Σ² kept in registers across all the CTA's tiles.
+// Two accumulator buffers in TMEM let tile i+1's MMAs overlap tile i's epilogue.  What bounds it: the activation read from
+// HBM (rows × (Ktot + Cout) × 4 bytes); the MMAs of a tile take ≈0.8 us of the ≈1.9 us the tile's bytes need.
+#include <algorithm>
+#include <cstdlib>
+#include <type_traits>
+
+#include "common.cuh"
+#include "linear_args.cuh"
+#include "umma.cuh"
+
+namespace crf {
+namespace lin3 {
+
+using lin::FwdArgs;
+using namespace umma;
+
+constexpr int kEpiWarps = 4, kProdWarps = 12;
+constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;      // 544
+constexpr int kGroupWarps = 2;                                   // producer warps that share one slab
+constexpr int kGroups = kProdWarps / kGroupWarps;                // slabs in flight per CTA (6 × 16 KB of loads)
+constexpr int kRowsPerPass = kGroupWarps * 4;                    // a producer warp covers 4 rows × 128 B per load instruction
+constexpr int kLoadsPerSlab = 128 / kRowsPerPass;                // float4 loads per producer thread and slab (16)
+constexpr int BM = 128, BK = 32, RING = 3;
+static_assert(kGroups == RING || kGroups == 2 * RING, "slot hand-over protocol below assumes at most two groups alternate on a ring slot");
+constexpr int kSlabBytes = BM * 128;                             // one [128 × 32] fp32 slab
+constexpr int kSlotBytes = 2 * kSlabBytes;                       // hi + lo
+
+__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.0f ? v : v * slope; }
+
+template <int BN>
+struct Layout {
+    static constexpr int kStageLd = BN + 4;                      // padded staging rows: conflict-free row-per-thread float4 stores
+    static constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+    static size_t bytes(int nch) {
+        return 1024 + (size_t)RING * kSlotBytes + (size_t)2 * nch * BN * 128 + (size_t)BM * kStageLd * 4 + (size_t)2 * nch * BK * 4 +
+               (size_t)(2 * RING + 4) * 8 + 16;
+    }
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) fwd3_kernel(const FwdArgs a, const int ntiles) {
+    using L = Layout<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int nch1 = (a.C1 + BK - 1) / BK, nch2 = (a.C2 + BK - 1) / BK, nch = nch1 + nch2;
+    const int Kpad = nch * BK, Ktot = a.C1 + a.C2;
+    uint8_t* ring = smem;                                          // [RING][hi slab | lo slab]
+    uint8_t* w_hi = ring + RING * kSlotBytes;                      // [nch][BN rows × 128 B]
+    uint8_t* w_lo = w_hi + nch * BN * 128;
+    float* stage = reinterpret_cast<float*>(w_lo + nch * BN * 128);   // [BM][BN + 4]
+    float* s_sc = stage + BM * L::kStageLd;
+    float* s_sh = s_sc + Kpad;
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_sh + Kpad);     // producers → issuer, per ring slot
+    uint64_t* empty = full + RING;                                 // issuer (commit) → producers
+    uint64_t* tfull = empty + RING;                                // issuer (commit) → epilogue, per accumulator buffer
+    uint64_t* tempty = tfull + 2;                                  // epilogue → issuer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tmem_alloc(tmem_slot, L::kTmemCols);
+    if (tid == kEpiWarps * 32) {
+        for (int i = 0; i < RING; ++i) { mbar_init(full + i, kGroupWarps); mbar_init(empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, kEpiWarps); }
+        mbar_init_fence();
+    }
+    // weights: split once per CTA, resident in the operand layout for the whole kernel
+    for (int e = tid; e < BN * Kpad; e += kThreads) {
+        const int n = e / Kpad, k = e % Kpad, c = k / BK, kk = k % BK;
+        int col = -1;
+        if (c < nch1) { if (c * BK + kk < a.C1) col = c * BK + kk; }
+        else if ((c - nch1) * BK + kk < a.C2) col = a.C1 + (c - nch1) * BK + kk;
+        const float w = (col >= 0 && n < a.Cout) ? __ldg(a.W + (int64_t)n * Ktot + col) : 0.f;
+        float hi, lo;
+        split_tf32(w, hi, lo);
+        const uint32_t off = (uint32_t)(c * BN * 128) + slab_chunk_off(n, kk >> 2) + ((kk & 3) << 2);
+        *reinterpret_cast<float*>(w_hi + off) = hi;
+        *reinterpret_cast<float*>(w_lo + off) = lo;
+    }
+    for (int k = tid; k < Kpad; k += kThreads) {
+        float sc = 1.f, sh = 0.f;
+        if (a.scale1 && k < nch1 * BK && k < a.C1) { sc = __ldg(a.scale1 + k); sh = __ldg(a.shift1 + k); }
+        s_sc[k] = sc; s_sh[k] = sh;
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (warp > kEpiWarps) {
+        // ===================================================================== producers
+        // Slab q of this CTA's stream belongs to producer group q % kGroups.  A group loads its whole slab into registers, waits
+        // for the ring slot, converts and publishes it, then moves on to its next slab.  fence.proxy.async compiles to
+        // MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC and therefore waits for every global load the thread still has in flight — a thread
+        // that prefetched further slabs would serialise on HBM latency at each publish (measured: 1.4 us per slab) — so the
+        // memory-level parallelism comes from the kGroups groups being at different points of this loop, not from deeper
+        // per-thread prefetch.
+        const int g = (warp - (kEpiWarps + 1)) / kGroupWarps;
+        const int t = tid - (kEpiWarps + 1) * 32 - g * (kGroupWarps * 32);
+        const int c4 = t & 7, rb = t >> 3;                         // 16-byte column chunk; rows rb + kRowsPerPass·j
+        const int Q = my_tiles * nch;
+        for (int q = g; q < Q; q += kGroups) {
+            const int lt = q / nch, lc = q - lt * nch;
+            const int slot = q % RING;
+            const uint32_t use = (uint32_t)(q / RING);
+            const int64_t m0 = ((int64_t)blockIdx.x + (int64_t)lt * gridDim.x) * BM;
+            const bool seg1 = lc < nch1;
+            const float* X = seg1 ? a.X1 : a.X2;
+            const int C = seg1 ? a.C1 : a.C2;
+            const int col = (seg1 ? lc : lc - nch1) * BK + 4 * c4;
+            float4 buf[kLoadsPerSlab];
+            if (seg1 && a.idx1) {
+#pragma unroll
+                for (int j = 0; j < kLoadsPerSlab; ++j) {
+                    const int64_t m = m0 + rb + kRowsPerPass * j;
+                    const bool ok = (m < a.M) && (col < C);
+                    const int64_t srow = ok ? (m / a.rows_dst) * a.rows_src + __ldg(a.idx1 + m) : 0;
+                    buf[j] = ok ? __ldg(reinterpret_cast<const float4*>(X + srow * C + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else {
+                const float* base = X + (m0 + rb) * C + col;
+                const int64_t left = a.M - m0 - rb;                // rows of this thread's column that exist
+#pragma unroll
+                for (int j = 0; j < kLoadsPerSlab; ++j) {
+                    const bool ok = (kRowsPerPass * j < left) && (col < C);
+                    buf[j] = ok ? __ldg(reinterpret_cast<const float4*>(base + (int64_t)(kRowsPerPass * j) * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            // Ring slot `slot` alternates between two groups (kGroups = 2·RING).  mbarrier waits carry one parity bit, so a group
+            // may only look at a slot barrier when it is at most one phase behind: first wait until the previous use of the slot
+            // has been PUBLISHED by the other group, then until the tensor core has CONSUMED it.
+            if (use > 0) mbar_wait(full + slot, (use - 1) & 1);
+            mbar_wait(empty + slot, (use & 1) ^ 1);
+            const bool pro = seg1 && a.scale1;
+            const float4 sc = *reinterpret_cast<const float4*>(s_sc + lc * BK + 4 * c4);
+            const float4 sh = *reinterpret_cast<const float4*>(s_sh + lc * BK + 4 * c4);
+            uint8_t* hi_slab = ring + slot * kSlotBytes;
+#pragma unroll
+            for (int j = 0; j < kLoadsPerSlab; ++j) {
+                float4 v = buf[j];
+                if (pro) {
+                    v.x = lrelu(fmaf(v.x, sc.x, sh.x), a.slope1); v.y = lrelu(fmaf(v.y, sc.y, sh.y), a.slope1);
+                    v.z = lrelu(fmaf(v.z, sc.z, sh.z), a.slope1); v.w = lrelu(fmaf(v.w, sc.w, sh.w), a.slope1);
+                }
+                float4 h, l;
+                split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+                const uint32_t off = slab_chunk_off(rb + kRowsPerPass * j, c4);
+                *reinterpret_cast<float4*>(hi_slab + off) = h;
+                *reinterpret_cast<float4*>(hi_slab + kSlabBytes + off) = l;
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full + slot);
+        }
+    } else if (warp == kEpiWarps) {
+        // ===================================================================== MMA issuer (whole warp waits, one elected lane issues)
+        constexpr uint32_t idesc = idesc_tf32(BM, BN);
+        const uint32_t ring_u = smem_u32(ring), whi_u = smem_u32(w_hi), wlo_u = smem_u32(w_lo);
+        int slot = 0;
+        uint32_t use = 0;
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            const int buf = ti & 1;
+            mbar_wait(tempty + buf, ((uint32_t)(ti >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d = tmem + (uint32_t)(buf * BN);
+            for (int c = 0; c < nch; ++c) {
+                mbar_wait(full + slot, use & 1);
+                tc_fence_after();
+                const int kvalid = c < nch1 ? min(BK, a.C1 - c * BK) : min(BK, a.C2 - (c - nch1) * BK);
+                const int nk8 = (kvalid + 7) >> 3;
+                if (elect_one()) {
+                    const uint64_t ah0 = smem_desc_k128(ring_u + slot * kSlotBytes), al0 = smem_desc_k128(ring_u + slot * kSlotBytes + kSlabBytes);
+                    const uint64_t bh0 = smem_desc_k128(whi_u + c * BN * 128), bl0 = smem_desc_k128(wlo_u + c * BN * 128);
+#pragma unroll
+                    for (int k8 = 0; k8 < 4; ++k8) {
+                        if (k8 < nk8) {
+                            const uint64_t ko = (uint64_t)(k8 * 2);            // 32 bytes along K, in 16-byte descriptor units
+                            mma_tf32(d, al0 + ko, bh0 + ko, idesc, (c | k8) != 0);
+                            mma_tf32(d, ah0 + ko, bl0 + ko, idesc, 1);
+                            mma_tf32(d, ah0 + ko, bh0 + ko, idesc, 1);
+                        }
+                    }
+                    mma_commit(empty + slot);                      // slot reusable once these MMAs have read it
+                    if (c == nch - 1) mma_commit(tfull + buf);     // accumulator complete
+                }
+                __syncwarp();
+                if (++slot == RING) { slot = 0; ++use; }
+            }
+        }
+    } else {
+        // ===================================================================== epilogue (warps 0..3, one accumulator row per thread)
+        const int row = tid;                                       // TMEM lane == tile row
+        constexpr int LD = L::kStageLd;
+        constexpr int TPC = BM / BN;                               // threads per column in the statistics pass (each sums BN rows)
+        const int scol = tid % BN, spart = tid / BN;
+        constexpr int CH = BN / 4;                                 // 16-byte chunks per output row
+        const int ochunk = tid % CH, orow = tid / CH;
+        constexpr int RPP = BM / CH;                               // rows written per pass by the 128 threads
+        float ssum = 0.f, ssq = 0.f;
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            const int buf = ti & 1;
+            const int64_t m0 = ((int64_t)blockIdx.x + (int64_t)ti * gridDim.x) * BM;
+            const int valid = (int)min((int64_t)BM, a.M - m0);
+            mbar_wait(tfull + buf, (uint32_t)(ti >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN + c0), v);
+                if (a.bias) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] += (c0 + i < a.Cout) ? __ldg(a.bias + c0 + i) : 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; i += 4)
+                    *reinterpret_cast<float4*>(stage + row * LD + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty + buf);              // accumulator buffer free for tile ti + 2
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (4 * ochunk < a.Cout) {
+                for (int r = orow; r < valid; r += RPP)
+                    *reinterpret_cast<float4*>(a.Y + (m0 + r) * a.Cout + 4 * ochunk) = *reinterpret_cast<const float4*>(stage + r * LD + 4 * ochunk);
+            }
+            if (a.stats) {
+                const int r1 = min((spart + 1) * (BM / TPC), valid);
+                for (int r = spart * (BM / TPC); r < r1; ++r) {
+                    const float x = stage[r * LD + scol];
+                    ssum += x;
+                    ssq = fmaf(x, x, ssq);
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        if (a.stats && scol < a.Cout) {
+            float* st = a.stats + (size_t)(blockIdx.x % kStatSlots) * 2 * a.Cout;
+            atomicAdd(st + scol, ssum);
+            atomicAdd(st + a.Cout + scol, ssq);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, L::kTmemCols);
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+inline bool disabled() {
+    static const bool v = [] { const char* e = std::getenv("CRFCONV_NO_TCGEN05"); return e && e[0] == '1'; }();
+    return v;
+}
+
+}  // namespace lin3
+
+namespace lin {
+
+// tcgen05 forward: fp32-grade precision only (3xTF32); shapes of the hot path (Cout <= 64, <= 4 slabs of 32 input channels)
+bool try_fwd3(const FwdArgs& a, int precision, cudaStream_t st, int* rc) {
+    using namespace lin3;
+    if (disabled() || precision != 0) return false;
+    if (a.Cout > 64 || (a.Cout & 3) || (a.C1 & 3) || (a.C2 & 3) || a.C1 <= 0) return false;
+    const int nch = (a.C1 + BK - 1) / BK + (a.C2 + BK - 1) / BK;
+    if (nch > 4) return false;
+    if (!aligned16(a.X1) || (a.C2 && !aligned16(a.X2)) || !aligned16(a.Y)) return false;
+    const int ntiles = (int)ceil_div(a.M, BM);
+    if (ntiles <= 0) return false;
+    *rc = CRF_OK;
+    auto go = [&](auto bnv) {
+        constexpr int BN = decltype(bnv)::value;
+        const size_t smem = Layout<BN>::bytes(nch);
+        cudaError_t e = cudaFuncSetAttribute(fwd3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) {
+            fwd3_kernel<BN><<<std::min(ntiles, kNumSMs), kThreads, smem, st>>>(a, ntiles);
+            e = cudaPeekAtLastError();
+        }
+        if (e != cudaSuccess) *rc = (int)e;
+        return true;
+    };
+    if (a.Cout > 32) return go(std::integral_constant<int, 64>{});
+    if (a.Cout > 16) return go(std::integral_constant<int, 32>{});
+    return go(std::integral_constant<int, 16>{});
+}
+
+}  // namespace lin
+}  // namespace crf

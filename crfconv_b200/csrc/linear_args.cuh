@@ -53,6 +53,8 @@ struct WgradArgs {
 bool try_fwd2(const FwdArgs& a, int precision, cudaStream_t st, int* rc);
 bool try_dgrad2(const DgradArgs& a, int precision, cudaStream_t st, int* rc);
 bool try_wgrad2(const WgradArgs& a, int precision, cudaStream_t st, int* rc);
+// tcgen05 / TMEM forward (linear3.cu)
+bool try_fwd3(const FwdArgs& a, int precision, cudaStream_t st, int* rc);
 // CUDA-core kernels for hidden-width layers (linear_narrow.cu); w == nullptr ⇒ dgrad only
 bool try_narrow_fwd(const FwdArgs& a, cudaStream_t st, int* rc);
 bool try_narrow_bwd(const DgradArgs& d, const WgradArgs* w, cudaStream_t st, int* rc);

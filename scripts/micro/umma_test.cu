@@ -193,7 +193,77 @@ static int run(const char* name, bool exact_inputs) {
     return 0;
 }
 
+
+// ---- throughput probe: one elected lane issues `iters` MMAs back to back (descriptors precomputed, loop unrolled by 4) ----
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+template <int M, int N, int NACC>
+__global__ void __launch_bounds__(128) umma_rate_kernel(int iters, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* a_s = smem;                  // 128 × 128 B
+    uint8_t* b_s = smem + 128 * 128;      // N × 128 B
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    for (int i = tid; i < (128 + N) * 32; i += 128) ((float*)smem)[i] = 0.001f * (i % 7);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base;
+    if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc(M, N);
+        const uint64_t a0 = make_desc(smem_u32(a_s)), b0 = make_desc(smem_u32(b_s));
+        long long t0 = 0, t1 = 0;
+        if (elect_one()) {
+            t0 = clock64();
+            for (int i = 0; i < iters; i += 4) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) umma_tf32(tmem + (uint32_t)((j % NACC) * N), a0 + 2 * j, b0 + 2 * j, idesc, 1);
+            }
+            t1 = clock64();
+            umma_commit(&bar);
+        }
+        __syncwarp();
+        mbar_wait_bounded(&bar, 0);
+        const long long t2 = clock64();
+        if (t0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+template <int M, int N, int NACC>
+static void rate() {
+    long long* d;
+    cudaMalloc(&d, 16);
+    const size_t smem = (128 + N) * 128 + 1024;
+    auto kern = umma_rate_kernel<M, N, NACC>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int iters = 4096;
+    kern<<<1, 128, smem>>>(iters, d);
+    kern<<<1, 128, smem>>>(iters, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long h[2] = {0, 0};
+    cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    printf("rate M=%3d N=%3d nacc=%d: issue %.1f cyc/MMA, complete %.1f cyc/MMA  (math floor max(M,128)*N/256 = %d)  %s\n", M, N, NACC,
+           (double)h[0] / iters, (double)h[1] / iters, (M > 128 ? M : 128) * N / 256, e == cudaSuccess ? "" : cudaGetErrorString(e));
+    cudaFree(d);
+}
+
 int main() {
+    rate<128, 16, 1>(); rate<128, 32, 1>(); rate<128, 64, 1>(); rate<128, 64, 2>(); rate<128, 128, 1>(); rate<128, 256, 1>(); rate<128, 256, 2>();
+    rate<64, 16, 1>(); rate<64, 64, 1>(); rate<64, 128, 1>(); rate<64, 256, 1>();
     int rc = 0;
     rc |= run<64, 1, false>("exact  ", true);
     rc |= run<64, 2, false>("exact2 ", true);
