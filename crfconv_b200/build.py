@@ -65,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(obj)
         if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t):
             continue
-        cmd = [nvcc, *NVCC_FLAGS, *_ccbin(), *inc, "-c", src, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("CRFCONV_NVCC_EXTRA", "").split(), *_ccbin(), *inc, "-c", src, "-o", obj]
         if verbose:
             cmd[1:1] = ["-Xptxas", "-v"]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -40,6 +40,21 @@ static_assert(kGroups == RING || kGroups == 2 * RING, "slot hand-over protocol b
 constexpr int kSlabBytes = BM * 128;                             // one [128 × 32] fp32 slab
 constexpr int kSlotBytes = 2 * kSlabBytes;                       // hi + lo
 
+// Development aid (-DCRF_FWD3_TRACE): CTA 0 appends (event, index, clock) records; read back with crfconv_debug_fwd3_trace.
+#ifdef CRF_FWD3_TRACE
+__device__ long long g_trace[3 * 8192];
+__device__ int g_trace_n;
+__device__ __forceinline__ void trace(int ev, int idx) {      // fixed record slot per (event, index): plain stores, no atomics
+    if (blockIdx.x != 0) return;
+    const int i = ev <= 4 ? idx * 4 + (ev - 1) : (ev <= 6 ? 400 + idx * 2 + (ev - 5) : 700 + idx * 3 + (ev - 7));
+    if (i < 8192) { g_trace[3 * i] = ev; g_trace[3 * i + 1] = idx; g_trace[3 * i + 2] = clock64(); }
+    g_trace_n = 1000;
+}
+#define CRF_TRACE(ev, idx) trace(ev, idx)
+#else
+#define CRF_TRACE(ev, idx)
+#endif
+
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.0f ? v : v * slope; }
 
 template <int BN>
@@ -47,7 +62,7 @@ struct Layout {
     static constexpr int kStageLd = BN + 4;                      // padded staging rows: conflict-free row-per-thread float4 stores
     static constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
     static size_t bytes(int nch) {
-        return 1024 + (size_t)RING * kSlotBytes + (size_t)2 * nch * BN * 128 + (size_t)BM * kStageLd * 4 + (size_t)2 * nch * BK * 4 +
+        return (size_t)RING * kSlotBytes + (size_t)2 * nch * BN * 128 + (size_t)BM * kStageLd * 4 + (size_t)2 * nch * BK * 4 +
                (size_t)(2 * RING + 4) * 8 + 16;
     }
 };
@@ -55,8 +70,9 @@ struct Layout {
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1) fwd3_kernel(const FwdArgs a, const int ntiles) {
     using L = Layout<BN>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // Declared 1024-byte aligned (operand slabs need it for SWIZZLE_128B) and used through plain pointer arithmetic only: an
+    // integer round-trip to align by hand makes the compiler lose the address space and emit generic ST.E/LD.E instead of STS/LDS.
+    extern __shared__ __align__(1024) uint8_t smem[];
     const int nch1 = (a.C1 + BK - 1) / BK, nch2 = (a.C2 + BK - 1) / BK, nch = nch1 + nch2;
     const int Kpad = nch * BK, Ktot = a.C1 + a.C2;
     uint8_t* ring = smem;                                          // [RING][hi slab | lo slab]
@@ -101,6 +117,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd3_kernel(const FwdArgs a, cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    if ((smem_u32(smem) & 1023u) != 0) __trap();                  // dynamic shared memory base not 1024-byte aligned
     const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (warp > kEpiWarps) {
@@ -142,31 +159,49 @@ __global__ void __launch_bounds__(kThreads, 1) fwd3_kernel(const FwdArgs a, cons
                     buf[j] = ok ? __ldg(reinterpret_cast<const float4*>(base + (int64_t)(kRowsPerPass * j) * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
+            // BatchNorm + LeakyReLU prologue in place, BEFORE asking for the ring slot (this is where the thread waits for its loads)
+            if (seg1 && a.scale1) {
+                const float4 sc = *reinterpret_cast<const float4*>(s_sc + lc * BK + 4 * c4);
+                const float4 sh = *reinterpret_cast<const float4*>(s_sh + lc * BK + 4 * c4);
+                const float sl = a.slope1;
+                if (sl >= 0.f && sl <= 1.f) {                       // lrelu(v) = max(v, slope·v) for slopes in [0, 1]
+#pragma unroll
+                    for (int j = 0; j < kLoadsPerSlab; ++j) {
+                        float4 v = buf[j];
+                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                        buf[j] = make_float4(fmaxf(v.x, v.x * sl), fmaxf(v.y, v.y * sl), fmaxf(v.z, v.z * sl), fmaxf(v.w, v.w * sl));
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kLoadsPerSlab; ++j) {
+                        float4 v = buf[j];
+                        buf[j] = make_float4(lrelu(fmaf(v.x, sc.x, sh.x), sl), lrelu(fmaf(v.y, sc.y, sh.y), sl), lrelu(fmaf(v.z, sc.z, sh.z), sl),
+                                             lrelu(fmaf(v.w, sc.w, sh.w), sl));
+                    }
+                }
+            }
             // Ring slot `slot` alternates between two groups (kGroups = 2·RING).  mbarrier waits carry one parity bit, so a group
             // may only look at a slot barrier when it is at most one phase behind: first wait until the previous use of the slot
             // has been PUBLISHED by the other group, then until the tensor core has CONSUMED it.
-            if (use > 0) mbar_wait(full + slot, (use - 1) & 1);
-            mbar_wait(empty + slot, (use & 1) ^ 1);
-            const bool pro = seg1 && a.scale1;
-            const float4 sc = *reinterpret_cast<const float4*>(s_sc + lc * BK + 4 * c4);
-            const float4 sh = *reinterpret_cast<const float4*>(s_sh + lc * BK + 4 * c4);
+            if (use > 0) mbar_wait_relaxed(full + slot, (use - 1) & 1);
+            if (t == 0) CRF_TRACE(1, q);                       // previous use published
+            mbar_wait_relaxed(empty + slot, (use & 1) ^ 1);
+            if (t == 0) CRF_TRACE(2, q);                       // slot acquired
             uint8_t* hi_slab = ring + slot * kSlotBytes;
 #pragma unroll
             for (int j = 0; j < kLoadsPerSlab; ++j) {
-                float4 v = buf[j];
-                if (pro) {
-                    v.x = lrelu(fmaf(v.x, sc.x, sh.x), a.slope1); v.y = lrelu(fmaf(v.y, sc.y, sh.y), a.slope1);
-                    v.z = lrelu(fmaf(v.z, sc.z, sh.z), a.slope1); v.w = lrelu(fmaf(v.w, sc.w, sh.w), a.slope1);
-                }
+                const float4 v = buf[j];
                 float4 h, l;
                 split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
                 const uint32_t off = slab_chunk_off(rb + kRowsPerPass * j, c4);
                 *reinterpret_cast<float4*>(hi_slab + off) = h;
                 *reinterpret_cast<float4*>(hi_slab + kSlabBytes + off) = l;
             }
+            if (t == 0) CRF_TRACE(3, q);                       // converted (data had arrived)
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(full + slot);
+            if (t == 0) CRF_TRACE(4, q);                       // published
         }
     } else if (warp == kEpiWarps) {
         // ===================================================================== MMA issuer (whole warp waits, one elected lane issues)
@@ -185,6 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd3_kernel(const FwdArgs a, cons
                 const int kvalid = c < nch1 ? min(BK, a.C1 - c * BK) : min(BK, a.C2 - (c - nch1) * BK);
                 const int nk8 = (kvalid + 7) >> 3;
                 if (elect_one()) {
+                    CRF_TRACE(5, ti * nch + c);                  // issuer saw the slab
                     const uint64_t ah0 = smem_desc_k128(ring_u + slot * kSlotBytes), al0 = smem_desc_k128(ring_u + slot * kSlotBytes + kSlabBytes);
                     const uint64_t bh0 = smem_desc_k128(whi_u + c * BN * 128), bl0 = smem_desc_k128(wlo_u + c * BN * 128);
 #pragma unroll
@@ -198,6 +234,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd3_kernel(const FwdArgs a, cons
                     }
                     mma_commit(empty + slot);                      // slot reusable once these MMAs have read it
                     if (c == nch - 1) mma_commit(tfull + buf);     // accumulator complete
+                    CRF_TRACE(6, ti * nch + c);                  // MMAs issued
                 }
                 __syncwarp();
                 if (++slot == RING) { slot = 0; ++use; }
@@ -207,8 +244,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd3_kernel(const FwdArgs a, cons
         // ===================================================================== epilogue (warps 0..3, one accumulator row per thread)
         const int row = tid;                                       // TMEM lane == tile row
         constexpr int LD = L::kStageLd;
-        constexpr int TPC = BM / BN;                               // threads per column in the statistics pass (each sums BN rows)
-        const int scol = tid % BN, spart = tid / BN;
+        const int scol = tid % BN, spart = tid / BN;               // statistics pass: BM / BN threads per column, BN rows each
         constexpr int CH = BN / 4;                                 // 16-byte chunks per output row
         const int ochunk = tid % CH, orow = tid / CH;
         constexpr int RPP = BM / CH;                               // rows written per pass by the 128 threads
@@ -217,37 +253,78 @@ __global__ void __launch_bounds__(kThreads, 1) fwd3_kernel(const FwdArgs a, cons
             const int buf = ti & 1;
             const int64_t m0 = ((int64_t)blockIdx.x + (int64_t)ti * gridDim.x) * BM;
             const int valid = (int)min((int64_t)BM, a.M - m0);
-            mbar_wait(tfull + buf, (uint32_t)(ti >> 1) & 1);
+            mbar_wait_relaxed(tfull + buf, (uint32_t)(ti >> 1) & 1);
             tc_fence_after();
+            if (tid == 0) CRF_TRACE(7, ti);                    // accumulator complete
+            {
+                uint32_t v[BN / 16][16];
 #pragma unroll
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                float v[16];
-                tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN + c0), v);
-                if (a.bias) {
+                for (int cb = 0; cb < BN / 16; ++cb) tmem_ld16_issue(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN + cb * 16), v[cb]);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty + buf);          // accumulator buffer free for tile ti + 2
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] += (c0 + i < a.Cout) ? __ldg(a.bias + c0 + i) : 0.f;
-                }
+                for (int cb = 0; cb < BN / 16; ++cb) {
 #pragma unroll
-                for (int i = 0; i < 16; i += 4)
-                    *reinterpret_cast<float4*>(stage + row * LD + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty + buf);              // accumulator buffer free for tile ti + 2
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (4 * ochunk < a.Cout) {
-                for (int r = orow; r < valid; r += RPP)
-                    *reinterpret_cast<float4*>(a.Y + (m0 + r) * a.Cout + 4 * ochunk) = *reinterpret_cast<const float4*>(stage + r * LD + 4 * ochunk);
-            }
-            if (a.stats) {
-                const int r1 = min((spart + 1) * (BM / TPC), valid);
-                for (int r = spart * (BM / TPC); r < r1; ++r) {
-                    const float x = stage[r * LD + scol];
-                    ssum += x;
-                    ssq = fmaf(x, x, ssq);
+                    for (int i = 0; i < 16; i += 4) {
+                        float4 o = make_float4(__uint_as_float(v[cb][i]), __uint_as_float(v[cb][i + 1]), __uint_as_float(v[cb][i + 2]),
+                                               __uint_as_float(v[cb][i + 3]));
+                        if (a.bias) {
+                            const int c = cb * 16 + i;
+                            o.x += c < a.Cout ? __ldg(a.bias + c) : 0.f;         o.y += c + 1 < a.Cout ? __ldg(a.bias + c + 1) : 0.f;
+                            o.z += c + 2 < a.Cout ? __ldg(a.bias + c + 2) : 0.f; o.w += c + 3 < a.Cout ? __ldg(a.bias + c + 3) : 0.f;
+                        }
+                        *reinterpret_cast<float4*>(stage + row * LD + cb * 16 + i) = o;
+                    }
                 }
             }
+            if (tid == 0) CRF_TRACE(8, ti);                    // TMEM read out
             asm volatile("bar.sync 1, 128;" ::: "memory");
+            const bool colok = 4 * ochunk < a.Cout;
+            if (valid == BM) {                                     // full tile: compile-time trip counts, loads batched ahead of their uses
+                if (colok) {
+                    float* yp = a.Y + (m0 + orow) * a.Cout + 4 * ochunk;
+                    const float* sp = stage + orow * LD + 4 * ochunk;
+#pragma unroll
+                    for (int i0 = 0; i0 < CH; i0 += 8) {
+                        float4 tmp[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (i0 + i < CH) tmp[i] = *reinterpret_cast<const float4*>(sp + (i0 + i) * RPP * LD);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (i0 + i < CH) *reinterpret_cast<float4*>(yp + (int64_t)(i0 + i) * RPP * a.Cout) = tmp[i];
+                    }
+                }
+                if (a.stats) {
+                    const float* sp = stage + spart * BN * LD + scol;
+                    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+                    for (int r = 0; r < BN; r += 2) {
+                        const float x0 = sp[r * LD], x1 = sp[(r + 1) * LD];
+                        s0 += x0; s1 += x1;
+                        q0 = fmaf(x0, x0, q0); q1 = fmaf(x1, x1, q1);
+                    }
+                    ssum += s0 + s1;
+                    ssq += q0 + q1;
+                }
+            } else {
+                if (colok) {
+                    for (int r = orow; r < valid; r += RPP)
+                        *reinterpret_cast<float4*>(a.Y + (m0 + r) * a.Cout + 4 * ochunk) = *reinterpret_cast<const float4*>(stage + r * LD + 4 * ochunk);
+                }
+                if (a.stats) {
+                    const int r1 = min((spart + 1) * BN, valid);
+                    for (int r = spart * BN; r < r1; ++r) {
+                        const float x = stage[r * LD + scol];
+                        ssum += x;
+                        ssq = fmaf(x, x, ssq);
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (tid == 0) CRF_TRACE(9, ti);                    // tile stored
         }
         if (a.stats && scol < a.Cout) {
             float* st = a.stats + (size_t)(blockIdx.x % kStatSlots) * 2 * a.Cout;
@@ -268,6 +345,18 @@ inline bool disabled() {
 }
 
 }  // namespace lin3
+
+#ifdef CRF_FWD3_TRACE
+extern "C" int crfconv_debug_fwd3_trace(long long* out, int max_records, int reset) {
+    int n = 0;
+    cudaMemcpyFromSymbol(&n, lin3::g_trace_n, sizeof(int));
+    if (n > 8192) n = 8192;
+    if (n > max_records) n = max_records;
+    if (out && n > 0) cudaMemcpyFromSymbol(out, lin3::g_trace, (size_t)n * 3 * sizeof(long long));
+    if (reset) { const int z = 0; cudaMemcpyToSymbol(lin3::g_trace_n, &z, sizeof(int)); }
+    return n;
+}
+#endif
 
 namespace lin {
 
