@@ -46,9 +46,9 @@ __device__ long long g_trace[3 * 8192];
 __device__ int g_trace_n;
 __device__ __forceinline__ void trace(int ev, int idx) {      // fixed record slot per (event, index): plain stores, no atomics
     if (blockIdx.x != 0) return;
-    const int i = ev <= 4 ? idx * 4 + (ev - 1) : (ev <= 6 ? 400 + idx * 2 + (ev - 5) : 700 + idx * 3 + (ev - 7));
+    const int i = ev <= 4 ? idx * 4 + (ev - 1) : (ev <= 6 ? 400 + idx * 2 + (ev - 5) : (ev <= 9 ? 700 + idx * 3 + (ev - 7) : 1000 + idx * 4 + (ev - 10)));
     if (i < 8192) { g_trace[3 * i] = ev; g_trace[3 * i + 1] = idx; g_trace[3 * i + 2] = clock64(); }
-    g_trace_n = 1000;
+    g_trace_n = 1400;
 }
 #define CRF_TRACE(ev, idx) trace(ev, idx)
 #else
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd3_kernel(const FwdArgs a, cons
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) tmem_alloc(tmem_slot, L::kTmemCols);
     if (tid == kEpiWarps * 32) {
-        for (int i = 0; i < RING; ++i) { mbar_init(full + i, kGroupWarps); mbar_init(empty + i, 1); }
+        for (int i = 0; i < RING; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, kEpiWarps); }
         mbar_init_fence();
     }
@@ -142,15 +142,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd3_kernel(const FwdArgs a, cons
             const int C = seg1 ? a.C1 : a.C2;
             const int col = (seg1 ? lc : lc - nch1) * BK + 4 * c4;
             float4 buf[kLoadsPerSlab];
-            if (seg1 && a.idx1) {
-#pragma unroll
-                for (int j = 0; j < kLoadsPerSlab; ++j) {
-                    const int64_t m = m0 + rb + kRowsPerPass * j;
-                    const bool ok = (m < a.M) && (col < C);
-                    const int64_t srow = ok ? (m / a.rows_dst) * a.rows_src + __ldg(a.idx1 + m) : 0;
-                    buf[j] = ok ? __ldg(reinterpret_cast<const float4*>(X + srow * C + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            } else {
+            {
                 const float* base = X + (m0 + rb) * C + col;
                 const int64_t left = a.M - m0 - rb;                // rows of this thread's column that exist
 #pragma unroll
@@ -164,20 +156,11 @@ __global__ void __launch_bounds__(kThreads, 1) fwd3_kernel(const FwdArgs a, cons
                 const float4 sc = *reinterpret_cast<const float4*>(s_sc + lc * BK + 4 * c4);
                 const float4 sh = *reinterpret_cast<const float4*>(s_sh + lc * BK + 4 * c4);
                 const float sl = a.slope1;
-                if (sl >= 0.f && sl <= 1.f) {                       // lrelu(v) = max(v, slope·v) for slopes in [0, 1]
 #pragma unroll
-                    for (int j = 0; j < kLoadsPerSlab; ++j) {
-                        float4 v = buf[j];
-                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-                        buf[j] = make_float4(fmaxf(v.x, v.x * sl), fmaxf(v.y, v.y * sl), fmaxf(v.z, v.z * sl), fmaxf(v.w, v.w * sl));
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < kLoadsPerSlab; ++j) {
-                        float4 v = buf[j];
-                        buf[j] = make_float4(lrelu(fmaf(v.x, sc.x, sh.x), sl), lrelu(fmaf(v.y, sc.y, sh.y), sl), lrelu(fmaf(v.z, sc.z, sh.z), sl),
-                                             lrelu(fmaf(v.w, sc.w, sh.w), sl));
-                    }
+                for (int j = 0; j < kLoadsPerSlab; ++j) {               // lrelu(v) = max(v, slope·v): slopes in [0, 1] only (checked by try_fwd3)
+                    float4 v = buf[j];
+                    v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                    buf[j] = make_float4(fmaxf(v.x, v.x * sl), fmaxf(v.y, v.y * sl), fmaxf(v.z, v.z * sl), fmaxf(v.w, v.w * sl));
                 }
             }
             // Ring slot `slot` alternates between two groups (kGroups = 2·RING).  mbarrier waits carry one parity bit, so a group
@@ -199,8 +182,10 @@ __global__ void __launch_bounds__(kThreads, 1) fwd3_kernel(const FwdArgs a, cons
             }
             if (t == 0) CRF_TRACE(3, q);                       // converted (data had arrived)
             fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full + slot);
+            // the group's warps advance together (named barrier 2 + g): the parity argument above needs "this group has published
+            // use U−2" to hold for every warp of the group before any of them looks at the slot barriers again
+            asm volatile("bar.sync %0, %1;" ::"r"(2 + g), "n"(kGroupWarps * 32) : "memory");
+            if (t == 0) mbar_arrive(full + slot);
             if (t == 0) CRF_TRACE(4, q);                       // published
         }
     } else if (warp == kEpiWarps) {
@@ -215,14 +200,17 @@ __global__ void __launch_bounds__(kThreads, 1) fwd3_kernel(const FwdArgs a, cons
             tc_fence_after();
             const uint32_t d = tmem + (uint32_t)(buf * BN);
             for (int c = 0; c < nch; ++c) {
+                if (lane == 0) CRF_TRACE(10, ti * nch + c);      // loop top
                 mbar_wait(full + slot, use & 1);
                 tc_fence_after();
+                if (lane == 0) CRF_TRACE(11, ti * nch + c);      // slab visible
                 const int kvalid = c < nch1 ? min(BK, a.C1 - c * BK) : min(BK, a.C2 - (c - nch1) * BK);
                 const int nk8 = (kvalid + 7) >> 3;
                 if (elect_one()) {
                     CRF_TRACE(5, ti * nch + c);                  // issuer saw the slab
                     const uint64_t ah0 = smem_desc_k128(ring_u + slot * kSlotBytes), al0 = smem_desc_k128(ring_u + slot * kSlotBytes + kSlabBytes);
                     const uint64_t bh0 = smem_desc_k128(whi_u + c * BN * 128), bl0 = smem_desc_k128(wlo_u + c * BN * 128);
+                    CRF_TRACE(12, ti * nch + c);                 // descriptors ready
 #pragma unroll
                     for (int k8 = 0; k8 < 4; ++k8) {
                         if (k8 < nk8) {
@@ -232,6 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd3_kernel(const FwdArgs a, cons
                             mma_tf32(d, ah0 + ko, bh0 + ko, idesc, 1);
                         }
                     }
+                    CRF_TRACE(13, ti * nch + c);                 // MMAs issued, before the commits
                     mma_commit(empty + slot);                      // slot reusable once these MMAs have read it
                     if (c == nch - 1) mma_commit(tfull + buf);     // accumulator complete
                     CRF_TRACE(6, ti * nch + c);                  // MMAs issued
@@ -364,6 +353,7 @@ namespace lin {
 bool try_fwd3(const FwdArgs& a, int precision, cudaStream_t st, int* rc) {
     using namespace lin3;
     if (disabled() || precision != 0) return false;
+    if (a.idx1 || (a.scale1 && !(a.slope1 >= 0.f && a.slope1 <= 1.f))) return false;   // gathered rows / expanding slopes: older kernels
     if (a.Cout > 64 || (a.Cout & 3) || (a.C1 & 3) || (a.C2 & 3) || a.C1 <= 0) return false;
     const int nch = (a.C1 + BK - 1) / BK + (a.C2 + BK - 1) / BK;
     if (nch > 4) return false;

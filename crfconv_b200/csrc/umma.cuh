@@ -33,31 +33,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded by TIME (≈2 s of SM clock): a mis-programmed pipeline traps (surfacing as a CUDA error at the C ABI) instead of
-// hanging the device.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
+// Waits are bounded by TIME (≈2 s of SM clock): a mis-programmed pipeline traps (surfacing as a CUDA error at the C ABI)
+// instead of hanging the device.  The slow path is kept out of line: the kernels' three warp roles share a small instruction
+// cache, and an inlined printf call site per wait would triple the size of the issue loop.
+__device__ __noinline__ void mbar_timeout() {
+    printf("crfconv_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+    __trap();
+}
+__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, unsigned sleep_ns) {
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
-            printf("crfconv_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-            __trap();
-        }
+        if (sleep_ns) __nanosleep(sleep_ns);
+        if (clock64() - t0 > 4000000000LL) mbar_timeout();
     }
 }
-
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, 0);
+}
 // Same, for warps that can afford a slower wake-up: sleeps between polls so that waiting warps leave the issue slots to the
 // warps that are converting / storing.
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        __nanosleep(40);
-        if (clock64() - t0 > 4000000000LL) {
-            printf("crfconv_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-            __trap();
-        }
-    }
+    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, 40);
 }
 
 // one lane of a converged warp; unlike `lane == 0` the compiler knows the region is single-threaded and issues tcgen05

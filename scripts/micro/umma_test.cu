@@ -261,7 +261,73 @@ static void rate() {
     cudaFree(d);
 }
 
+
+// ---- issuer-loop probe: per "slab" 12 MMAs + commit, optionally an (already satisfied) mbarrier wait, syncwarp and a fresh election ----
+template <int N, int MODE>
+__global__ void __launch_bounds__(128) umma_loop_kernel(int slabs, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem_dyn[];
+    uint8_t* a_s = smem_dyn;
+    uint8_t* b_s = smem_dyn + 128 * 128;
+    __shared__ uint64_t bar_commit, bar_ready;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) { mbar_init(&bar_commit, 1); mbar_init(&bar_ready, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    for (int i = tid; i < (128 + N) * 32; i += 128) ((float*)smem_dyn)[i] = 0.001f * (i % 7);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base;
+    if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc(128, N);
+        const uint64_t a0 = make_desc(smem_u32(a_s)), b0 = make_desc(smem_u32(b_s));
+        const long long t0 = clock64();
+        for (int s = 0; s < slabs; ++s) {
+            if (MODE >= 1) { while (!mbar_try_wait(&bar_ready, 1)) {} asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+            if (elect_one()) {
+#pragma unroll
+                for (int j = 0; j < 12; ++j) umma_tf32(tmem, a0 + 2 * (j & 3), b0 + 2 * (j & 3), idesc, 1);
+                if (MODE != 3) umma_commit(&bar_commit);
+            }
+            if (MODE >= 2) __syncwarp();
+        }
+        const long long t1 = clock64();
+        if (elect_one()) umma_commit(&bar_ready);     // final: wait for everything
+        __syncwarp();
+        // bar_ready phase 0 completes when all MMAs are done
+        for (uint32_t i = 0; i < (1u << 24); ++i) if (mbar_try_wait(&bar_ready, 0)) break;
+        const long long t2 = clock64();
+        if ((tid & 31) == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+template <int N, int MODE>
+static void loop_rate() {
+    long long* d;
+    cudaMalloc(&d, 16);
+    const size_t smem = (128 + N) * 128;
+    auto kern = umma_loop_kernel<N, MODE>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int slabs = 512;
+    kern<<<1, 128, smem>>>(slabs, d);
+    kern<<<1, 128, smem>>>(slabs, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long h[2] = {0, 0};
+    cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    printf("issuer loop N=%3d mode=%d (0: mma+commit, 1: +wait, 2: +syncwarp, 3: no commit): issue %.0f cyc/slab, complete %.0f cyc/slab  %s\n", N, MODE,
+           (double)h[0] / slabs, (double)h[1] / slabs, e == cudaSuccess ? "" : cudaGetErrorString(e));
+    cudaFree(d);
+}
+
 int main() {
+    loop_rate<64, 0>(); loop_rate<64, 1>(); loop_rate<64, 2>(); loop_rate<64, 3>(); loop_rate<16, 2>();
+
     rate<128, 16, 1>(); rate<128, 32, 1>(); rate<128, 64, 1>(); rate<128, 64, 2>(); rate<128, 128, 1>(); rate<128, 256, 1>(); rate<128, 256, 2>();
     rate<64, 16, 1>(); rate<64, 64, 1>(); rate<64, 128, 1>(); rate<64, 256, 1>();
     int rc = 0;

@@ -30,7 +30,7 @@ rec = rec[rec[:, 0] > 0]
 n = len(rec)
 t0 = rec[:, 2].min()
 names = {1: "P loads issued", 2: "P slot acquired", 3: "P converted", 4: "P published", 5: "I saw slab", 6: "I mma issued", 7: "E acc complete",
-         8: "E tmem read", 9: "E tile stored"}
+         8: "E tmem read", 9: "E tile stored", 10: "I loop top", 11: "I slab visible", 12: "I desc", 13: "I mmas issued"}
 rec = rec[np.argsort(rec[:, 2], kind="stable")]
 print(f"{n} records; total span {(rec[:, 2].max() - t0) / 1.9e3:.1f} us (at 1.9 GHz)")
 lim = int(os.environ.get("LIMIT", 0))
@@ -40,11 +40,19 @@ for ev, idx, t in rec[:lim]:
 import collections
 per = collections.defaultdict(dict)
 for ev, idx, t in rec:
-    per[(int(ev) <= 6, int(idx))][int(ev)] = (t - t0) / 1.9e3
+    if int(ev) <= 9: per[(int(ev) <= 6, int(idx))][int(ev)] = (t - t0) / 1.9e3
 print("slab: issued -> slot -> converted -> published | issuer saw -> issued")
 for q in range(0, 52):
     d = per.get((True, q), {})
     print(q, " ".join(f"{d.get(k, float('nan')):7.2f}" for k in (1, 2, 3, 4, 5, 6)))
+print("issuer per slab: loop top -> slab visible -> elected(5) -> desc ready -> mmas issued -> committed(6)")
+fine = collections.defaultdict(dict)
+for ev, idx, t in rec:
+    if int(ev) >= 10 or int(ev) in (5, 6):
+        fine[int(idx)][int(ev)] = (t - t0) / 1.9e3
+for q in range(8, 40):
+    d = fine.get(q, {})
+    print(q, " ".join(f"{d.get(k, float('nan')):7.2f}" for k in (10, 11, 5, 12, 13, 6)))
 print("tile: acc complete -> tmem read -> stored")
 for ti in range(13):
     d = per.get((False, ti), {})
