@@ -190,8 +190,19 @@ __global__ void __launch_bounds__(kThreads, 1) fwd3_kernel(const FwdArgs a, cons
         }
     } else if (warp == kEpiWarps) {
         // ===================================================================== MMA issuer (whole warp waits, one elected lane issues)
+        // The loop below is the kernel's critical path (one slab per iteration, ≈600 cycles of MMA issue): everything that
+        // does not depend on the slot is hoisted, the chunk loop is unrolled so per-chunk constants sit in registers, and a full
+        // chunk issues its 12 MMAs without predicates.
         constexpr uint32_t idesc = idesc_tf32(BM, BN);
-        const uint32_t ring_u = smem_u32(ring), whi_u = smem_u32(w_hi), wlo_u = smem_u32(w_lo);
+        const uint64_t a_desc0 = smem_desc_k128(smem_u32(ring));          // + slot·(kSlotBytes/16), + kSlabBytes/16 for lo
+        const uint64_t bh_desc0 = smem_desc_k128(smem_u32(w_hi));         // + c·(BN·128/16)
+        const uint64_t bl_desc0 = smem_desc_k128(smem_u32(w_lo));
+        int nk8[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int kvalid = c < nch1 ? min(BK, a.C1 - c * BK) : min(BK, a.C2 - (c - nch1) * BK);
+            nk8[c] = c < nch ? (kvalid + 7) >> 3 : 0;
+        }
         int slot = 0;
         uint32_t use = 0;
         for (int ti = 0; ti < my_tiles; ++ti) {
@@ -199,34 +210,40 @@ __global__ void __launch_bounds__(kThreads, 1) fwd3_kernel(const FwdArgs a, cons
             mbar_wait(tempty + buf, ((uint32_t)(ti >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint32_t d = tmem + (uint32_t)(buf * BN);
-            for (int c = 0; c < nch; ++c) {
-                if (lane == 0) CRF_TRACE(10, ti * nch + c);      // loop top
-                mbar_wait(full + slot, use & 1);
-                tc_fence_after();
-                if (lane == 0) CRF_TRACE(11, ti * nch + c);      // slab visible
-                const int kvalid = c < nch1 ? min(BK, a.C1 - c * BK) : min(BK, a.C2 - (c - nch1) * BK);
-                const int nk8 = (kvalid + 7) >> 3;
-                if (elect_one()) {
-                    CRF_TRACE(5, ti * nch + c);                  // issuer saw the slab
-                    const uint64_t ah0 = smem_desc_k128(ring_u + slot * kSlotBytes), al0 = smem_desc_k128(ring_u + slot * kSlotBytes + kSlabBytes);
-                    const uint64_t bh0 = smem_desc_k128(whi_u + c * BN * 128), bl0 = smem_desc_k128(wlo_u + c * BN * 128);
-                    CRF_TRACE(12, ti * nch + c);                 // descriptors ready
 #pragma unroll
-                    for (int k8 = 0; k8 < 4; ++k8) {
-                        if (k8 < nk8) {
-                            const uint64_t ko = (uint64_t)(k8 * 2);            // 32 bytes along K, in 16-byte descriptor units
-                            mma_tf32(d, al0 + ko, bh0 + ko, idesc, (c | k8) != 0);
-                            mma_tf32(d, ah0 + ko, bl0 + ko, idesc, 1);
-                            mma_tf32(d, ah0 + ko, bh0 + ko, idesc, 1);
+            for (int c = 0; c < 4; ++c) {
+                if (c < nch) {
+                    if (lane == 0) CRF_TRACE(10, ti * nch + c);      // loop top
+                    mbar_wait(full + slot, use & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        CRF_TRACE(5, ti * nch + c);                  // issuer saw the slab
+                        const uint64_t ah0 = a_desc0 + (uint64_t)(slot * (kSlotBytes / 16)), al0 = ah0 + kSlabBytes / 16;
+                        const uint64_t bh0 = bh_desc0 + (uint64_t)(c * (BN * 128 / 16)), bl0 = bl_desc0 + (uint64_t)(c * (BN * 128 / 16));
+                        if (nk8[c] == 4) {
+#pragma unroll
+                            for (int k8 = 0; k8 < 4; ++k8) {           // 32 bytes along K = 2 descriptor units per step
+                                mma_tf32(d, al0 + 2 * k8, bh0 + 2 * k8, idesc, (c | k8) != 0);
+                                mma_tf32(d, ah0 + 2 * k8, bl0 + 2 * k8, idesc, 1);
+                                mma_tf32(d, ah0 + 2 * k8, bh0 + 2 * k8, idesc, 1);
+                            }
+                        } else {
+#pragma unroll
+                            for (int k8 = 0; k8 < 3; ++k8) {
+                                if (k8 < nk8[c]) {
+                                    mma_tf32(d, al0 + 2 * k8, bh0 + 2 * k8, idesc, (c | k8) != 0);
+                                    mma_tf32(d, ah0 + 2 * k8, bl0 + 2 * k8, idesc, 1);
+                                    mma_tf32(d, ah0 + 2 * k8, bh0 + 2 * k8, idesc, 1);
+                                }
+                            }
                         }
+                        CRF_TRACE(13, ti * nch + c);                 // MMAs issued, before the commits
+                        mma_commit(empty + slot);                      // slot reusable once these MMAs have read it
+                        if (c == nch - 1) mma_commit(tfull + buf);     // accumulator complete
+                        CRF_TRACE(6, ti * nch + c);
                     }
-                    CRF_TRACE(13, ti * nch + c);                 // MMAs issued, before the commits
-                    mma_commit(empty + slot);                      // slot reusable once these MMAs have read it
-                    if (c == nch - 1) mma_commit(tfull + buf);     // accumulator complete
-                    CRF_TRACE(6, ti * nch + c);                  // MMAs issued
+                    if (++slot == RING) { slot = 0; ++use; }
                 }
-                __syncwarp();
-                if (++slot == RING) { slot = 0; ++use; }
             }
         }
     } else {
