@@ -727,6 +727,7 @@ int crfconv_linear_bwd(const float* dY, const float* H, const float* act_ref, co
         lin::WgradArgs a{dY, H, bn, X1, C1, scale1, shift1, slope1, idx1, rows_dst, rows_src, X2, C2, wdst, dbias, M, Cout, 0, wstride};
         if (lin::use_fast(M)) {
             int rc2 = CRF_OK;
+            if (lin::try_wgrad3(a, precision, st, &rc2)) return rc2 != CRF_OK ? rc2 : reduce_slots();
             if (lin::try_wgrad2(a, precision, st, &rc2)) return rc2 != CRF_OK ? rc2 : reduce_slots();
         }
         const int ty = (int)ceil_div(Cout, 64), tz = (int)ceil_div(Ktot, 64);

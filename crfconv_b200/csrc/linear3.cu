@@ -5,10 +5,10 @@
 // MMAs accumulate hi·hi + hi·lo + lo·hi in fp32 (measured 1.7e-6 relative, scripts/micro/umma_test.cu).
 //
 // One persistent CTA per SM, 17 warps with fixed roles, rows streamed in 128-row tiles:
-//   warps 5..16  producers : 6 groups of 2 warps; a group owns every 6th [128 rows × 32 columns] slab: coalesced 128-bit global
-//                            loads into registers, BatchNorm+LeakyReLU prologue, hi/lo split, stores into a 3-slot shared-memory
-//                            ring in the swizzled K-major operand layout, then fence.proxy.async + mbarrier arrive (the tensor
-//                            core reads shared memory through the async proxy);
+//   warps 5..16  producers : 3 groups of 4 warps; group g owns every 3rd [128 rows × 32 columns] slab and ring slot g: coalesced
+//                            128-bit global loads into registers (double-buffered: the next slab's loads fly while this one is
+//                            converted), BatchNorm+LeakyReLU prologue, hi/lo split, stores in the swizzled K-major operand layout,
+//                            mbarrier arrive (release); the generic→async proxy fence is on the issuer's side;
 //   warp 4       issuer    : one thread waits for a slab, issues its ≤12 MMAs against the CTA-resident split weights and
 //                            tcgen05.commit's the slot back to the producers; after a tile's last slab it commits the accumulator;
 //   warps 0..3   epilogue  : tcgen05.ld of the [128 × N] accumulator (one row per thread), bias, staging in shared memory,
@@ -31,12 +31,12 @@ using namespace umma;
 
 constexpr int kEpiWarps = 4, kProdWarps = 12;
 constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;      // 544
-constexpr int kGroupWarps = 2;                                   // producer warps that share one slab
-constexpr int kGroups = kProdWarps / kGroupWarps;                // slabs in flight per CTA (6 × 16 KB of loads)
+constexpr int kGroupWarps = 4;                                   // producer warps that share one slab
+constexpr int kGroups = kProdWarps / kGroupWarps;                // = RING: group g owns ring slot g
 constexpr int kRowsPerPass = kGroupWarps * 4;                    // a producer warp covers 4 rows × 128 B per load instruction
-constexpr int kLoadsPerSlab = 128 / kRowsPerPass;                // float4 loads per producer thread and slab (16)
+constexpr int kLoadsPerSlab = 128 / kRowsPerPass;                // float4 loads per producer thread and slab (8)
 constexpr int BM = 128, BK = 32, RING = 3;
-static_assert(kGroups == RING || kGroups == 2 * RING, "slot hand-over protocol below assumes at most two groups alternate on a ring slot");
+static_assert(kGroups == RING, "group g owns ring slot g: its uses of the slot barriers are consecutive phases");
 constexpr int kSlabBytes = BM * 128;                             // one [128 × 32] fp32 slab
 constexpr int kSlotBytes = 2 * kSlabBytes;                       // hi + lo
 
@@ -122,55 +122,48 @@ __global__ void __launch_bounds__(kThreads, 1) fwd3_kernel(const FwdArgs a, cons
 
     if (warp > kEpiWarps) {
         // ===================================================================== producers
-        // Slab q of this CTA's stream belongs to producer group q % kGroups.  A group loads its whole slab into registers, waits
-        // for the ring slot, converts and publishes it, then moves on to its next slab.  fence.proxy.async compiles to
-        // MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC and therefore waits for every global load the thread still has in flight — a thread
-        // that prefetched further slabs would serialise on HBM latency at each publish (measured: 1.4 us per slab) — so the
-        // memory-level parallelism comes from the kGroups groups being at different points of this loop, not from deeper
-        // per-thread prefetch.
+        // Slab q of this CTA's stream belongs to producer group q % kGroups, which also owns ring slot q % RING (kGroups == RING).
+        // Two register sets per thread: the loads of the group's NEXT slab are in flight while the current one is converted, so
+        // 6 slabs (96 KB) of HBM reads are outstanding per SM.  Producers do NOT execute fence.proxy.async: it compiles to
+        // MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, and the MEMBAR waits for every global load the thread has in flight, which serialised
+        // each slab on a full HBM round trip (measured 1.4 us per slab).  The generic→async proxy fence is executed by the issuer
+        // instead, after it has acquired the slab through the mbarrier and before it hands the shared-memory tile to the tensor core.
         const int g = (warp - (kEpiWarps + 1)) / kGroupWarps;
         const int t = tid - (kEpiWarps + 1) * 32 - g * (kGroupWarps * 32);
         const int c4 = t & 7, rb = t >> 3;                         // 16-byte column chunk; rows rb + kRowsPerPass·j
         const int Q = my_tiles * nch;
-        for (int q = g; q < Q; q += kGroups) {
+        uint8_t* hi_slab = ring + g * kSlotBytes;
+        auto load = [&](int q, float4 (&buf)[kLoadsPerSlab]) {
             const int lt = q / nch, lc = q - lt * nch;
-            const int slot = q % RING;
-            const uint32_t use = (uint32_t)(q / RING);
             const int64_t m0 = ((int64_t)blockIdx.x + (int64_t)lt * gridDim.x) * BM;
             const bool seg1 = lc < nch1;
             const float* X = seg1 ? a.X1 : a.X2;
             const int C = seg1 ? a.C1 : a.C2;
             const int col = (seg1 ? lc : lc - nch1) * BK + 4 * c4;
-            float4 buf[kLoadsPerSlab];
-            {
-                const float* base = X + (m0 + rb) * C + col;
-                const int64_t left = a.M - m0 - rb;                // rows of this thread's column that exist
+            const float* base = X + (m0 + rb) * C + col;
+            const int64_t left = a.M - m0 - rb;                    // rows of this thread's column that exist
 #pragma unroll
-                for (int j = 0; j < kLoadsPerSlab; ++j) {
-                    const bool ok = (kRowsPerPass * j < left) && (col < C);
-                    buf[j] = ok ? __ldg(reinterpret_cast<const float4*>(base + (int64_t)(kRowsPerPass * j) * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+            for (int j = 0; j < kLoadsPerSlab; ++j) {
+                const bool ok = (kRowsPerPass * j < left) && (col < C);
+                buf[j] = ok ? __ldg(reinterpret_cast<const float4*>(base + (int64_t)(kRowsPerPass * j) * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            // BatchNorm + LeakyReLU prologue in place, BEFORE asking for the ring slot (this is where the thread waits for its loads)
-            if (seg1 && a.scale1) {
+        };
+        auto publish = [&](int q, float4 (&buf)[kLoadsPerSlab]) {
+            const int lt = q / nch, lc = q - lt * nch;
+            const uint32_t use = (uint32_t)(q / RING);
+            if (lc < nch1 && a.scale1) {                           // BatchNorm + LeakyReLU prologue (this is where the thread waits for its loads)
                 const float4 sc = *reinterpret_cast<const float4*>(s_sc + lc * BK + 4 * c4);
                 const float4 sh = *reinterpret_cast<const float4*>(s_sh + lc * BK + 4 * c4);
                 const float sl = a.slope1;
 #pragma unroll
-                for (int j = 0; j < kLoadsPerSlab; ++j) {               // lrelu(v) = max(v, slope·v): slopes in [0, 1] only (checked by try_fwd3)
+                for (int j = 0; j < kLoadsPerSlab; ++j) {          // lrelu(v) = max(v, slope·v): slopes in [0, 1] only (checked by try_fwd3)
                     float4 v = buf[j];
                     v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
                     buf[j] = make_float4(fmaxf(v.x, v.x * sl), fmaxf(v.y, v.y * sl), fmaxf(v.z, v.z * sl), fmaxf(v.w, v.w * sl));
                 }
             }
-            // Ring slot `slot` alternates between two groups (kGroups = 2·RING).  mbarrier waits carry one parity bit, so a group
-            // may only look at a slot barrier when it is at most one phase behind: first wait until the previous use of the slot
-            // has been PUBLISHED by the other group, then until the tensor core has CONSUMED it.
-            if (use > 0) mbar_wait_relaxed(full + slot, (use - 1) & 1);
-            if (t == 0) CRF_TRACE(1, q);                       // previous use published
-            mbar_wait_relaxed(empty + slot, (use & 1) ^ 1);
-            if (t == 0) CRF_TRACE(2, q);                       // slot acquired
-            uint8_t* hi_slab = ring + slot * kSlotBytes;
+            mbar_wait_relaxed(empty + g, (use & 1) ^ 1);           // the tensor core has consumed this slot's previous slab
+            if (t == 0) CRF_TRACE(2, q);
 #pragma unroll
             for (int j = 0; j < kLoadsPerSlab; ++j) {
                 const float4 v = buf[j];
@@ -180,13 +173,19 @@ __global__ void __launch_bounds__(kThreads, 1) fwd3_kernel(const FwdArgs a, cons
                 *reinterpret_cast<float4*>(hi_slab + off) = h;
                 *reinterpret_cast<float4*>(hi_slab + kSlabBytes + off) = l;
             }
-            if (t == 0) CRF_TRACE(3, q);                       // converted (data had arrived)
-            fence_async_smem();
-            // the group's warps advance together (named barrier 2 + g): the parity argument above needs "this group has published
-            // use U−2" to hold for every warp of the group before any of them looks at the slot barriers again
+            if (t == 0) CRF_TRACE(3, q);
+            // all of the group's stores are ordered before the (release) arrive of its thread 0 by the named barrier
             asm volatile("bar.sync %0, %1;" ::"r"(2 + g), "n"(kGroupWarps * 32) : "memory");
-            if (t == 0) mbar_arrive(full + slot);
-            if (t == 0) CRF_TRACE(4, q);                       // published
+            if (t == 0) mbar_arrive(full + g);
+            if (t == 0) CRF_TRACE(4, q);
+        };
+        float4 bufA[kLoadsPerSlab], bufB[kLoadsPerSlab];
+        if (g < Q) load(g, bufA);
+        for (int q = g; q < Q; q += 2 * kGroups) {
+            if (q + kGroups < Q) load(q + kGroups, bufB);
+            publish(q, bufA);
+            if (q + 2 * kGroups < Q) load(q + 2 * kGroups, bufA);
+            if (q + kGroups < Q) publish(q + kGroups, bufB);
         }
     } else if (warp == kEpiWarps) {
         // ===================================================================== MMA issuer (whole warp waits, one elected lane issues)
@@ -215,6 +214,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd3_kernel(const FwdArgs a, cons
                 if (c < nch) {
                     if (lane == 0) CRF_TRACE(10, ti * nch + c);      // loop top
                     mbar_wait(full + slot, use & 1);
+                    fence_async_smem();                          // producers' generic-proxy stores (acquired above) → async proxy
                     tc_fence_after();
                     if (elect_one()) {
                         CRF_TRACE(5, ti * nch + c);                  // issuer saw the slab

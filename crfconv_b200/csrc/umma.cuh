@@ -36,11 +36,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Waits are bounded by TIME (≈2 s of SM clock): a mis-programmed pipeline traps (surfacing as a CUDA error at the C ABI)
 // instead of hanging the device.  The slow path is kept out of line: the kernels' three warp roles share a small instruction
 // cache, and an inlined printf call site per wait would triple the size of the issue loop.
-__device__ __noinline__ void mbar_timeout() {
+static __device__ __noinline__ void mbar_timeout() {
     printf("crfconv_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
     __trap();
 }
-__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, unsigned sleep_ns) {
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, unsigned sleep_ns) {
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
         if (sleep_ns) __nanosleep(sleep_ns);

@@ -263,25 +263,39 @@ static void rate() {
 
 
 // ---- issuer-loop probe: per "slab" 12 MMAs + commit, optionally an (already satisfied) mbarrier wait, syncwarp and a fresh election ----
-template <int N, int MODE>
-__global__ void __launch_bounds__(128) umma_loop_kernel(int slabs, long long* out) {
+template <int N, int MODE, int SPIN>
+__global__ void __launch_bounds__(256) umma_loop_kernel(int slabs, long long* out) {
     extern __shared__ __align__(1024) uint8_t smem_dyn[];
     uint8_t* a_s = smem_dyn;
     uint8_t* b_s = smem_dyn + 128 * 128;
-    __shared__ uint64_t bar_commit, bar_ready;
+    __shared__ uint64_t bar_commit, bar_ready, bar_never;
+    __shared__ volatile int stop_flag;
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5;
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    if (tid == 0) { mbar_init(&bar_commit, 1); mbar_init(&bar_ready, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    for (int i = tid; i < (128 + N) * 32; i += 128) ((float*)smem_dyn)[i] = 0.001f * (i % 7);
+    if (tid == 0) { stop_flag = 0; mbar_init(&bar_never, 1); mbar_init(&bar_commit, 1); mbar_init(&bar_ready, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    for (int i = tid; i < (128 + N) * 32; i += 256) ((float*)smem_dyn)[i] = 0.001f * (i % 7);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base;
+    if (warp >= 2 && SPIN > 0) {            // 6 bystander warps: 1 = tight mbarrier polling, 2 = polling with nanosleep(40), 3 = shared-memory store traffic, 4 = ALU spin
+        float* scratch = (float*)(smem_dyn + (128 + N) * 128);
+        float acc = 0.f;
+        while (!stop_flag) {
+            if (SPIN == 1) { mbar_try_wait(&bar_never, 0); }
+            if (SPIN == 2) { mbar_try_wait(&bar_never, 0); __nanosleep(40); }
+            if (SPIN == 3) { for (int r = 0; r < 8; ++r) *(float4*)(scratch + ((tid - 64) * 4 + r * 768)) = make_float4(acc, 1.f, 2.f, 3.f); }
+            if (SPIN == 4) { for (int r = 0; r < 64; ++r) acc = fmaf(acc, 1.0001f, 0.5f); }
+            if (SPIN == 5) { mbar_try_wait(&bar_commit, 0); }                       // poll the barrier the commits arrive on
+            if (SPIN == 6) { mbar_try_wait(&bar_commit, 0); mbar_try_wait(&bar_ready, 1); }   // ... and the one the issuer waits on
+        }
+        if (acc == 12345.f) out[1] = 0;
+    }
     if (warp == 1) {
         constexpr uint32_t idesc = make_idesc(128, N);
         const uint64_t a0 = make_desc(smem_u32(a_s)), b0 = make_desc(smem_u32(b_s));
@@ -302,34 +316,128 @@ __global__ void __launch_bounds__(128) umma_loop_kernel(int slabs, long long* ou
         for (uint32_t i = 0; i < (1u << 24); ++i) if (mbar_try_wait(&bar_ready, 0)) break;
         const long long t2 = clock64();
         if ((tid & 31) == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+        stop_flag = 1;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
-template <int N, int MODE>
+template <int N, int MODE, int SPIN>
 static void loop_rate() {
     long long* d;
     cudaMalloc(&d, 16);
-    const size_t smem = (128 + N) * 128;
-    auto kern = umma_loop_kernel<N, MODE>;
+    const size_t smem = (128 + N) * 128 + 8 * 768 * 4 + 4096;
+    auto kern = umma_loop_kernel<N, MODE, SPIN>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int slabs = 512;
-    kern<<<1, 128, smem>>>(slabs, d);
-    kern<<<1, 128, smem>>>(slabs, d);
+    kern<<<1, 256, smem>>>(slabs, d);
+    kern<<<1, 256, smem>>>(slabs, d);
     cudaError_t e = cudaDeviceSynchronize();
     long long h[2] = {0, 0};
     cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
-    printf("issuer loop N=%3d mode=%d (0: mma+commit, 1: +wait, 2: +syncwarp, 3: no commit): issue %.0f cyc/slab, complete %.0f cyc/slab  %s\n", N, MODE,
+    printf("issuer loop N=%3d mode=%d bystanders=%d (0 blocked, 1 mbarrier poll, 2 poll+nanosleep, 3 STS traffic, 4 ALU): issue %.0f cyc/slab, complete %.0f cyc/slab  %s\n", N, MODE, SPIN,
            (double)h[0] / slabs, (double)h[1] / slabs, e == cudaSuccess ? "" : cudaGetErrorString(e));
     cudaFree(d);
 }
 
-int main() {
-    loop_rate<64, 0>(); loop_rate<64, 1>(); loop_rate<64, 2>(); loop_rate<64, 3>(); loop_rate<16, 2>();
 
-    rate<128, 16, 1>(); rate<128, 32, 1>(); rate<128, 64, 1>(); rate<128, 64, 2>(); rate<128, 128, 1>(); rate<128, 256, 1>(); rate<128, 256, 2>();
-    rate<64, 16, 1>(); rate<64, 64, 1>(); rate<64, 128, 1>(); rate<64, 256, 1>();
+// ---- MN-major bring-up: D[M, N] = Σ_k A[k][m] · B[k][n], operands stored "row = k" exactly like an activation tile ----
+// slab image: [channel block of 32][KR rows × 128 B], chunk c of row r at c ^ (r & 7): the SAME bytes the K-major kernels use.
+// tf32 MN-major operands only exist in the SWIZZLE_128B_BASE32B layout (type 1): rows (k) of 128 bytes, 32-byte chunk c of row k at
+// position c ^ (k & 3); an atom is 4 rows (512 B); SBO = stride between K atoms, LBO = stride between 32-channel blocks.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)1 << 61);
+}
+__device__ __forceinline__ uint32_t sw32_off(int r, int k) {      // element k (0..31) of row r
+    const int c32 = (k >> 3) ^ (r & 3);
+    return (uint32_t)(r * 128 + (c32 << 5) + ((k & 7) << 2));
+}
+template <int M, int N, int KR>
+__global__ void __launch_bounds__(128) umma_mn_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D) {
+    extern __shared__ __align__(1024) uint8_t smem_dyn[];
+    constexpr int SLAB = KR * 128;
+    uint8_t* a_s = smem_dyn;                       // [M/32][KR][128 B]
+    uint8_t* b_s = smem_dyn + (M / 32) * SLAB;     // [N/32][KR][128 B]
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(64));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    for (int i = tid; i < KR * M; i += 128) {      // A is [KR][M] row-major in global
+        const int r = i / M, m = i % M;
+        *(float*)(a_s + (m / 32) * SLAB + sw32_off(r, m % 32)) = A[i];
+    }
+    for (int i = tid; i < KR * N; i += 128) {
+        const int r = i / N, n = i % N;
+        *(float*)(b_s + (n / 32) * SLAB + sw32_off(r, n % 32)) = B[i];
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base;
+    if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc(M, N) | (1u << 15) | (1u << 16);      // A and B MN-major
+            for (int j = 0; j < KR / 8; ++j)
+                umma_tf32(tmem, make_desc_mn(smem_u32(a_s) + j * 1024, SLAB), make_desc_mn(smem_u32(b_s) + j * 1024, SLAB), idesc, j > 0);
+            umma_commit(&bar);
+        }
+        __syncwarp();
+    }
+    mbar_wait_bounded(&bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = warp * 32 + (tid & 31);
+    for (int c = 0; c < N; c += 16) {
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
+        if (row < M)
+            for (int i = 0; i < 16; ++i) D[row * N + c + i] = v[i];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64));
+}
+template <int M, int N, int KR>
+static void run_mn() {
+    std::vector<float> A(KR * M), B(KR * N), D(128 * N, -1.f), ref(M * N);
+    srand(7);
+    for (auto& x : A) x = (float)((rand() % 17) - 8) * 0.25f;
+    for (auto& x : B) x = (float)((rand() % 17) - 8) * 0.5f;
+    for (int m = 0; m < M; ++m)
+        for (int n = 0; n < N; ++n) {
+            double s = 0;
+            for (int k = 0; k < KR; ++k) s += (double)A[k * M + m] * (double)B[k * N + n];
+            ref[m * N + n] = (float)s;
+        }
+    float *dA, *dB, *dD;
+    cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dB, B.size() * 4); cudaMalloc(&dD, D.size() * 4);
+    cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dD, D.data(), D.size() * 4, cudaMemcpyHostToDevice);
+    const size_t smem = (size_t)(M / 32 + N / 32) * KR * 128;
+    auto kern = umma_mn_kernel<M, N, KR>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<1, 128, smem>>>(dA, dB, dD);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+    double err = 0;
+    for (int i = 0; i < M * N; ++i) err = fmax(err, fabs((double)D[i] - (double)ref[i]));
+    printf("MN-major M=%d N=%d Krows=%d: max|err| = %.3e   D[0..3] = %g %g %g %g  ref = %g %g %g %g   D[33*N+5]=%g ref %g  %s\n", M, N, KR, err, D[0], D[1], D[2],
+           D[3], ref[0], ref[1], ref[2], ref[3], D[33 * N + 5], ref[33 * N + 5], e == cudaSuccess ? "" : cudaGetErrorString(e));
+    cudaFree(dA); cudaFree(dB); cudaFree(dD);
+}
+
+int main() {
+    run_mn<128, 64, 64>();
+
+    loop_rate<64, 2, 0>(); loop_rate<64, 2, 5>(); loop_rate<64, 2, 6>();
+
+    rate<128, 16, 1>(); rate<128, 64, 1>(); rate<128, 256, 1>(); rate<64, 64, 1>();
     int rc = 0;
     rc |= run<64, 1, false>("exact  ", true);
     rc |= run<64, 2, false>("exact2 ", true);

@@ -47,3 +47,22 @@ for C1, C2, Co, pro in shapes:
     t = timeit(run)
     nb = rows * (C1 + C2 + Co) * 4
     print(f"linear_fwd [{C1}+{C2} -> {Co}] rows={rows}: {t:7.1f} us   {nb / t / 1e3:7.0f} GB/s   ({nb / 1e6:.0f} MB)")
+
+# ---- weight gradients (plain Linear form: dH = dY; the BN-backward transform adds one more row-sized read of H)
+print("--- wgrad only (dW = dY^T X), rows x (Cout + Ktot) x 4 bytes")
+for C1, C2, Co in [(64, 64, 64), (16, 0, 64), (64, 0, 16), (128, 0, 16)]:
+    rows = M if C1 != 128 else M // 4
+    X1 = [torch.randn(rows, C1, device=dev) for _ in range(NSETS)]
+    X2 = [torch.randn(rows, C2, device=dev) for _ in range(NSETS)] if C2 else [None] * NSETS
+    dY = [torch.randn(rows, Co, device=dev) for _ in range(NSETS)]
+    W = torch.randn(Co, C1 + C2, device=dev) * 0.1
+    dW = torch.zeros_like(W)
+    scratch = torch.zeros(ops.GRAD_SLOTS * W.numel(), device=dev)
+
+    def runw(i):
+        j = i % NSETS
+        ops.linear_bwd(dY[j], None, None, 1.0, X1[j], W, X2=X2[j], dW=dW, scratch=scratch, scratch_stride=W.numel())
+
+    t = timeit(runw)
+    nb = rows * (C1 + C2 + Co) * 4
+    print(f"wgrad [{Co} <- {C1}+{C2}] rows={rows}: {t:7.1f} us   {nb / t / 1e3:7.0f} GB/s   ({nb / 1e6:.0f} MB)")
