@@ -21,3 +21,17 @@ def rel_l2(a, b, floor=0.0):
     implementations of a 10^7-activation layer disagree on (a flipped branch changes one gradient entry by O(1))."""
     a, b = np.asarray(a, dtype=np.float64).ravel(), np.asarray(b, dtype=np.float64).ravel()
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), floor * np.sqrt(b.size), 1e-30))
+
+
+def rel_err_trimmed(a, b, floor=0.0, outlier_frac=2e-5):
+    """`rel_err` after setting aside the ceil(outlier_frac·n) largest deviations (at most 2 in 10^5 entries).
+    Why: BatchNorm statistics are accumulated with floating-point atomics, so two runs of the SAME kernel differ in the last
+    bit; an activation that sits within one ulp of a LeakyReLU kink then takes the other branch in one run out of a few dozen
+    and changes ONE input-gradient entry by O(1).  Tests that use this also bound the L2 error over ALL entries."""
+    a, b = np.asarray(a, dtype=np.float64).ravel(), np.asarray(b, dtype=np.float64).ravel()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    d = np.abs(a - b)
+    k = int(np.ceil(outlier_frac * d.size)) if d.size >= 1000 else 0
+    if k:
+        d = np.partition(d, d.size - k - 1)[: d.size - k]
+    return float(d.max() / max(np.abs(b).max(), floor, 1e-30))

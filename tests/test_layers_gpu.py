@@ -9,7 +9,7 @@ import torch
 from oracle import layers as ol
 from oracle import native as on
 from oracle import synthetic
-from tests._util import grad_floor, rel_err, rel_l2
+from tests._util import grad_floor, rel_err, rel_err_trimmed, rel_l2
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
@@ -77,9 +77,13 @@ def _oracle_vs_product(make_oracle, make_product, inputs_cpu, grad_idx, seed=0, 
     (oo * cot).sum().backward()
     og = mp(*ig)
     (og * cot.cuda()).sum().backward()
-    errs = {"out": rel_err(og.detach().cpu().numpy(), oo.detach().numpy())}
+    # activations / input gradients: max-norm over all but <= 2e-5 of the entries (run-to-run kink flips, see rel_err_trimmed)
+    # AND relative L2 over every entry
+    errs = {"out": rel_err_trimmed(og.detach().cpu().numpy(), oo.detach().numpy()),
+            "out(l2)": rel_l2(og.detach().cpu().numpy(), oo.detach().numpy())}
     for i in grad_idx:
-        errs[f"gin{i}"] = rel_err(ig[i].grad.cpu().numpy(), ic[i].grad.numpy())
+        errs[f"gin{i}"] = rel_err_trimmed(ig[i].grad.cpu().numpy(), ic[i].grad.numpy())
+        errs[f"gin{i}(l2)"] = rel_l2(ig[i].grad.cpu().numpy(), ic[i].grad.numpy())
     floor = 1e-3 * max(float(p.grad.abs().max()) for p in mo.parameters())
     po = dict(mo.named_parameters())
     for n, p in mp.named_parameters():
