@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(256) umma_loop_kernel(int slabs, long long* ou
             if (SPIN == 2) { mbar_try_wait(&bar_never, 0); __nanosleep(40); }
             if (SPIN == 3) { for (int r = 0; r < 8; ++r) *(float4*)(scratch + ((tid - 64) * 4 + r * 768)) = make_float4(acc, 1.f, 2.f, 3.f); }
             if (SPIN == 4) { for (int r = 0; r < 64; ++r) acc = fmaf(acc, 1.0001f, 0.5f); }
+            if (SPIN == 7) { for (int r = 0; r < 8; ++r) *(float4*)(scratch + ((tid - 64) * 4 + r * 768)) = make_float4(acc, 1.f, 2.f, 3.f); asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
             if (SPIN == 5) { mbar_try_wait(&bar_commit, 0); }                       // poll the barrier the commits arrive on
             if (SPIN == 6) { mbar_try_wait(&bar_commit, 0); mbar_try_wait(&bar_ready, 1); }   // ... and the one the issuer waits on
         }
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(256) umma_loop_kernel(int slabs, long long* ou
         const uint64_t a0 = make_desc(smem_u32(a_s)), b0 = make_desc(smem_u32(b_s));
         const long long t0 = clock64();
         for (int s = 0; s < slabs; ++s) {
-            if (MODE >= 1) { while (!mbar_try_wait(&bar_ready, 1)) {} asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+            if (MODE >= 1) { while (!mbar_try_wait(&bar_ready, 1)) {} if (MODE == 4) asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
             if (elect_one()) {
 #pragma unroll
                 for (int j = 0; j < 12; ++j) umma_tf32(tmem, a0 + 2 * (j & 3), b0 + 2 * (j & 3), idesc, 1);
@@ -435,7 +436,7 @@ static void run_mn() {
 int main() {
     run_mn<128, 64, 64>();
 
-    loop_rate<64, 2, 0>(); loop_rate<64, 2, 5>(); loop_rate<64, 2, 6>();
+    loop_rate<64, 2, 0>(); loop_rate<64, 4, 0>(); loop_rate<64, 2, 7>(); loop_rate<64, 4, 7>();
 
     rate<128, 16, 1>(); rate<128, 64, 1>(); rate<128, 256, 1>(); rate<64, 64, 1>();
     int rc = 0;
