@@ -64,6 +64,20 @@ __device__ __forceinline__ void gather_full(float4 v, float (&full)[F], int lane
     }
 }
 
+// The 16 int64 neighbour indices of a point are one 128-byte row.  Per-lane scalar loads of them cost one L1 wavefront per index
+// and point (15 of the ≈50 wavefronts a point costs in the forward kernel, which ncu shows bound by l1tex data-pipe
+// wavefronts); instead the 4 lanes of a point fetch the row with two 128-bit loads each and hand indices around by shuffle.
+// Lane s of the group ends up with indices {2s, 2s+1, 8+2s, 8+2s+1} in r[0..3].
+__device__ __forceinline__ void load_idx16(const int64_t* nb, int sub, int (&r)[4]) {
+    const longlong2 a = __ldg(reinterpret_cast<const longlong2*>(nb) + sub);
+    const longlong2 b = __ldg(reinterpret_cast<const longlong2*>(nb) + 4 + sub);
+    r[0] = (int)a.x; r[1] = (int)a.y; r[2] = (int)b.x; r[3] = (int)b.y;
+}
+template <int k>
+__device__ __forceinline__ int idx16_get(const int (&r)[4], int gbase) {
+    return __shfl_sync(0xffffffffu, r[(k >> 3) * 2 + (k & 1)], gbase + ((k & 7) >> 1));
+}
+
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 mul4(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
 __device__ __forceinline__ float4 sub4(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
@@ -139,8 +153,7 @@ __global__ void __launch_bounds__(256) step_fwd_kernel(const StepArgs a) {
     float mx = -INFINITY, l = 0.f;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const int64_t* nb = a.nbr + p * a.K;
-    for (int k = 1; k < a.K; ++k) {
-        const int64_t row = base + __ldg(nb + k);
+    auto edge = [&](int64_t row) {
         const float4 df = sub4(yi, mul4(ld4(a.Hy + row * F + c0), sc));
         const float d = group_sum<LP>(dot4(df, df));
         const float4 xj = ld4(a.xprev + row * F + c0);
@@ -151,7 +164,23 @@ __global__ void __launch_bounds__(256) step_fwd_kernel(const StepArgs a) {
         acc.x = acc.x * corr + pj * xj.x; acc.y = acc.y * corr + pj * xj.y;
         acc.z = acc.z * corr + pj * xj.z; acc.w = acc.w * corr + pj * xj.w;
         mx = nm;
+    };
+    bool done = false;
+    if constexpr (F == 16) {
+        if (a.K == 16) {                                   // the reference's kernel_size: indices by vector load + shuffle
+            int r[4];
+            load_idx16(nb, lane % LP, r);
+            const int gb = lane & ~(LP - 1);
+            edge(base + idx16_get<1>(r, gb));  edge(base + idx16_get<2>(r, gb));  edge(base + idx16_get<3>(r, gb));
+            edge(base + idx16_get<4>(r, gb));  edge(base + idx16_get<5>(r, gb));  edge(base + idx16_get<6>(r, gb));
+            edge(base + idx16_get<7>(r, gb));  edge(base + idx16_get<8>(r, gb));  edge(base + idx16_get<9>(r, gb));
+            edge(base + idx16_get<10>(r, gb)); edge(base + idx16_get<11>(r, gb)); edge(base + idx16_get<12>(r, gb));
+            edge(base + idx16_get<13>(r, gb)); edge(base + idx16_get<14>(r, gb)); edge(base + idx16_get<15>(r, gb));
+            done = true;
+        }
     }
+    if (!done)
+        for (int k = 1; k < a.K; ++k) edge(base + __ldg(nb + k));
     const float inv_l = a.K > 1 ? 1.0f / l : 0.0f;
     const float4 msg = make_float4(acc.x * inv_l, acc.y * inv_l, acc.z * inv_l, acc.w * inv_l);
     float full[F];
@@ -283,8 +312,18 @@ __global__ void __launch_bounds__(128) step_bwd_reg_kernel(const StepArgs a) {
     float4 dfj[KN];
     float dj[KN], gsj[KN];
     const int64_t* nb = a.nbr + p * a.K + 1;
+    if constexpr (F == 16 && KN == 15) {                   // K = 16: the index row by vector load + shuffle (see load_idx16)
+        int r[4];
+        load_idx16(nb - 1, lane % LP, r);
+        const int gb = lane & ~(LP - 1);
+        rj[0] = idx16_get<1>(r, gb);   rj[1] = idx16_get<2>(r, gb);   rj[2] = idx16_get<3>(r, gb);   rj[3] = idx16_get<4>(r, gb);
+        rj[4] = idx16_get<5>(r, gb);   rj[5] = idx16_get<6>(r, gb);   rj[6] = idx16_get<7>(r, gb);   rj[7] = idx16_get<8>(r, gb);
+        rj[8] = idx16_get<9>(r, gb);   rj[9] = idx16_get<10>(r, gb);  rj[10] = idx16_get<11>(r, gb); rj[11] = idx16_get<12>(r, gb);
+        rj[12] = idx16_get<13>(r, gb); rj[13] = idx16_get<14>(r, gb); rj[14] = idx16_get<15>(r, gb);
+    } else {
 #pragma unroll
-    for (int k = 0; k < KN; ++k) rj[k] = (int)__ldg(nb + k);
+        for (int k = 0; k < KN; ++k) rj[k] = (int)__ldg(nb + k);
+    }
     float mx = -INFINITY;
     float4 xj[KN];
 #pragma unroll

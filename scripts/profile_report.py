@@ -1,0 +1,115 @@
+"""Turns the two ncu captures of `bench.py --no-graph` into the committed summaries under profiles/ (development aid).
+
+  python scripts/profile_report.py launches gpurun_out/launches.csv            -> markdown table of one step (kernel, launches, us, share)
+  python scripts/profile_report.py metrics  gpurun_out/full.ncu-rep out.json   -> per-kernel DRAM bytes / time / pipe utilisation (+ per-call traffic)
+
+The launch list comes from `ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file ...`, the metrics from one
+`ncu --set full --clock-control none` capture; both are cold-cache and serialised, so only SHARES and per-launch bytes are comparable
+with the graph-replayed step.
+"""
+import collections
+import csv
+import io
+import json
+import re
+import subprocess
+import sys
+
+
+def short(name):
+    name = re.sub(r"\(.*$", "", name)                       # drop the argument list
+    name = name.replace("void ", "").replace("crf::", "").replace("(int)", "")
+    return name.strip()
+
+
+def launches(path):
+    rows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))]
+    hdr, rows = rows[0], rows[1:]
+    iK, iV = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    seq = [(short(r[iK]), float(r[iV].replace(",", "")) / 1e3) for r in rows]
+    # one step = the span between two consecutive occurrences of the first kernel of the forward pass (two steps are captured)
+    names = [n for n, _ in seq]
+    # find the period: smallest p such that the last 2p launches repeat
+    period = None
+    for p in range(20, len(seq) // 2 + 1):
+        if names[-p:] == names[-2 * p:-p]:
+            period = p
+            break
+    step = seq[-period:] if period else seq
+    agg = collections.OrderedDict()
+    for n, us in step:
+        a = agg.setdefault(n, [0, 0.0])
+        a[0] += 1
+        a[1] += us
+    tot = sum(v[1] for v in agg.values())
+    print(f"kernels per step: {len(step)}; summed device time (cold-cache, serialised): {tot:.1f} us\n")
+    print("| kernel | launches/step | us/step | share |\n|---|---|---|---|")
+    for n, (c, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"| `{n[:80]}` | {c} | {us:.1f} | {100 * us / tot:.1f}% |")
+
+
+KEYS = {
+    "time_us": "gpu__time_duration.sum",
+    "dram_read_mb": "dram__bytes_read.sum",
+    "dram_write_mb": "dram__bytes_write.sum",
+    "issue_active_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "tensor_pipe_pct": "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "l1tex_pct": "l1tex__throughput.avg.pct_of_peak_sustained_active",
+    "lts_pct": "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "dram_pct": "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "regs": "launch__registers_per_thread",
+    "warps_active_pct": "sm__warps_active.avg.pct_of_peak_sustained_active",
+}
+
+
+def metrics(rep, out):
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    hdr, units, rows = rows[0], rows[1], rows[2:]
+    ks = collections.OrderedDict()
+    order = []
+    for r in rows:
+        d = dict(zip(hdr, r))
+        n = short(d["Kernel Name"]) + " grid=" + d.get("Grid Size", "").replace(" ", "")
+        m = {}
+        for k, col in KEYS.items():
+            if col in d and d[col] not in ("", "n/a"):
+                v = float(d[col].replace(",", ""))
+                u = units[hdr.index(col)]
+                if k == "time_us":
+                    v = v / 1e3 if u in ("ns", "nsecond") else (v * 1e3 if u in ("ms", "msecond") else v)
+                if k in ("dram_read_mb", "dram_write_mb"):
+                    v = {"byte": v / 1e6, "Kbyte": v / 1e3, "Mbyte": v, "Gbyte": v * 1e3}.get(u, v)
+                m[k] = round(v, 3)
+        order.append((n, m))
+        ks.setdefault(n, m)                                  # first launch of each (kernel, grid)
+    calls = {}
+
+    def first(sub):
+        for n, m in order:
+            if sub in n:
+                return m
+        return None
+    # linear_bwd[64<-128] (fusion layer, first Linear backward of the step) = its dgrad + its wgrad launch
+    dg, wg = first("dgrad2_kernel<128"), first("wgrad3_kernel<64") or first("wgrad2_kernel<64, 128")
+    if dg and wg:
+        calls["linear_bwd[64<-128]"] = {"traffic_bytes": round((dg["dram_read_mb"] + dg["dram_write_mb"] + wg["dram_read_mb"] + wg["dram_write_mb"]) * 1e6)}
+    sb = first("step_bwd_reg_kernel")
+    if sb:
+        calls["crf_step_bwd[16]"] = {"traffic_bytes": round((sb["dram_read_mb"] + sb["dram_write_mb"]) * 1e6)}
+    fw = first("fwd3_kernel<64")
+    if fw:
+        calls["linear_fwd[16->64]"] = {"traffic_bytes": round((fw["dram_read_mb"] + fw["dram_write_mb"]) * 1e6)}
+    json.dump({"source": "ncu --set full --clock-control none, profiles/README_r01.md (scripts/profile_report.py)", "kernels": ks, "calls": calls},
+              open(out, "w"), indent=1)
+    print("| kernel (grid) | us | DRAM rd MB | DRAM wr MB | DRAM % | L2 % | L1TEX % | issue % | tensor % | regs |\n|---|---|---|---|---|---|---|---|---|---|")
+    for n, m in ks.items():
+        print(f"| `{n[:70]}` | {m.get('time_us', 0):.1f} | {m.get('dram_read_mb', 0):.1f} | {m.get('dram_write_mb', 0):.1f} | {m.get('dram_pct', 0):.0f} | "
+              f"{m.get('lts_pct', 0):.0f} | {m.get('l1tex_pct', 0):.0f} | {m.get('issue_active_pct', 0):.0f} | {m.get('tensor_pipe_pct', 0):.0f} | {int(m.get('regs', 0))} |")
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2])
+    else:
+        metrics(sys.argv[2], sys.argv[3])
