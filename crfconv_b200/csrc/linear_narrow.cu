@@ -353,6 +353,8 @@ namespace lin {
 // per-element BN+LeakyReLU prologue and the per-channel butterfly statistics cost more issue slots than the FFMAs they feed.
 // CRFCONV_NARROW_ALL=1 routes every eligible shape here (for experiments).
 static inline bool narrow_shape(int Cout, int Ktot) {
+    static const bool none = [] { const char* e = getenv("CRFCONV_NO_NARROW"); return e && e[0] == '1'; }();
+    if (none) return false;
     static const bool all = [] { const char* e = getenv("CRFCONV_NARROW_ALL"); return e && e[0] == '1'; }();
     if (all) return (Cout <= 16 && Ktot <= 128) || (Ktot <= 16 && Cout <= 64);
     return Cout <= 16 && Ktot <= 16;
