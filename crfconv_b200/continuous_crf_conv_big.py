@@ -32,6 +32,18 @@ def _side_stream(dev):
     return _SIDE[key]
 
 
+_AUX = {}
+
+
+def _aux_stream(dev):
+    """Third stream: the F×F compatibility algebra (C = cᵀc, (I+C)⁻¹ and its backward) is a single-CTA kernel of 10-16 us that
+    depends on nothing but `c` (forward) / GC, GM (backward); on its own graph branch it costs nothing."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _AUX:
+        _AUX[key] = torch.cuda.Stream(device=dev)
+    return _AUX[key]
+
+
 def _mlp_params(m: MLP):
     return m.lin.weight, m.bn.batch_norm.weight, m.bn.batch_norm.bias
 
@@ -69,10 +81,17 @@ class _CRFConvFunction(torch.autograd.Function):
         s1p, fin1p = bn_forward_state(F, dev, M, bns[2], tr(bns[2]), fstats.take(ops.STAT_SLOTS * 2 * F), nbt)
         s2p, fin2p = bn_forward_state(F, dev, M, bns[3], tr(bns[3]), fstats.take(ops.STAT_SLOTS * 2 * F), nbt)
         H1u, H2u = torch.empty((Mc, F), dtype=torch.float32, device=dev), torch.empty((Mc, F), dtype=torch.float32, device=dev)
-        main, side = torch.cuda.current_stream(dev), _side_stream(dev)
-        fork, join = torch.cuda.Event(), torch.cuda.Event()
+        main, side, aux = torch.cuda.current_stream(dev), _side_stream(dev), _aux_stream(dev)
+        fork, join, join_aux = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        cc = c.detach().contiguous().float()
+        Cm, Minv = torch.empty_like(cc), torch.empty_like(cc)
+        cscr = torch.empty(3 * F * F, dtype=torch.float64, device=dev)
         fork.record(main)
         side.wait_event(fork)
+        aux.wait_event(fork)
+        with torch.cuda.stream(aux):
+            ops.crf_compat_fwd(cc, out=(Cm, Minv), scratch=cscr)
+            join_aux.record(aux)
         with torch.cuda.stream(side):
             ops.linear_fwd(U, W1u, stats=s1u.stats, out=H1u); fin1u()
             ops.linear_fwd(H1u, W2u, scale1=s1u.scale, shift1=s1u.shift, slope1=sl[0], stats=s2u.stats, out=H2u); fin2u()
@@ -80,9 +99,8 @@ class _CRFConvFunction(torch.autograd.Function):
         H1p = ops.linear_fwd(P, W1p, stats=s1p.stats); fin1p()
         H2p = ops.linear_fwd(H1p, W2p, scale1=s1p.scale, shift1=s1p.shift, slope1=sl[2], stats=s2p.stats); fin2p()
         # mean field (:60-72)
-        cc = c.detach().contiguous().float()
-        Cm, Minv = ops.crf_compat_fwd(cc)
         main.wait_event(join)
+        main.wait_event(join_aux)
         z = ops.crf_upsample_fwd(H2u, s2u, up, B, N, Nc)
         xs = [z]
         for _ in range(steps):
@@ -162,7 +180,14 @@ class _CRFConvFunction(torch.autograd.Function):
             g = gprev
         ops.grad_slots_reduce(wscr, small, 2 * F * F, n_small)    # fold the GC / GM partial slots
         Gc = zeros(F, F)
-        ops.crf_compat_bwd(cc, Minv, GC, GM, Gc)
+        aux = _aux_stream(dev)
+        fork_aux, join_aux = torch.cuda.Event(), torch.cuda.Event()
+        bscr = torch.empty(3 * F * F, dtype=torch.float64, device=dev)
+        fork_aux.record(torch.cuda.current_stream(dev))
+        aux.wait_event(fork_aux)
+        with torch.cuda.stream(aux):                             # off the critical path: Gc is only needed when backward returns
+            ops.crf_compat_bwd(cc, Minv, GC, GM, Gc, scratch=bscr)
+            join_aux.record(aux)
         Gu = big.take(Mc, F)
         if steps > 0:
             ops.crf_upsample_bwd(Gz, g, up, Gu, B, N, Nc)      # dL/dz = Σ_t h^t + g^0
@@ -191,6 +216,7 @@ class _CRFConvFunction(torch.autograd.Function):
         ops.linear_bwd(dA, H1p, s1p, sl[2], P, W1p, dX1=dP if need_p else None, acc1=True, dW=dW["1p"], scratch=scr(dW["1p"]), scratch_stride=n_small)
 
         main.wait_event(join)
+        main.wait_event(join_aux)
         ops.grad_slots_reduce(wscr[2 * F * F:], small[2 * F * F:], n_small - 2 * F * F, n_small)   # all weight gradients, one launch
         grads = []
         for k in ("1u", "2u", "1p", "2p", "o", "f"):

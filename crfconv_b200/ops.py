@@ -206,20 +206,23 @@ def _linear_bwd_call(L, dY, H, act_ref, b, slope, X1, C1, scale1, shift1, slope1
 
 
 # ------------------------------------------------------------------------------------------ CRF mean-field
-def crf_compat_fwd(c):
+def crf_compat_fwd(c, out=None, scratch=None):
+    """`out` / `scratch`: preallocated (Cm, Minv) and f64 scratch, for callers that launch on a side stream."""
     L = _lib.lib()
     F = c.shape[0]
-    Cm, Minv = torch.empty_like(c), torch.empty_like(c)
-    scratch = torch.empty(3 * F * F, dtype=torch.float64, device=c.device)
+    Cm, Minv = out if out is not None else (torch.empty_like(c), torch.empty_like(c))
+    if scratch is None:
+        scratch = torch.empty(3 * F * F, dtype=torch.float64, device=c.device)
     COUNTERS["launches"] += 1
     _lib.check(L.crfconv_crf_compat_fwd(_p(c), _p(Cm), _p(Minv), _p(scratch), F, _lib.stream_ptr()), "crf_compat_fwd")
     return Cm, Minv
 
 
-def crf_compat_bwd(c, Minv, GC, GM, Gc):
+def crf_compat_bwd(c, Minv, GC, GM, Gc, scratch=None):
     L = _lib.lib()
     F = c.shape[0]
-    scratch = torch.empty(3 * F * F, dtype=torch.float64, device=c.device)
+    if scratch is None:
+        scratch = torch.empty(3 * F * F, dtype=torch.float64, device=c.device)
     COUNTERS["launches"] += 1
     _lib.check(L.crfconv_crf_compat_bwd(_p(c), _p(Minv), _p(GC), _p(GM), _p(Gc), _p(scratch), F, _lib.stream_ptr()), "crf_compat_bwd")
 
