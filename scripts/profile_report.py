@@ -56,7 +56,7 @@ KEYS = {
     "tensor_pipe_pct": "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
     "l1tex_pct": "l1tex__throughput.avg.pct_of_peak_sustained_active",
     "lts_pct": "lts__throughput.avg.pct_of_peak_sustained_elapsed",
-    "dram_pct": "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "dram_pct": "dram__cycles_active.avg.pct_of_peak_sustained_elapsed",
     "regs": "launch__registers_per_thread",
     "warps_active_pct": "sm__warps_active.avg.pct_of_peak_sustained_active",
 }
@@ -68,6 +68,7 @@ def metrics(rep, out):
     hdr, units, rows = rows[0], rows[1], rows[2:]
     ks = collections.OrderedDict()
     order = []
+    seen = {}
     for r in rows:
         d = dict(zip(hdr, r))
         n = short(d["Kernel Name"]) + " grid=" + d.get("Grid Size", "").replace(" ", "")
@@ -82,7 +83,8 @@ def metrics(rep, out):
                     v = {"byte": v / 1e6, "Kbyte": v / 1e3, "Mbyte": v, "Gbyte": v * 1e3}.get(u, v)
                 m[k] = round(v, 3)
         order.append((n, m))
-        ks.setdefault(n, m)                                  # first launch of each (kernel, grid)
+        seen[n] = seen.get(n, 0) + 1
+        ks[n + f" #{seen[n]}"] = m                           # every captured launch, numbered per (kernel, grid)
     calls = {}
 
     def first(sub):
