@@ -712,7 +712,7 @@ int crfconv_linear_bwd(const float* dY, const float* H, const float* act_ref, co
         // with idx1, dX1 is the gradient wrt the GATHERED rows [M, C1]; scatter it with crfconv_scatter_add_rows
         lin::DgradArgs a{dY, H, bn, W, dX1, C1, acc1, dX2, C2, acc2, M, Cout};
         int rc = CRF_OK;
-        if (!(lin::use_fast(M) && lin::try_dgrad2(a, precision, st, &rc)))
+        if (!(lin::use_fast(M) && (lin::try_dgrad3(a, precision, st, &rc) || lin::try_dgrad2(a, precision, st, &rc))))
         rc = lin::dispatch_bn(Ktot, [&](auto bnv) {
             constexpr int BN = decltype(bnv)::value;
             dim3 grid((unsigned)ceil_div(M, lin::BM), (unsigned)ceil_div(Ktot, BN));

@@ -56,6 +56,7 @@ bool try_wgrad2(const WgradArgs& a, int precision, cudaStream_t st, int* rc);
 // tcgen05 / TMEM forward (linear3.cu)
 bool try_fwd3(const FwdArgs& a, int precision, cudaStream_t st, int* rc);
 bool try_wgrad3(const WgradArgs& a, int precision, cudaStream_t st, int* rc);   // linear3w.cu
+bool try_dgrad3(const DgradArgs& a, int precision, cudaStream_t st, int* rc);   // linear3d.cu
 // CUDA-core kernels for hidden-width layers (linear_narrow.cu); w == nullptr ⇒ dgrad only
 bool try_narrow_fwd(const FwdArgs& a, cudaStream_t st, int* rc);
 bool try_narrow_bwd(const DgradArgs& d, const WgradArgs* w, cudaStream_t st, int* rc);

@@ -66,3 +66,22 @@ for C1, C2, Co in [(64, 64, 64), (16, 0, 64), (64, 0, 16), (128, 0, 16)]:
     t = timeit(runw)
     nb = rows * (C1 + C2 + Co) * 4
     print(f"wgrad [{Co} <- {C1}+{C2}] rows={rows}: {t:7.1f} us   {nb / t / 1e3:7.0f} GB/s   ({nb / 1e6:.0f} MB)")
+
+# ---- input gradients (plain Linear form: dH = dY)
+print("--- dgrad only (dX = dY W), rows x (Cout + Ktot) x 4 bytes")
+for C1, C2, Co in [(64, 64, 64), (16, 0, 64), (64, 0, 16), (128, 0, 16)]:
+    rows = M if C1 != 128 else M // 4
+    dY = [torch.randn(rows, Co, device=dev) for _ in range(NSETS)]
+    X1 = torch.empty(rows, C1, device=dev)
+    W = torch.randn(Co, C1 + C2, device=dev) * 0.1
+    dX1 = [torch.empty(rows, C1, device=dev) for _ in range(NSETS)]
+    dX2 = [torch.empty(rows, C2, device=dev) for _ in range(NSETS)] if C2 else [None] * NSETS
+    X2 = torch.empty(rows, C2, device=dev) if C2 else None
+
+    def rund(i):
+        j = i % NSETS
+        ops.linear_bwd(dY[j], None, None, 1.0, X1, W, X2=X2, dX1=dX1[j], dX2=dX2[j])
+
+    t = timeit(rund)
+    nb = rows * (C1 + C2 + Co) * 4
+    print(f"dgrad [{Co} <- {C1}+{C2}] rows={rows}: {t:7.1f} us   {nb / t / 1e3:7.0f} GB/s   ({nb / 1e6:.0f} MB)")
