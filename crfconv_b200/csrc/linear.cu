@@ -455,6 +455,107 @@ __global__ void __launch_bounds__(kThreads) dgrad_kernel(const DgradArgs a) {
     }
 }
 
+// ---- weight gradient for very narrow inputs (Ktot <= 4: the 3-d relative positions feeding PointConv's edge MLP,
+// point_conv_big.py:37-44).  dW is Cout × 3 while the contraction runs over millions of edges: the tiled kernel below spends its
+// time in atomics onto a few dozen addresses (measured 2.1 ms per call at 3.9 M edges, 44 % of the full network's step).  Here one
+// thread owns a 4-channel slice of a row, keeps its 4 × Ktot partial sums in registers over all its rows, and the CTA folds them
+// through shared memory into one partial slot.  Pure streaming: rows × (2·Cout + Ktot) × 4 bytes.
+template <int KT>
+__global__ void __launch_bounds__(256) wgrad_tiny_kernel(const WgradArgs a) {
+    __shared__ float red[256 * 4 * KT];
+    const int C = a.Cout, C4 = C >> 2;
+    const int rows_per_it = 256 / C4;                // C4 divides 256 for Cout in {4, 8, ..., 1024}
+    const int tid = threadIdx.x;
+    const int cslot = tid % C4, rslot = tid / C4;
+    const bool plain = a.bn.scale == nullptr;
+    const bool has_ref = !plain && a.bn.act_ref != nullptr;
+    float acc[4][KT];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int k = 0; k < KT; ++k) acc[e][k] = 0.f;
+    if (rslot < rows_per_it) {
+        const int c = cslot * 4;
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f), pz = sh, pw = sh;
+        if (!plain) {
+            sc = __ldg(reinterpret_cast<const float4*>(a.bn.scale + c)); sh = __ldg(reinterpret_cast<const float4*>(a.bn.shift + c));
+            const float4 mu = __ldg(reinterpret_cast<const float4*>(a.bn.mean + c)), is = __ldg(reinterpret_cast<const float4*>(a.bn.invstd + c));
+            const float4 k1 = __ldg(reinterpret_cast<const float4*>(a.bn.k1 + c)), k2 = __ldg(reinterpret_cast<const float4*>(a.bn.k2 + c));
+            pz = make_float4(-sc.x * is.x * k2.x, -sc.y * is.y * k2.y, -sc.z * is.z * k2.z, -sc.w * is.w * k2.w);
+            pw = make_float4(-sc.x * k1.x - pz.x * mu.x, -sc.y * k1.y - pz.y * mu.y, -sc.z * k1.z - pz.z * mu.z, -sc.w * k1.w - pz.w * mu.w);
+        }
+        float xs[KT], xh[KT];
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            xs[k] = (a.scale1 && k < a.C1) ? __ldg(a.scale1 + k) : 1.f;
+            xh[k] = (a.scale1 && k < a.C1) ? __ldg(a.shift1 + k) : 0.f;
+        }
+        const float slope = a.bn.slope, slope1 = a.scale1 ? a.slope1 : 1.f;
+        constexpr int U = 4;
+        const int64_t stride = (int64_t)gridDim.x * rows_per_it;
+        for (int64_t m0 = (int64_t)blockIdx.x * rows_per_it + rslot; m0 < a.M; m0 += U * stride) {
+            float4 dy[U], h[U], rf[U];
+            float x[U][KT];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t m = m0 + u * stride;
+                const bool ok = m < a.M;
+                const int64_t off = ok ? m * C + c : 0;
+                dy[u] = ok ? __ldg(reinterpret_cast<const float4*>(a.dY + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                h[u] = (ok && !plain) ? __ldg(reinterpret_cast<const float4*>(a.H + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                rf[u] = (ok && has_ref) ? __ldg(reinterpret_cast<const float4*>(a.bn.act_ref + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                int64_t srow = ok ? m : 0;
+                if (ok && a.idx1) srow = (m / a.rows_dst) * a.rows_src + __ldg(a.idx1 + m);
+#pragma unroll
+                for (int k = 0; k < KT; ++k) x[u][k] = (ok && k < a.C1) ? __ldg(a.X1 + srow * a.C1 + k) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool ok = m0 + u * stride < a.M;
+                float d[4] = {dy[u].x, dy[u].y, dy[u].z, dy[u].w};
+                if (!plain) {
+                    d[0] = fmaf(sc.x, bn_dv(dy[u].x, h[u].x, rf[u].x, has_ref, sc.x, sh.x, slope), fmaf(pz.x, h[u].x, pw.x));
+                    d[1] = fmaf(sc.y, bn_dv(dy[u].y, h[u].y, rf[u].y, has_ref, sc.y, sh.y, slope), fmaf(pz.y, h[u].y, pw.y));
+                    d[2] = fmaf(sc.z, bn_dv(dy[u].z, h[u].z, rf[u].z, has_ref, sc.z, sh.z, slope), fmaf(pz.z, h[u].z, pw.z));
+                    d[3] = fmaf(sc.w, bn_dv(dy[u].w, h[u].w, rf[u].w, has_ref, sc.w, sh.w, slope), fmaf(pz.w, h[u].w, pw.w));
+                }
+#pragma unroll
+                for (int k = 0; k < KT; ++k) {
+                    float xv = fmaf(x[u][k], xs[k], xh[k]);
+                    xv = xv > 0.f ? xv : xv * slope1;
+                    xv = (ok && k < a.C1) ? xv : 0.f;          // padding rows contribute nothing (their dH is not zero under BN)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[e][k] = fmaf(d[e], xv, acc[e][k]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int k = 0; k < KT; ++k) red[(tid * 4 + e) * KT + k] = acc[e][k];
+    __syncthreads();
+    for (int j = tid; j < C4 * 4 * KT; j += 256) {               // (channel slot, e, k) summed over the row slots
+        const int cs = j / (4 * KT), ek = j % (4 * KT);
+        float tot = 0.f;
+        for (int r = 0; r < rows_per_it; ++r) tot += red[((r * C4 + cs) * 4) * KT + ek];
+        const int co = cs * 4 + ek / KT, k = ek % KT;
+        if (k < a.C1) atomicAdd(a.dW + a.slot_stride * (int64_t)(blockIdx.x % kGradSlots) + (int64_t)co * a.C1 + k, tot);
+    }
+}
+
+inline bool try_wgrad_tiny(const WgradArgs& a, cudaStream_t st, int* rc) {
+    if (a.C2 != 0 || a.C1 < 1 || a.C1 > 4 || a.dbias || (a.Cout & 3) || a.Cout > 1024 || (256 % (a.Cout >> 2)) != 0) return false;
+    if ((reinterpret_cast<uintptr_t>(a.dY) & 15) || (a.bn.scale && (reinterpret_cast<uintptr_t>(a.H) & 15))) return false;
+    if (a.bn.scale && a.bn.act_ref && (reinterpret_cast<uintptr_t>(a.bn.act_ref) & 15)) return false;
+    const int rows_per_it = 256 / (a.Cout >> 2);
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(a.M, (int64_t)rows_per_it * 4), (int64_t)kNumSMs * 8);
+    wgrad_tiny_kernel<4><<<grid, 256, 0, st>>>(a);
+    cudaError_t e = cudaPeekAtLastError();
+    *rc = e == cudaSuccess ? CRF_OK : (int)e;
+    return true;
+}
+
 // dW[co, k] += Σ_m dH[m, co] · A[m, k],  A = [prologue(X1) | X2].  Output tile 64 (co) × 64 (k) per CTA; CTAs along
 // x split the rows; partial tiles are combined with fp32 atomics.
 
@@ -725,6 +826,10 @@ int crfconv_linear_bwd(const float* dY, const float* H, const float* act_ref, co
     }
     if (dW) {
         lin::WgradArgs a{dY, H, bn, X1, C1, scale1, shift1, slope1, idx1, rows_dst, rows_src, X2, C2, wdst, dbias, M, Cout, 0, wstride};
+        {
+            int rc2 = CRF_OK;
+            if (lin::try_wgrad_tiny(a, st, &rc2)) return rc2 != CRF_OK ? rc2 : reduce_slots();
+        }
         if (lin::use_fast(M)) {
             int rc2 = CRF_OK;
             if (lin::try_wgrad3(a, precision, st, &rc2)) return rc2 != CRF_OK ? rc2 : reduce_slots();

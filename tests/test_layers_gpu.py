@@ -84,14 +84,20 @@ def _oracle_vs_product(make_oracle, make_product, inputs_cpu, grad_idx, seed=0, 
     for i in grad_idx:
         errs[f"gin{i}"] = rel_err_trimmed(ig[i].grad.cpu().numpy(), ic[i].grad.numpy())
         errs[f"gin{i}(l2)"] = rel_l2(ig[i].grad.cpu().numpy(), ic[i].grad.numpy())
+    # parameter gradients: relative L2 at `tol` over all entries; max-norm at 5·tol.  These cases have as few as 1,280 rows, so ONE
+    # run-to-run kink flip (see rel_err_trimmed) moves a weight-gradient entry by ≈1/rows of its magnitude — 1e-3 max-norm flaked
+    # about once in 15 runs on the widest case (512/256 channels); the full-size tests keep the strict kink-free 1e-3 check.
     floor = 1e-3 * max(float(p.grad.abs().max()) for p in mo.parameters())
     po = dict(mo.named_parameters())
+    loose = {}
     for n, p in mp.named_parameters():
-        errs["grad " + n] = rel_err(p.grad.cpu().numpy(), po[n].grad.numpy(), floor)
+        errs["grad(l2) " + n] = rel_l2(p.grad.cpu().numpy(), po[n].grad.numpy(), floor)
+        loose["grad " + n] = rel_err(p.grad.cpu().numpy(), po[n].grad.numpy(), floor)
     bo = dict(mo.named_buffers())
     for n, b in mp.named_buffers():
         errs["buf " + n] = rel_err(b.cpu().numpy(), bo[n].numpy())
     bad = {k: v for k, v in errs.items() if not v < tol}
+    bad.update({k: v for k, v in loose.items() if not v < 5 * tol})
     assert not bad, bad
     return max(errs.values())
 
