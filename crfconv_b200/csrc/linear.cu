@@ -37,12 +37,13 @@ template <int BN, bool X3>
 __global__ void __launch_bounds__(kThreads) fwd_kernel(const FwdArgs a) {
     __shared__ __align__(16) float As[BM][AS];
     __shared__ __align__(16) float Ws[BN][AS];
-    __shared__ float s_sum[BN], s_sq[BN];
+    // per-warp partial Σ / Σ² (no shared-memory atomics: the statistics, and with them every LeakyReLU branch decision
+    // downstream, are bit-reproducible from run to run as long as at most kStatSlots row tiles exist)
+    __shared__ float s_part[kThreads / 32][2][BN];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
     const int64_t m0 = (int64_t)blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;
     const int Ktot = a.C1 + a.C2;
-    if (tid < BN) { s_sum[tid] = 0.0f; s_sq[tid] = 0.0f; }
 
     float acc[BN / 8][4];
 #pragma unroll
@@ -164,17 +165,20 @@ __global__ void __launch_bounds__(kThreads) fwd_kernel(const FwdArgs a) {
                 q0 += __shfl_xor_sync(0xffffffffu, q0, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
             }
             if (g == 0) {
-                atomicAdd(&s_sum[nt * 8 + 2 * t], s0); atomicAdd(&s_sum[nt * 8 + 2 * t + 1], s1);
-                atomicAdd(&s_sq[nt * 8 + 2 * t], q0);  atomicAdd(&s_sq[nt * 8 + 2 * t + 1], q1);
+                s_part[w][0][nt * 8 + 2 * t] = s0; s_part[w][0][nt * 8 + 2 * t + 1] = s1;
+                s_part[w][1][nt * 8 + 2 * t] = q0; s_part[w][1][nt * 8 + 2 * t + 1] = q1;
             }
         }
     }
     if (a.stats) {
         __syncthreads();
         if (tid < BN && n0 + tid < a.Cout) {
+            float ssum = 0.f, ssq = 0.f;
+#pragma unroll
+            for (int ww = 0; ww < kThreads / 32; ++ww) { ssum += s_part[ww][0][tid]; ssq += s_part[ww][1][tid]; }
             float* st = a.stats + (size_t)(blockIdx.x % kStatSlots) * 2 * a.Cout;
-            atomicAdd(st + n0 + tid, s_sum[tid]);
-            atomicAdd(st + a.Cout + n0 + tid, s_sq[tid]);
+            atomicAdd(st + n0 + tid, ssum);
+            atomicAdd(st + a.Cout + n0 + tid, ssq);
         }
     }
 }
