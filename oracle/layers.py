@@ -171,3 +171,40 @@ class PointConvResNet(nn.Module):                       # point_conv_big.py:110-
         for lvl in (4, 3, 2, 1):
             x = getattr(self, f"deconv{lvl}")(x, skips[lvl - 1], ms[lvl - 1].up_idx, ms[lvl - 1].neighbor_idx)
         return self.classifier(x).reshape(-1, self.C)
+
+
+
+class EdgeListCRFConv(nn.Module):                         # continuous_crf_conv.py:72-133 (PyG family), restated without PyG
+    """`torch_geometric.utils.softmax(src, index)` = exp(src − max_group) / (Σ_group + 1e-16); `scatter_add` = index_add."""
+
+    def __init__(self, unary_channels, pairwise_channels, hidden_channels=None, out_channels=None, steps=1):
+        super().__init__()
+        self.out_channels = out_channels if out_channels is not None else pairwise_channels
+        self.hidden_channels = hidden_channels if hidden_channels is not None else self.out_channels // 4
+        self.steps = steps
+        h, o = self.hidden_channels, self.out_channels
+        self.unary_net = nn.Sequential(nn.Linear(unary_channels, h, bias=False), nn.BatchNorm1d(h))                    # :85-88
+        self.pairwise_net = nn.Sequential(nn.Linear(pairwise_channels, h, bias=False), nn.BatchNorm1d(h))              # :89-92
+        self.mlp = nn.Sequential(nn.Linear(h, o, bias=False), nn.BatchNorm1d(o), nn.LeakyReLU(inplace=True))           # :93-97
+        self.fusion_net = nn.Sequential(nn.Linear(o * 2, o, bias=False), nn.BatchNorm1d(o), nn.LeakyReLU(inplace=True))  # :99-103
+        self.c = nn.Parameter(torch.eye(h))                                                                            # :105,109-110
+
+    def forward(self, x, y, pos, edge_index):
+        N = pos.shape[0]
+        i, j = edge_index
+        x = self.unary_net(x)
+        s = self.pairwise_net(y)
+        s = -torch.sum((s[i] - s[j]) ** 2, dim=1, keepdim=True)                                                        # :117-118
+        mx = torch.full((N, 1), float("-inf"), dtype=s.dtype).scatter_reduce(0, i[:, None], s, reduce="amax", include_self=True)
+        ex = torch.exp(s - mx[i])
+        den = torch.zeros((N, 1), dtype=s.dtype).index_add(0, i, ex)
+        s = ex / (den[i] + 1e-16)
+        z = x
+        eye = torch.eye(self.hidden_channels, dtype=x.dtype)
+        C = torch.mm(self.c.t(), self.c)
+        for _ in range(self.steps):                                                                                    # :124-128
+            x = torch.zeros_like(z).index_add(0, i, s * x[j])
+            x = z + torch.mm(x, C)
+            x = torch.mm(x, torch.linalg.inv(eye + C))
+        x = self.mlp(x)
+        return self.fusion_net(torch.cat([x, y], dim=-1))                                                              # :130-131

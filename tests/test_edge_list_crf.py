@@ -1,0 +1,81 @@
+"""Edge-list (PyG-family) continuous-CRF layer, models/continuous_crf_conv.py:72-133: host logic on the CPU, parity on the GPU."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import layers as ol
+from oracle import native as on
+from tests._util import rel_err, rel_err_trimmed, rel_l2
+
+TOL = 1e-3      # relative fp32, as for the dense layers
+
+
+def _knn_edges(pos, k):
+    """knn_graph(pos, k) without self loops: for every target i its k nearest other points as sources."""
+    idx = on.knn_batch(pos[None].numpy(), pos[None].numpy(), k + 1)[0][:, 1:]            # drop the self match
+    i = torch.arange(pos.shape[0]).repeat_interleave(k)
+    return torch.stack([i, torch.from_numpy(idx.astype(np.int64)).reshape(-1)])
+
+
+def test_dense_neighbour_table_from_edge_lists():
+    from crfconv_b200.continuous_crf_conv import dense_neighbours
+    ei = torch.tensor([[0, 0, 1, 1, 2, 2], [1, 2, 0, 2, 0, 1]])
+    nbr = dense_neighbours(ei, 3)
+    assert nbr.shape == (1, 3, 3) and nbr[0].tolist() == [[0, 1, 2], [1, 0, 2], [2, 0, 1]]
+    perm = torch.tensor([4, 0, 2, 5, 1, 3])                                              # same graph, edges shuffled: grouped stably
+    assert dense_neighbours(ei[:, perm], 3)[0].tolist() == [[0, 1, 2], [1, 0, 2], [2, 0, 1]]
+    with pytest.raises(NotImplementedError):
+        dense_neighbours(torch.tensor([[0, 0, 1], [1, 2, 0]]), 3)                        # ragged in-degree
+    with pytest.raises(NotImplementedError):
+        dense_neighbours(torch.tensor([[0, 0, 0, 1, 2, 2], [1, 2, 1, 0, 0, 1]]), 3)
+
+
+def test_state_dict_keys_match_the_reference_module():
+    from crfconv_b200.continuous_crf_conv import ContinuousGaussianCRFConv
+    ours = ContinuousGaussianCRFConv(64, 32, steps=2)
+    ref = ol.EdgeListCRFConv(64, 32, steps=2)
+    assert list(ours.state_dict().keys()) == list(ref.state_dict().keys())
+    assert ours.hidden_channels == 8 and ours.out_channels == 32
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,Cu,Co,k,steps", [(3000, 64, 32, 16, 1), (2048, 128, 64, 15, 2)])
+def test_edge_list_layer_vs_oracle(N, Cu, Co, k, steps):
+    from crfconv_b200.continuous_crf_conv import ContinuousGaussianCRFConv
+    g = torch.Generator().manual_seed(N)
+    pos = torch.rand(N, 3, generator=g)
+    x, y = torch.randn(N, Cu, generator=g), torch.randn(N, Co, generator=g)
+    ei = _knn_edges(pos, k)
+    torch.manual_seed(1)
+    mo = ol.EdgeListCRFConv(Cu, Co, steps=steps).train()
+    with torch.no_grad():
+        mo.c.add_(0.1 * torch.randn(mo.c.shape, generator=g))
+        for n, p in mo.named_parameters():
+            if n.endswith("1.weight"):
+                p.copy_(1 + 0.2 * torch.randn(p.shape, generator=g))
+            elif n.endswith("1.bias"):
+                p.copy_(0.2 * torch.randn(p.shape, generator=g))
+    mp = ContinuousGaussianCRFConv(Cu, Co, steps=steps)
+    mp.load_state_dict(mo.state_dict())
+    mp = mp.cuda().train()
+    xc, yc = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+    xg, yg = x.clone().cuda().requires_grad_(True), y.clone().cuda().requires_grad_(True)
+    oo = mo(xc, yc, pos, ei)
+    cot = torch.randn(oo.shape, generator=g)
+    (oo * cot).sum().backward()
+    og = mp(xg, yg, pos.cuda(), ei.cuda())
+    (og * cot.cuda()).sum().backward()
+    errs = {"out": rel_err_trimmed(og.detach().cpu().numpy(), oo.detach().numpy()), "out(l2)": rel_l2(og.detach().cpu().numpy(), oo.detach().numpy()),
+            "dx": rel_err_trimmed(xg.grad.cpu().numpy(), xc.grad.numpy()), "dx(l2)": rel_l2(xg.grad.cpu().numpy(), xc.grad.numpy()),
+            "dy": rel_err_trimmed(yg.grad.cpu().numpy(), yc.grad.numpy()), "dy(l2)": rel_l2(yg.grad.cpu().numpy(), yc.grad.numpy())}
+    floor = 1e-3 * max(float(p.grad.abs().max()) for p in mo.parameters())
+    po = dict(mo.named_parameters())
+    loose = {}
+    for n, p in mp.named_parameters():
+        errs["grad(l2) " + n] = rel_l2(p.grad.cpu().numpy(), po[n].grad.numpy(), floor)
+        loose["grad " + n] = rel_err(p.grad.cpu().numpy(), po[n].grad.numpy(), floor)
+    for n, b in mp.named_buffers():
+        errs["buf " + n] = rel_err(b.cpu().numpy(), dict(mo.named_buffers())[n].numpy())
+    bad = {k_: v for k_, v in errs.items() if not v < TOL}
+    bad.update({k_: v for k_, v in loose.items() if not v < 5 * TOL})
+    assert not bad, bad
