@@ -364,6 +364,42 @@ def run_gpu(args, rank, local_rank, world):
     torch.cuda.synchronize()
     knn_qps = 10 * B * N_POINTS / (e0.elapsed_time(e1) * 1e-3)
 
+    # ---- secondary: the whole PointConvResNet (BASELINE configs[2]) fwd+bwd on the same clouds, replayed as one CUDA graph.
+    # Reported next to the headline, never instead of it; any failure here leaves the bench line intact.
+    network = None
+    if args.graph and world == 1:
+        try:
+            import torch.nn.functional as Fn
+            from crfconv_b200 import train_dp
+            from crfconv_b200.graphs import GraphedStep
+            from crfconv_b200.point_conv_big import PointConvResNet
+            net = PointConvResNet(6, 13).to(dev).train()
+            ngr = FlatGradients(net)
+            npos, nfeat, nlab, ngen = train_dp.synthetic_shard(B, N_POINTS, 13, dev, seed=77)
+            ndata = train_dp.make_batch(npos, nfeat, nlab, generator=ngen)
+
+            def net_step():
+                ngr.zero()
+                loss = Fn.cross_entropy(net(ndata), ndata.y.reshape(-1) - 1)
+                loss.backward()
+                return loss.detach()
+
+            gs = GraphedStep(net_step)
+            for _ in range(2):
+                gs.replay()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                gs.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            net_ms = e0.elapsed_time(e1) / 5
+            network = {"metric": "PointConvResNet fwd+bwd points/s", "value": B * N_POINTS / (net_ms * 1e-3), "unit": "points/s", "ms_per_step": net_ms,
+                       "config": f"PointConvResNet(6, 13, use_crf=True), B={B}, N=40960, 5-level pyramid prebuilt on the device, one CUDA graph"}
+            del gs, net, ngr, ndata
+        except Exception as exc:                                     # noqa: BLE001
+            network = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+
     _, _, cb = cpu_layer_points_per_s(clouds=2, repeats=6, warm=1)
     line = {"metric": "CRFConv fwd+bwd points/s (N=40960,k=16)", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -378,6 +414,7 @@ def run_gpu(args, rank, local_rank, world):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_step": roofline_step, "kernels": kernels,
             "knn": {"metric": "kNN queries/s", "value": knn_qps, "unit": "queries/s", "config": f"B={B}, N=Q=40960, K=16, device-resident"},
+            "network": network,
             "cpu_baseline": cb}
     print(json.dumps(line), flush=True)
     if world > 1:
