@@ -6,10 +6,11 @@
     x^t  = ( z + (Σ_j s_ij x^{t−1}_j)·C )·(I + C)⁻¹ ,  z = unary_net(x) ,  C = cᵀc                       (:121-128)
     out  = fusion_net([ mlp(x^T) | y ])                                                                 (:130-131)
 
-It runs on the same sm_100a mean-field kernels as the dense layer (csrc/crf.cu).  Those kernels take a [N, K] neighbour table,
-so the edge list must be REGULAR: every node is the target of the same number of edges — what ``knn_graph(pos, k)`` produces
-(point_conv.py:267-280).  Ragged graphs (``radius_graph`` with ``max_num_neighbors``) need a CSR kernel that is not built yet and
-are rejected loudly.  ``GuideGaussianCRFConv`` (:9-69) builds its own radius graph and is not provided for the same reason.
+It runs on the same sm_100a mean-field kernels as the dense layer (csrc/crf.cu).  Those kernels take a [N, K] neighbour table:
+a REGULAR edge list (every node the target of the same number of edges — what ``knn_graph(pos, k)`` produces, point_conv.py:267-280)
+maps onto it directly; a ragged one (``radius_graph`` with ``max_num_neighbors``) is padded to its largest in-degree with an extra
+node whose softmax weight is exactly zero (see ``dense_neighbours``).  ``GuideGaussianCRFConv`` (:9-69) builds its own radius graph
+with ``torch_cluster`` and is not provided (no radius search kernel yet).
 """
 from __future__ import annotations
 
@@ -20,24 +21,45 @@ from . import ops
 from .common import _LinearBNAct
 
 
+_FAR = 1.0e18       # embedding of the padding node: (1e18)² · F stays finite in fp32 and exp(−that) is exactly 0
+
+
 def dense_neighbours(edge_index, num_nodes):
-    """edge_index [2, E] (row 0 = target i, row 1 = source j, as the reference unpacks it at :114) → [1, N, K+1] int64 table whose
-    column 0 is the node itself (ignored by the kernels, like the self-match of the dense pipeline) and columns 1..K its sources."""
+    """edge_index [2, E] (row 0 = target i, row 1 = source j, as the reference unpacks it at :114) → ([1, N', K+1] int64 table, padded).
+
+    Column 0 of the table is the node itself (ignored by the kernels, like the self-match of the dense pipeline), columns 1..K its
+    sources in the order given.  Regular graphs (every node the target of exactly K edges, e.g. ``knn_graph``) map one to one
+    (N' = N, padded = False).  Ragged graphs (``radius_graph``) are padded to the largest in-degree with the index N of an extra
+    PADDING NODE (N' = N + 1, padded = True) that the caller appends with a far-away embedding and a zero state: its softmax
+    weight is exactly 0 in the forward and in the backward pass, so the result equals the ragged sum."""
     i, j = edge_index[0].to(torch.int64), edge_index[1].to(torch.int64)
     E = i.numel()
-    if num_nodes <= 0 or E % num_nodes != 0:
-        raise NotImplementedError("crfconv_b200: the edge-list CRF layer needs a regular graph (same in-degree for every node)")
-    K = E // num_nodes
-    expect = torch.arange(num_nodes, device=i.device).repeat_interleave(K)
-    if not torch.equal(i, expect):
+    if num_nodes <= 0:
+        raise ValueError("crfconv_b200: edge-list CRF layer needs at least one node")
+    dev = i.device
+    K = E // num_nodes if E % num_nodes == 0 else -1
+    if K > 0:
+        expect = torch.arange(num_nodes, device=dev).repeat_interleave(K)
+        regular = torch.equal(i, expect)
+    else:
+        regular = False
+    if not regular:
         order = torch.sort(i, stable=True).indices            # group by target, keeping the given order inside a group
         i, j = i[order], j[order]
-        if not torch.equal(i, expect):
-            raise NotImplementedError("crfconv_b200: the edge-list CRF layer needs a regular graph (same in-degree for every node)")
-    nbr = torch.empty((1, num_nodes, K + 1), dtype=torch.int64, device=i.device)
-    nbr[0, :, 0] = torch.arange(num_nodes, device=i.device)
-    nbr[0, :, 1:] = j.view(num_nodes, K)
-    return nbr
+        regular = K > 0 and torch.equal(i, torch.arange(num_nodes, device=dev).repeat_interleave(K))
+    if regular:
+        nbr = torch.empty((1, num_nodes, K + 1), dtype=torch.int64, device=dev)
+        nbr[0, :, 0] = torch.arange(num_nodes, device=dev)
+        nbr[0, :, 1:] = j.view(num_nodes, K)
+        return nbr, False
+    counts = torch.bincount(i, minlength=num_nodes)
+    kmax = max(int(counts.max()), 1) if E > 0 else 1
+    start = torch.cumsum(counts, 0) - counts                   # first edge of every group (edges are grouped by target now)
+    slot = torch.arange(E, device=dev) - start[i]
+    nbr = torch.full((1, num_nodes + 1, kmax + 1), num_nodes, dtype=torch.int64, device=dev)
+    nbr[0, :, 0] = torch.arange(num_nodes + 1, device=dev)
+    nbr[0, i, 1 + slot] = j
+    return nbr, True
 
 
 class _MeanField(torch.autograd.Function):
@@ -116,10 +138,15 @@ class ContinuousGaussianCRFConv(nn.Module):
         if self.hidden_channels not in (4, 8, 16, 32, 64):
             raise RuntimeError("ContinuousGaussianCRFConv: hidden channels must be 4, 8, 16, 32 or 64")
         N = pos.shape[0]
-        nbr = dense_neighbours(edge_index, N)
+        nbr, padded = dense_neighbours(edge_index, N)
         tr = self.training
         z = _lin_bn(x, self.unary_net[0], self.unary_net[1], 1.0, tr)
         e = _lin_bn(y, self.pairwise_net[0], self.pairwise_net[1], 1.0, tr)
-        xm = _MeanField.apply(z, e, nbr, self.c, self.steps)
+        if padded:                                             # the padding node: far-away embedding, zero state (after the BatchNorms)
+            zp = torch.cat([z, z.new_zeros(1, z.shape[1])], dim=0)
+            ep = torch.cat([e, e.new_full((1, e.shape[1]), _FAR)], dim=0)
+            xm = _MeanField.apply(zp, ep, nbr, self.c, self.steps)[:N]
+        else:
+            xm = _MeanField.apply(z, e, nbr, self.c, self.steps)
         o = _lin_bn(xm, self.mlp[0], self.mlp[1], self.mlp[2].negative_slope, tr)
         return _lin_bn(o, self.fusion_net[0], self.fusion_net[1], self.fusion_net[2].negative_slope, tr, x2=y)

@@ -20,14 +20,17 @@ def _knn_edges(pos, k):
 def test_dense_neighbour_table_from_edge_lists():
     from crfconv_b200.continuous_crf_conv import dense_neighbours
     ei = torch.tensor([[0, 0, 1, 1, 2, 2], [1, 2, 0, 2, 0, 1]])
-    nbr = dense_neighbours(ei, 3)
-    assert nbr.shape == (1, 3, 3) and nbr[0].tolist() == [[0, 1, 2], [1, 0, 2], [2, 0, 1]]
+    nbr, padded = dense_neighbours(ei, 3)
+    assert not padded and nbr.shape == (1, 3, 3) and nbr[0].tolist() == [[0, 1, 2], [1, 0, 2], [2, 0, 1]]
     perm = torch.tensor([4, 0, 2, 5, 1, 3])                                              # same graph, edges shuffled: grouped stably
-    assert dense_neighbours(ei[:, perm], 3)[0].tolist() == [[0, 1, 2], [1, 0, 2], [2, 0, 1]]
-    with pytest.raises(NotImplementedError):
-        dense_neighbours(torch.tensor([[0, 0, 1], [1, 2, 0]]), 3)                        # ragged in-degree
-    with pytest.raises(NotImplementedError):
-        dense_neighbours(torch.tensor([[0, 0, 0, 1, 2, 2], [1, 2, 1, 0, 0, 1]]), 3)
+    nbr, padded = dense_neighbours(ei[:, perm], 3)
+    assert not padded and nbr[0].tolist() == [[0, 1, 2], [1, 0, 2], [2, 0, 1]]
+    # ragged in-degrees (2, 1, 0): padded to 2 with the index of the extra node (3), which gets a row of its own
+    nbr, padded = dense_neighbours(torch.tensor([[0, 1, 0], [1, 0, 2]]), 3)
+    assert padded and nbr[0].tolist() == [[0, 1, 2], [1, 0, 3], [2, 3, 3], [3, 3, 3]]
+    # same edge count as a regular graph but uneven: must not be mistaken for one
+    nbr, padded = dense_neighbours(torch.tensor([[0, 0, 0, 1, 2, 2], [1, 2, 1, 0, 0, 1]]), 3)
+    assert padded and nbr.shape == (1, 4, 4) and nbr[0, 0].tolist() == [0, 1, 2, 1] and nbr[0, 1].tolist() == [1, 0, 3, 3]
 
 
 def test_state_dict_keys_match_the_reference_module():
@@ -39,13 +42,18 @@ def test_state_dict_keys_match_the_reference_module():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("N,Cu,Co,k,steps", [(3000, 64, 32, 16, 1), (2048, 128, 64, 15, 2)])
-def test_edge_list_layer_vs_oracle(N, Cu, Co, k, steps):
+@pytest.mark.parametrize("N,Cu,Co,k,steps,ragged", [(3000, 64, 32, 16, 1, False), (2048, 128, 64, 15, 2, False), (2500, 64, 32, 12, 2, True)])
+def test_edge_list_layer_vs_oracle(N, Cu, Co, k, steps, ragged):
     from crfconv_b200.continuous_crf_conv import ContinuousGaussianCRFConv
     g = torch.Generator().manual_seed(N)
     pos = torch.rand(N, 3, generator=g)
     x, y = torch.randn(N, Cu, generator=g), torch.randn(N, Co, generator=g)
     ei = _knn_edges(pos, k)
+    if ragged:                                      # radius-graph-like: drop a random 40 % of the edges (some nodes keep none) and shuffle
+        keep = torch.rand(ei.shape[1], generator=g) > 0.4
+        keep[: 3 * k] = False                       # nodes 0..2 end up with no incoming edge at all
+        ei = ei[:, keep]
+        ei = ei[:, torch.randperm(ei.shape[1], generator=g)]
     torch.manual_seed(1)
     mo = ol.EdgeListCRFConv(Cu, Co, steps=steps).train()
     with torch.no_grad():
