@@ -208,3 +208,40 @@ class EdgeListCRFConv(nn.Module):                         # continuous_crf_conv.
             x = torch.mm(x, torch.linalg.inv(eye + C))
         x = self.mlp(x)
         return self.fusion_net(torch.cat([x, y], dim=-1))                                                              # :130-131
+
+
+
+class EdgeListPointConv(nn.Module):                       # point_conv.py:12-66 (PyG family), restated without PyG
+    """MessagePassing defaults: flow source_to_target (edge_index[0] = j, edge_index[1] = i), aggr = add."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        h = out_channels // 4
+        self.mlp1 = nn.Sequential(nn.Linear(3, h, bias=False), nn.BatchNorm1d(h), nn.LeakyReLU(inplace=True),
+                                  nn.Linear(h, h, bias=False), nn.BatchNorm1d(h))                                      # :21-27
+        self.mlp2 = nn.Sequential(nn.Linear(in_channels, h, bias=False), nn.BatchNorm1d(h), nn.LeakyReLU(inplace=True))   # :28-32
+        self.mlp3 = nn.Sequential(nn.Linear(h, out_channels, bias=False), nn.BatchNorm1d(out_channels))                 # :33-36
+        if in_channels != out_channels:
+            self.mlp4 = nn.Sequential(nn.Linear(in_channels, out_channels), nn.BatchNorm1d(out_channels))              # :37-41
+
+    def forward(self, x, pos, edge_index):
+        src, dst = edge_index
+        if torch.is_tensor(pos):                                                                                       # :46-48
+            keep = src != dst
+            loops = torch.arange(pos.size(0))
+            src, dst = torch.cat([src[keep], loops]), torch.cat([dst[keep], loops])
+            pos_src, pos_dst, n_dst = pos, pos, pos.size(0)
+            residual = x
+        else:                                                                                                          # :50-53
+            pos_src, pos_dst = pos
+            n_dst = pos_dst.size(0)
+            residual = torch.full((n_dst, x.shape[1]), float("-inf"), dtype=x.dtype).scatter_reduce(
+                0, dst[:, None].expand(-1, x.shape[1]), x[src], reduce="amax", include_self=True)
+        if self.in_channels != self.out_channels:
+            residual = self.mlp4(residual)
+        x = self.mlp2(x)
+        msg = self.mlp1(pos_dst[dst] - pos_src[src]) * x[src]                                                          # :61-65
+        x = torch.zeros((n_dst, x.shape[1]), dtype=x.dtype).index_add(0, dst, msg)
+        x = self.mlp3(x)
+        return F.leaky_relu(x + residual)                                                                              # :58
