@@ -19,6 +19,8 @@ from . import ops
 from .common import MLP, bn_forward_state
 
 
+USE_FUSED = True      # tests flip this to compare the layer-specialised kernels with the generic ones
+
 _SIDE = {}
 
 
@@ -225,6 +227,213 @@ class _CRFConvFunction(torch.autograd.Function):
                 None, Gc, *grads)
 
 
+_THIRD = {}
+
+
+def _third_stream(dev):
+    """Fourth stream: in the fused backward the first layers' weight gradients (dW1 = dH1ᵀ·X) and input gradients (dX = dH1·W1)
+    are independent kernels; the weight gradient runs here."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _THIRD:
+        _THIRD[key] = torch.cuda.Stream(device=dev)
+    return _THIRD[key]
+
+
+def fused_eligible(unary, pairwise, neighbor_idx, steps, training, mods, F, Co):
+    """The layer-specialised kernels (csrc/crf_fused.cu) cover the hot-path shape family: hidden width 16 (out_channels 64),
+    16 neighbours, batch statistics in every BatchNorm, LeakyReLU-family activations in the reference's positions."""
+    if F != 16 or Co != 64 or pairwise.shape[-1] != 64 or unary.shape[-1] not in (64, 128) or neighbor_idx.shape[-1] != 16 or steps < 1:
+        return False
+    if unary.dtype != torch.float32 or pairwise.dtype != torch.float32:
+        return False
+    for m in mods:
+        bn = m.bn.batch_norm
+        if not (training or not bn.track_running_stats) or bn.momentum is None:
+            return False
+    sl = [m.slope for m in mods]
+    if any(v is None for v in sl) or sl[1] != 1.0 or sl[3] != 1.0 or not all(0.0 <= v <= 1.0 for v in sl):
+        return False
+    return True
+
+
+class _CRFConvFusedFunction(torch.autograd.Function):
+    """The same layer as _CRFConvFunction on the layer-specialised kernels: 13 launches forward, 15 backward for steps = 1
+    (was 24 + 33), every BatchNorm finalize folded into the producing kernel, out_nn's backward reduced to one pass."""
+
+    @staticmethod
+    def forward(ctx, unary, pairwise, up_idx, neighbor_idx, steps, mods, c, *params):
+        if not (unary.is_cuda and pairwise.is_cuda):
+            raise RuntimeError("crfconv_b200 layers run on CUDA tensors only (no CPU fallback)")
+        (W1u, _, _, W2u, _, _, W1p, _, _, W2p, _, _, Wo, _, _, Wf, _, _) = [p.detach().contiguous().float() for p in params]
+        bns = [m.bn.batch_norm for m in mods]          # order: u0, u1, p0, p1, out, fusion
+        sl = [m.slope for m in mods]
+        B, Nc, Cu = unary.shape
+        _, N, Cp = pairwise.shape
+        K = neighbor_idx.shape[-1]
+        dev = unary.device
+        U, P = ops.as2d(unary), ops.as2d(pairwise)
+        up = up_idx.detach().reshape(B, N).contiguous().to(torch.int64)
+        nbr = neighbor_idx.detach().contiguous().to(torch.int64)
+        Mc, M = B * Nc, B * N
+        F, Co = 16, 64
+        NP = ops.fused_max_parts()
+
+        # one zero-filled allocation: [tcgen05 statistics slots of out_nn and fusion_nn | 8 counters]; partial-sum scratches need no init
+        zf = ops.Flat(2 * ops.STAT_SLOTS * 2 * Co + 8, torch.float32, dev)
+        st_o, st_f = zf.take(ops.STAT_SLOTS * 2 * Co), zf.take(ops.STAT_SLOTS * 2 * Co)
+        cnt = zf.take(8).view(torch.int32)
+        parts = torch.empty((4, NP * 32), dtype=torch.float32, device=dev)
+        s1u, s2u, s1p, s2p = (ops.BN(F, dev, alloc_stats=False) for _ in range(4))
+        so, sf = ops.BN(Co, dev, st_o), ops.BN(Co, dev, st_f)
+        H1u, H2u = torch.empty((Mc, F), dtype=torch.float32, device=dev), torch.empty((Mc, F), dtype=torch.float32, device=dev)
+        H1p, H2p = torch.empty((M, F), dtype=torch.float32, device=dev), torch.empty((M, F), dtype=torch.float32, device=dev)
+        main, side, aux = torch.cuda.current_stream(dev), _side_stream(dev), _aux_stream(dev)
+        fork, join, join_aux = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        cc = c.detach().contiguous().float()
+        Cm, Minv = torch.empty_like(cc), torch.empty_like(cc)
+        cscr = torch.empty(3 * F * F, dtype=torch.float64, device=dev)
+        fork.record(main)
+        side.wait_event(fork)
+        aux.wait_event(fork)
+        with torch.cuda.stream(aux):
+            ops.crf_compat_fwd(cc, out=(Cm, Minv), scratch=cscr)
+            join_aux.record(aux)
+        with torch.cuda.stream(side):                  # unary_nn (:58)
+            ops.lin16_fwd(U, W1u, s1u, bns[0], parts[0], cnt[0:1], out=H1u)
+            ops.lin16_fwd(H1u, W2u, s2u, bns[1], parts[1], cnt[1:2], pre=s1u, pslope=sl[0], out=H2u)
+            join.record(side)
+        ops.lin16_fwd(P, W1p, s1p, bns[2], parts[2], cnt[2:3], out=H1p)          # pairwise_nn (:59)
+        ops.lin16_fwd(H1p, W2p, s2p, bns[3], parts[3], cnt[3:4], pre=s1p, pslope=sl[2], out=H2p)
+        main.wait_event(join)
+        main.wait_event(join_aux)
+        z = ops.crf_upsample_fwd(H2u, s2u, up, B, N, Nc)                          # (:60)
+        xs = [z]
+        for _ in range(steps):                                                    # (:68-72)
+            xs.append(ops.crf_step_fwd(H2p, s2p.scale, z, xs[-1], nbr, Cm, Minv, B, N, K))
+        H3 = ops.linear_fwd_bn(xs[-1], Wo, so, bns[4], cnt[4:5])                  # out_nn (:74)
+        Hf = ops.linear_fwd_bn(H3, Wf, sf, bns[5], cnt[5:6], scale1=so.scale, shift1=so.shift, slope1=sl[4], X2=P)   # fusion_nn (:76)
+        out = ops.bn_act_fwd(Hf, sf, sl[5])
+        nbt = [b.num_batches_tracked for b in bns if b.track_running_stats and b.num_batches_tracked is not None]
+        if nbt:
+            torch._foreach_add_(nbt, 1)
+
+        ctx.dims = (B, N, Nc, K, F, Co, Cu, Cp, steps)
+        ctx.bn = (s1u, s2u, s1p, s2p, so, sf)
+        ctx.sl = sl
+        ctx.gamma_y = bns[3].weight.detach() if bns[3].weight is not None else torch.ones(F, dtype=torch.float32, device=dev)
+        ctx.save_for_backward(U, P, up, nbr, H1u, H2u, H1p, H2p, H3, Hf, Cm, Minv, cc, W1u, W2u, W1p, W2p, Wo, Wf, *xs)
+        return out.view(B, N, Co)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (U, P, up, nbr, H1u, H2u, H1p, H2p, H3, Hf, Cm, Minv, cc, W1u, W2u, W1p, W2p, Wo, Wf, *xs) = ctx.saved_tensors
+        B, N, Nc, K, F, Co, Cu, Cp, steps = ctx.dims
+        s1u, s2u, s1p, s2p, so, sf = ctx.bn
+        sl = ctx.sl
+        dev = gout.device
+        Mc, M = B * Nc, B * N
+        z = xs[0]
+        g2 = ops.as2d(gout)
+        NP = ops.fused_max_parts()
+
+        wl = (("1u", W1u), ("2u", W2u), ("1p", W1p), ("2p", W2p), ("o", Wo), ("f", Wf))
+        cl = (("1u", F), ("2u", F), ("1p", F), ("2p", F), ("o", Co), ("f", Co))
+        n_small = sum(w.numel() for _, w in wl) + 2 * sum(n for _, n in cl) + 3 * F * F
+        n_out = ops.out_bwd_part_floats()
+        n_big = (steps + 1) * M * F + Mc * F
+        # ONE zero-filled allocation: [small grads | weight-grad partial slots | fusion BN Σ slots | out_nn partials | y sums | counters | scatter targets]
+        flat = ops.Flat(n_small * (1 + ops.GRAD_SLOTS) + ops.STAT_SLOTS * 2 * Co + n_out + 128 + 8 + n_big, torch.float32, dev)
+        small = flat.take(n_small)
+        wscr = flat.take(ops.GRAD_SLOTS * n_small)
+        sums_f = flat.take(ops.STAT_SLOTS * 2 * Co)
+        out_part = flat.take(n_out)
+        ysum = flat.take(128)
+        cnt = flat.take(8).view(torch.int32)
+        big = ops.Flat.__new__(ops.Flat); big.buf, big.off = flat.take(n_big), 0
+        parts = torch.empty((3, NP * 32), dtype=torch.float32, device=dev)
+        cursor = [0]
+
+        def take_small(*shape):
+            n = 1
+            for d in shape:
+                n *= int(d)
+            v = small[cursor[0]:cursor[0] + n].view(*shape)
+            cursor[0] += n
+            return v
+
+        def scr(t):                                          # partial-slot region that mirrors the small-gradient view `t`
+            return wscr[(t.data_ptr() - small.data_ptr()) // 4:]
+
+        GC, GM = take_small(F, F), take_small(F, F)
+        dW = {k: take_small(*w.shape) for k, w in wl}
+        dg = {k: take_small(n) for k, n in cl}
+        db = {k: take_small(n) for k, n in cl}
+        # fusion_nn (:76): BatchNorm backward sums (+ finalize), input gradients dO | dP and weight gradient on tcgen05
+        ops.bn_backward_prepare_fin(g2, Hf, sf, sl[5], dg["f"], db["f"], sums_f, cnt[0:1])
+        dO = torch.empty((M, Co), dtype=torch.float32, device=dev)
+        dP = torch.empty((M, Cp), dtype=torch.float32, device=dev)
+        ops.linear_bwd(g2, Hf, sf, sl[5], H3, Wf, scale1=so.scale, shift1=so.shift, slope1=sl[4], X2=P, dX1=dO, dX2=dP, dW=dW["f"], scratch=scr(dW["f"]), scratch_stride=n_small)
+        # out_nn (:74) in one pass over dO
+        Q, a0 = torch.empty((F, F), dtype=torch.float32, device=dev), torch.empty(F, dtype=torch.float32, device=dev)
+        T = ops.out16_bwd(dO, H3, so, sl[4], xs[-1], Wo, out_part, cnt[1:2], dg["o"], db["o"], dW["o"], Q, a0)
+        # mean-field steps, last to first (:68-72)
+        Gy = big.take(M, F)
+        Gz = torch.empty((M, F), dtype=torch.float32, device=dev)
+        g = T
+        for t in range(steps, 0, -1):
+            gprev = big.take(M, F)
+            first = t == steps
+            ops.crf_step_bwd_fused(H2p, s2p, z, xs[t - 1], nbr, Cm, Minv, g, xs[-1] if first else None, Q if first else None,
+                                   a0 if first else None, Gz, not first, gprev, Gy, scr(GC), scr(GM), n_small, ysum, B, N, K,
+                                   t == 1, cnt[2:3], ctx.gamma_y, dg["2p"], db["2p"])
+            g = gprev
+        ops.grad_slots_reduce(wscr, small, 2 * F * F, n_small)    # fold the GC / GM partial slots
+        Gc = take_small(F, F)
+        aux = _aux_stream(dev)
+        fork_aux, join_aux = torch.cuda.Event(), torch.cuda.Event()
+        bscr = torch.empty(3 * F * F, dtype=torch.float64, device=dev)
+        main = torch.cuda.current_stream(dev)
+        fork_aux.record(main)
+        aux.wait_event(fork_aux)
+        with torch.cuda.stream(aux):
+            ops.crf_compat_bwd(cc, Minv, GC, GM, Gc, scratch=bscr)
+            join_aux.record(aux)
+        Gu = big.take(Mc, F)
+        ops.crf_upsample_bwd_fused(Gz, g, up, H2u, s2u, Gu, B, N, Nc, parts[0], cnt[3:4], dg["2u"], db["2u"])   # dL/dz = Σ_t h^t + g^0
+        need_u, need_p = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dV1u = torch.empty((Mc, F), dtype=torch.float32, device=dev)
+        dV1p = torch.empty((M, F), dtype=torch.float32, device=dev)
+        dU = torch.empty((Mc, Cu), dtype=torch.float32, device=dev) if need_u else None
+        side, third = _side_stream(dev), _third_stream(dev)
+        fork, join, fork3, join3 = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):                            # unary_nn
+            ops.mid16_bwd(Gu, H2u, s2u, H1u, s1u, sl[0], W2u, scr(dW["2u"]), n_small, parts[1], cnt[4:5], dg["1u"], db["1u"], out=dV1u)
+            ops.in16_wgrad(dV1u, H1u, s1u, U, scr(dW["1u"]), n_small)
+            if need_u:
+                ops.in16_dgrad(dV1u, H1u, s1u, W1u, dU, False)
+            join.record(side)
+        # pairwise_nn (its input gradient accumulates onto the fusion_nn branch)
+        ops.mid16_bwd(Gy, H2p, s2p, H1p, s1p, sl[2], W2p, scr(dW["2p"]), n_small, parts[2], cnt[5:6], dg["1p"], db["1p"], out=dV1p)
+        fork3.record(main)
+        third.wait_event(fork3)
+        with torch.cuda.stream(third):
+            ops.in16_wgrad(dV1p, H1p, s1p, P, scr(dW["1p"]), n_small)
+            join3.record(third)
+        if need_p:
+            ops.in16_dgrad(dV1p, H1p, s1p, W1p, dP, True)
+        main.wait_event(join)
+        main.wait_event(join3)
+        main.wait_event(join_aux)
+        ops.grad_slots_reduce(wscr[2 * F * F:], small[2 * F * F:], n_small - 2 * F * F, n_small)   # all weight gradients, one launch
+        grads = []
+        for k in ("1u", "2u", "1p", "2p", "o", "f"):
+            grads += [dW[k], dg[k], db[k]]
+        return (dU.view(B, Nc, Cu) if dU is not None else None, dP.view(B, N, Cp) if need_p else None, None, None, None, None,
+                Gc, *grads)
+
+
 class ContinuousGaussianCRFConv(nn.Module):
     def __init__(self, unary_channels, pairwise_channels, out_channels=None, steps=1):
         super(ContinuousGaussianCRFConv, self).__init__()
@@ -257,4 +466,6 @@ class ContinuousGaussianCRFConv(nn.Module):
         params = []
         for m in (self.unary_nn[0], self.unary_nn[1], self.pairwise_nn[0], self.pairwise_nn[1], self.out_nn, self.fusion_nn):
             params += list(_mlp_params(m))
+        if USE_FUSED and fused_eligible(unary, pairwise, neighbor_idx, self.steps, self.training, mods, self.hidden_channels, self.out_channels):
+            return _CRFConvFusedFunction.apply(unary, pairwise, up_idx, neighbor_idx, self.steps, mods, self.c, *params)
         return _CRFConvFunction.apply(unary, pairwise, up_idx, neighbor_idx, self.steps, self.training, mods, self.c, *params)

@@ -259,7 +259,7 @@ __device__ __forceinline__ float bn_dv(float dy, float h, float ref, bool has_re
 
 // s1[c] = Σ_rows dV, s2[c] = Σ_rows dV·Ĥ (double atomics).  C % 4 == 0, C <= 1024.
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ dY, const float* __restrict__ H, BnBwd bn,
-                                                            float* __restrict__ sums, int64_t M, int C) {
+                                                            float* __restrict__ sums, int64_t M, int C, const cl::BwdFin fin) {
     __shared__ float red[256 * 8];
     const int C4 = C >> 2;
     const int tpr = C4;                           // threads per row
@@ -308,6 +308,10 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
         for (int r = 0; r < rows_per_it; ++r) tot += red[(r * tpr + cs) * 8 + e];
         const int c = cs * 4 + (e & 3);
         atomicAdd(sums + (size_t)(blockIdx.x % kStatSlots) * 2 * C + (e < 4 ? 0 : C) + c, tot);
+    }
+    if (fin.part) {                                               // k1 / k2 / dγ / dβ by the last CTA (C == 64, checked by the launcher)
+        __shared__ double s_red[256];
+        cl::bwd_fin_tail<64, 256>(fin, kStatSlots, s_red);
     }
 }
 
@@ -760,7 +764,7 @@ int crfconv_bn_bwd_reduce(const float* dY, const float* H, const float* act_ref,
     const int rows_per_it = 256 / (C / 4);
     static const int mult = [] { const char* e = getenv("CRFCONV_REDUCE_CTAS_PER_SM"); return e ? std::max(1, atoi(e)) : 8; }();
     const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(M, rows_per_it * 8), (int64_t)kNumSMs * mult);
-    lin::bn_bwd_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dY, H, bn, sums, M, C);
+    lin::bn_bwd_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dY, H, bn, sums, M, C, cl::BwdFin{});
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }
@@ -849,6 +853,44 @@ int crfconv_linear_bwd(const float* dY, const float* H, const float* act_ref, co
         CRF_LAUNCH_CHECK();
         return reduce_slots();
     }
+    return CRF_OK;
+}
+
+// crfconv_linear_fwd + training-mode BatchNorm finalize of its output (what crfconv_bn_finalize_fwd computes from `stats`), in ONE
+// launch when the tcgen05 kernel takes the shape (the last CTA to finish folds the statistics slots), else in two.  stats is
+// required ([CRFCONV_STAT_SLOTS][2·Cout], zeroed); counter = one zeroed uint32 (left zero).
+int crfconv_linear_fwd_bn(const float* X1, int C1, const float* scale1, const float* shift1, float slope1, const float* X2, int C2,
+                          const float* W, float* Y, float* stats, int64_t M, int Cout, int precision, unsigned int* counter,
+                          const float* gamma, const float* beta, float* running_mean, float* running_var, float eps, float momentum,
+                          float* scale, float* shift, float* mean, float* invstd, void* stream) {
+    if (M <= 0 || Cout <= 0 || C1 <= 0 || C2 < 0 || !X1 || (C2 > 0 && !X2) || !W || !Y || !stats || !counter || !scale || !shift) return CRF_ERR_INVALID_ARG;
+    lin::FwdArgs a{X1, C1, scale1, shift1, slope1, nullptr, 0, 0, X2, C2, W, nullptr, Y, stats, M, Cout};
+    a.fin = cl::FwdFin{stats, counter, gamma, beta, running_mean, running_var, eps, momentum, (double)M, scale, shift, mean, invstd};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (lin::use_fast(M)) {
+        int rc2 = CRF_OK;
+        if (lin::try_fwd3(a, precision, st, &rc2)) return rc2;
+    }
+    const int rc = crfconv_linear_fwd(X1, C1, scale1, shift1, slope1, nullptr, 0, 0, X2, C2, W, nullptr, Y, stats, M, Cout, precision, stream);
+    if (rc != CRF_OK) return rc;
+    return crfconv_bn_finalize_fwd(stats, M, gamma, beta, eps, momentum, 1, running_mean, running_var, scale, shift, mean, invstd, Cout, stream);
+}
+
+// crfconv_bn_bwd_reduce + crfconv_bn_finalize_bwd in one launch (C == 64) or two.  sums: [CRFCONV_STAT_SLOTS][2·C] zeroed.
+int crfconv_bn_bwd_reduce_fin(const float* dY, const float* H, const float* act_ref, const float* scale, const float* shift,
+                              const float* mean, const float* invstd, float slope, float* sums, int64_t M, int C, unsigned int* counter,
+                              float* k1, float* k2, float* dgamma, float* dbeta, void* stream) {
+    if (!sums || !counter || !k1 || !k2) return CRF_ERR_INVALID_ARG;
+    if (C != 64 || M <= 0) {
+        const int rc = crfconv_bn_bwd_reduce(dY, H, act_ref, scale, shift, mean, invstd, slope, sums, M, C, stream);
+        if (rc != CRF_OK) return rc;
+        return crfconv_bn_finalize_bwd(sums, M, k1, k2, dgamma, dbeta, C, stream);
+    }
+    lin::BnBwd bn{scale, shift, mean, invstd, nullptr, nullptr, act_ref, slope};
+    const int rows_per_it = 256 / (C / 4);
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(M, rows_per_it * 8), (int64_t)kNumSMs * 8);
+    lin::bn_bwd_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dY, H, bn, sums, M, C, cl::BwdFin{sums, counter, (double)M, k1, k2, dgamma, dbeta});
+    CRF_LAUNCH_CHECK();
     return CRF_OK;
 }
 

@@ -360,6 +360,11 @@ __global__ void __launch_bounds__(kThreads, 1) fwd3_kernel(const FwdArgs a, cons
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, L::kTmemCols);
+    if (a.fin.part) {                                              // BatchNorm finalize by the last CTA (Cout == BN, checked by the launcher)
+        constexpr int NT = (kThreads / (2 * BN)) * (2 * BN);
+        __shared__ double s_red[NT];
+        cl::fwd_fin_tail<BN, NT>(a.fin, kStatSlots, s_red);
+    }
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -408,6 +413,7 @@ bool try_fwd3(const FwdArgs& a, int precision, cudaStream_t st, int* rc) {
         if (e != cudaSuccess) *rc = (int)e;
         return true;
     };
+    if (a.fin.part && (a.fin.part != a.stats || (a.Cout != 64 && a.Cout != 32 && a.Cout != 16))) return false;   // fused finalize: Cout == BN only
     if (a.Cout > 32) return go(std::integral_constant<int, 64>{});
     if (a.Cout > 16) return go(std::integral_constant<int, 32>{});
     return go(std::integral_constant<int, 16>{});

@@ -2,6 +2,8 @@
 #pragma once
 #include <cstdint>
 
+#include "fused_common.cuh"
+
 namespace crf {
 namespace lin {
 
@@ -15,6 +17,7 @@ struct FwdArgs {
     float* Y;                                     // [M, Cout]
     float* stats;                                 // [kStatSlots][2*Cout] partial Σ, Σ² over rows (or null)
     int64_t M; int Cout;
+    cl::FwdFin fin;                               // optional: BatchNorm finalize by the last CTA (kernels that support it; part = stats)
 };
 
 // Per-channel description of a BatchNorm(+LeakyReLU) node for the on-the-fly backward transform.

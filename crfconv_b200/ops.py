@@ -84,9 +84,11 @@ class BN:
     """Per-BatchNorm scratch: slotted f32 Σ/Σ² partial accumulators, fused affine (scale, shift), saved mean/invstd, backward k1/k2."""
     __slots__ = ("C", "stats", "scale", "shift", "mean", "invstd", "k1", "k2", "count", "training")
 
-    def __init__(self, C, device, stats=None):
+    def __init__(self, C, device, stats=None, alloc_stats=True):
         self.C = C
-        self.stats = stats if stats is not None else torch.zeros(STAT_SLOTS * 2 * C, dtype=torch.float32, device=device)   # zeroed
+        if stats is None and alloc_stats:
+            stats = torch.zeros(STAT_SLOTS * 2 * C, dtype=torch.float32, device=device)   # zeroed
+        self.stats = stats
         buf = torch.empty(6, C, dtype=torch.float32, device=device)
         self.scale, self.shift, self.mean, self.invstd, self.k1, self.k2 = buf.unbind(0)
         self.count = 0
@@ -335,3 +337,123 @@ def scatter_add_rows(src, idx, dst, B, Nq, Ns):
     with _call(f"scatter_add_rows[{src.shape[1]}]", 1, _nbytes(src, idx, dst)):
         rc = L.crfconv_scatter_add_rows(_p(src), _p(idx), _p(dst), B, Nq, Ns, src.shape[1], _lib.stream_ptr())
     _lib.check(rc, "scatter_add_rows")
+
+
+# --------------------------------------------------------------------- layer-specialised (fused) CRF kernels, F = 16
+def fused_max_parts():
+    return int(_lib.lib().crfconv_fused_max_parts())
+
+
+def out_bwd_part_floats():
+    return int(_lib.lib().crfconv_out_bwd_part_floats())
+
+
+def _bn_fin_args(bn_module):
+    """(gamma, beta, running_mean, running_var, eps, momentum) of an nn.BatchNorm1d in training mode."""
+    if bn_module.momentum is None:
+        raise RuntimeError("crfconv_b200: BatchNorm momentum=None (cumulative average) is not supported by the fused kernels")
+    track = bn_module.track_running_stats and bn_module.running_mean is not None
+    return (_p(bn_module.weight), _p(bn_module.bias), _p(bn_module.running_mean) if track else None,
+            _p(bn_module.running_var) if track else None, float(bn_module.eps), float(bn_module.momentum))
+
+
+def lin16_fwd(X, W, bn: BN, bn_module, part, counter, pre: BN = None, pslope=1.0, out=None):
+    """H = act(X)·Wᵀ (16 output channels) with `bn`'s scale/shift/mean/invstd (and the module's running statistics) finalized by
+    the same launch.  pre: BN state whose affine + LeakyReLU(pslope) is applied to X on the fly (X has 16 channels then)."""
+    L = _lib.lib()
+    M, Cin = X.shape
+    Y = out if out is not None else torch.empty((M, 16), dtype=torch.float32, device=X.device)
+    gm, bt, rm, rv, eps, mom = _bn_fin_args(bn_module)
+    bn.count, bn.training = int(M), True
+    with _call(f"lin16_fwd[{Cin}]", 1, _nbytes(X, Y)):
+        rc = L.crfconv_lin16_fwd(_p(X), int(Cin), _p(W), _p(pre.scale) if pre else None, _p(pre.shift) if pre else None, float(pslope),
+                                 _p(Y), int(M), _p(part), _p(counter), gm, bt, rm, rv, eps, mom, _p(bn.scale), _p(bn.shift), _p(bn.mean),
+                                 _p(bn.invstd), _lib.stream_ptr())
+    _lib.check(rc, "lin16_fwd")
+    return Y
+
+
+def linear_fwd_bn(X1, W, bn: BN, bn_module, counter, *, scale1=None, shift1=None, slope1=1.0, X2=None, out=None):
+    """linear_fwd + BatchNorm finalize of the output in one launch (tcgen05 kernel) or two (other shapes).  bn.stats zeroed."""
+    L = _lib.lib()
+    M, C1 = X1.shape
+    C2 = X2.shape[1] if X2 is not None else 0
+    Cout = W.shape[0]
+    Y = out if out is not None else torch.empty((M, Cout), dtype=torch.float32, device=X1.device)
+    gm, bt, rm, rv, eps, mom = _bn_fin_args(bn_module)
+    bn.count, bn.training = int(M), True
+    with _call(f"linear_fwd_bn[{C1 + C2}->{Cout}]", 1, M * (C1 + C2 + Cout) * 4):
+        rc = L.crfconv_linear_fwd_bn(_p(X1), int(C1), _p(scale1), _p(shift1), float(slope1), _p(X2), int(C2), _p(W), _p(Y), _p(bn.stats),
+                                     int(M), int(Cout), PRECISION, _p(counter), gm, bt, rm, rv, eps, mom, _p(bn.scale), _p(bn.shift),
+                                     _p(bn.mean), _p(bn.invstd), _lib.stream_ptr())
+    _lib.check(rc, "linear_fwd_bn")
+    return Y
+
+
+def bn_backward_prepare_fin(dY, H, bn: BN, slope, dgamma, dbeta, sums, counter):
+    """bn_backward_prepare in one launch (C = 64) or two."""
+    L = _lib.lib()
+    with _call(f"bn_bwd_reduce_fin[{bn.C}]", 1, _nbytes(dY, H)):
+        rc = L.crfconv_bn_bwd_reduce_fin(_p(dY), _p(H), None, _p(bn.scale), _p(bn.shift), _p(bn.mean), _p(bn.invstd), float(slope),
+                                         _p(sums), H.shape[0], bn.C, _p(counter), _p(bn.k1), _p(bn.k2), _p(dgamma), _p(dbeta),
+                                         _lib.stream_ptr())
+    _lib.check(rc, "bn_bwd_reduce_fin")
+
+
+def mid16_bwd(dY, H2, bn2: BN, H1, bn1: BN, slope1, W2, dW2_slots, slot_stride, part, counter, dgamma1, dbeta1, out=None):
+    L = _lib.lib()
+    dV1 = out if out is not None else torch.empty_like(H1)
+    with _call("mid16_bwd", 1, _nbytes(dY, H2, H1, dV1)):
+        rc = L.crfconv_mid16_bwd(_p(dY), _p(H2), _p(bn2.scale), _p(bn2.mean), _p(bn2.invstd), _p(bn2.k1), _p(bn2.k2), _p(H1), _p(bn1.scale),
+                                 _p(bn1.shift), _p(bn1.mean), _p(bn1.invstd), float(slope1), _p(W2), _p(dV1), _p(dW2_slots), int(slot_stride),
+                                 H1.shape[0], _p(part), _p(counter), _p(bn1.k1), _p(bn1.k2), _p(dgamma1), _p(dbeta1), _lib.stream_ptr())
+    _lib.check(rc, "mid16_bwd")
+    return dV1
+
+
+def in16_dgrad(dV1, H1, bn1: BN, W1, dX, accumulate):
+    L = _lib.lib()
+    Cin = W1.shape[1]
+    with _call(f"in16_dgrad[{Cin}]", 1, _nbytes(dV1, H1, dX, dX if accumulate else None)):
+        rc = L.crfconv_in16_dgrad(_p(dV1), _p(H1), _p(bn1.scale), _p(bn1.mean), _p(bn1.invstd), _p(bn1.k1), _p(bn1.k2), _p(W1), int(Cin),
+                                  _p(dX), int(bool(accumulate)), H1.shape[0], _lib.stream_ptr())
+    _lib.check(rc, "in16_dgrad")
+
+
+def in16_wgrad(dV1, H1, bn1: BN, X, dW_slots, slot_stride):
+    L = _lib.lib()
+    Cin = X.shape[1]
+    with _call(f"in16_wgrad[{Cin}]", 1, _nbytes(dV1, H1, X)):
+        rc = L.crfconv_in16_wgrad(_p(dV1), _p(H1), _p(bn1.scale), _p(bn1.mean), _p(bn1.invstd), _p(bn1.k1), _p(bn1.k2), _p(X), int(Cin),
+                                  _p(dW_slots), int(slot_stride), H1.shape[0], _lib.stream_ptr())
+    _lib.check(rc, "in16_wgrad")
+
+
+def out16_bwd(dO, H3, bn3: BN, slope3, X, W3, part, counter, dgamma, dbeta, dW3, Q, a0, out=None):
+    L = _lib.lib()
+    T = out if out is not None else torch.empty_like(X)
+    with _call("out16_bwd", 1, _nbytes(dO, H3, X, T)):
+        rc = L.crfconv_out16_bwd(_p(dO), _p(H3), _p(bn3.scale), _p(bn3.shift), _p(bn3.mean), _p(bn3.invstd), float(slope3), _p(X), _p(W3),
+                                 _p(T), X.shape[0], _p(part), _p(counter), _p(bn3.k1), _p(bn3.k2), _p(dgamma), _p(dbeta), _p(dW3), _p(Q),
+                                 _p(a0), _lib.stream_ptr())
+    _lib.check(rc, "out16_bwd")
+    return T
+
+
+def crf_step_bwd_fused(Hy, bn_y: BN, z, xprev, nbr, Cm, Minv, g, xT, Q, a0, Gz, gz_acc, gprev, Gy, GC_slots, GM_slots, slot_stride, ysum,
+                       B, N, K, finalize, counter, gamma_y, dgamma, dbeta):
+    L = _lib.lib()
+    with _call("crf_step_bwd_fused", 1, _nbytes(Hy, z, xprev, nbr, g, xT, Gz, gprev, Gy)):
+        rc = L.crfconv_crf_step_bwd_fused(_p(Hy), _p(bn_y.scale), _p(z), _p(xprev), _p(nbr), _p(Cm), _p(Minv), _p(g), _p(xT), _p(Q), _p(a0),
+                                          _p(Gz), int(gz_acc), _p(gprev), _p(Gy), _p(GC_slots), _p(GM_slots), int(slot_stride), _p(ysum),
+                                          B, N, K, z.shape[1], int(bool(finalize)), _p(counter), _p(gamma_y), _p(bn_y.k1), _p(bn_y.k2),
+                                          _p(dgamma), _p(dbeta), _lib.stream_ptr())
+    _lib.check(rc, "crf_step_bwd_fused")
+
+
+def crf_upsample_bwd_fused(Gz, G0, up_idx, Hu, bn_u: BN, Gu, B, N, Nc, part, counter, dgamma, dbeta):
+    L = _lib.lib()
+    with _call("crf_upsample_bwd_fused", 1, _nbytes(Gz, G0, up_idx, Gu)):
+        rc = L.crfconv_crf_upsample_bwd_fused(_p(Gz), _p(G0), _p(up_idx), _p(Hu), _p(bn_u.mean), _p(bn_u.invstd), _p(Gu), B, N, Nc, _p(part),
+                                              _p(counter), _p(bn_u.k1), _p(bn_u.k2), _p(dgamma), _p(dbeta), _lib.stream_ptr())
+    _lib.check(rc, "crf_upsample_bwd_fused")

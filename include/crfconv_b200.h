@@ -144,6 +144,62 @@ int crfconv_crf_step_bwd(const float* Hy, const float* scale_y, const float* z, 
                          const float* Cm, const float* Minv, const float* g, float* Gz, float* gprev, float* Gy, float* m_out,
                          float* v_out, float* h_out, int gz_acc, int64_t B, int64_t N, int K, int F, void* stream);
 
+/* --------------------------------------------- layer-specialised ("fused") kernels of the dense CRF layer, F = 16
+ * The same arithmetic as the entry points above for models/continuous_crf_conv_big.py:20-29,56-78, cut at the BatchNorm
+ * boundaries so that each boundary costs ONE streaming pass: the BatchNorm bookkeeping (crfconv_bn_finalize_fwd / _bwd) runs in
+ * the tail of the producing kernel (last CTA to finish), the backward sums of the NEXT BatchNorm are emitted by the kernel that
+ * produces its upstream gradient, and out_nn's backward (:74) collapses to a per-point affine map (see csrc/crf_fused.cu).
+ * `part` scratches hold per-CTA partial sums (no initialisation needed unless stated); every `counter` is one zeroed uint32
+ * that the kernel leaves zero.  Weight gradients go to CRFCONV_GRAD_SLOTS zero-initialised partial slots (slot_stride floats
+ * apart) that crfconv_grad_slots_reduce folds. */
+
+int crfconv_fused_max_parts(void);        /* rows of a `part` scratch: part = max_parts · 32 floats */
+int crfconv_out_bwd_part_floats(void);    /* floats of crfconv_out16_bwd's `part` (zero-initialised) */
+/* Tuning knobs for experiments (key 0: CTAs/SM of the mean-field backward, 2 or 3).  Returns the previous value. */
+int crfconv_fused_tune(int key, int value);
+
+/* H[M,16] = act(X[M,Cin])·Wᵀ + BatchNorm finalize of H (MLP(Cin,16), common.py:26-40).  Cin ∈ {64,128}: X raw; Cin = 16: X is the
+ * previous layer's pre-BN output and pscale/pshift/pslope its BN affine + LeakyReLU. */
+int crfconv_lin16_fwd(const float* X, int Cin, const float* W, const float* pscale, const float* pshift, float pslope, float* Y, int64_t M,
+                      float* part, unsigned int* counter, const float* gamma, const float* beta, float* running_mean,
+                      float* running_var, float eps, float momentum, float* scale, float* shift, float* mean, float* invstd, void* stream);
+/* crfconv_linear_fwd (no gather, no bias) + BatchNorm finalize of its output; stats [CRFCONV_STAT_SLOTS][2·Cout] zeroed. */
+int crfconv_linear_fwd_bn(const float* X1, int C1, const float* scale1, const float* shift1, float slope1, const float* X2, int C2,
+                          const float* W, float* Y, float* stats, int64_t M, int Cout, int precision, unsigned int* counter,
+                          const float* gamma, const float* beta, float* running_mean, float* running_var, float eps, float momentum,
+                          float* scale, float* shift, float* mean, float* invstd, void* stream);
+/* crfconv_bn_bwd_reduce + crfconv_bn_finalize_bwd (one launch for C = 64). */
+int crfconv_bn_bwd_reduce_fin(const float* dY, const float* H, const float* act_ref, const float* scale, const float* shift,
+                              const float* mean, const float* invstd, float slope, float* sums, int64_t M, int C, unsigned int* counter,
+                              float* k1, float* k2, float* dgamma, float* dbeta, void* stream);
+/* Backward of y = BN2(lrelu(BN1(H1))·W2ᵀ) given dY: dV1 = (dH2·W2)⊙lrelu'(BN1(H1)), dW2 slots, BN1's backward constants. */
+int crfconv_mid16_bwd(const float* dY, const float* H2, const float* sc2, const float* mu2, const float* is2, const float* k1_2,
+                      const float* k2_2, const float* H1, const float* sc1, const float* sh1, const float* mu1, const float* is1,
+                      float slope1, const float* W2, float* dV1, float* dW2, int64_t slot_stride, int64_t M, float* part,
+                      unsigned int* counter, float* k1_1, float* k2_1, float* dgamma1, float* dbeta1, void* stream);
+/* dX[M,Cin] (= or +=) BNbwd(dV1,H1)·W1 ;  dW1 slots += BNbwd(dV1,H1)ᵀ·X.  Cin ∈ {64,128}. */
+int crfconv_in16_dgrad(const float* dV1, const float* H1, const float* sc1, const float* mu1, const float* is1, const float* k1,
+                       const float* k2, const float* W1, int Cin, float* dX, int accumulate, int64_t M, void* stream);
+int crfconv_in16_wgrad(const float* dV1, const float* H1, const float* sc1, const float* mu1, const float* is1, const float* k1,
+                       const float* k2, const float* X, int Cin, float* dW, int64_t slot_stride, int64_t M, void* stream);
+/* out_nn = MLP(16,64) backward in one pass over dO: T = W3ᵀ·(sc3⊙dv3), k1/k2, dγ/dβ, dW3 +=, and Q[16,16], a0[16] with
+ * dL/dx_i = T_i − a0 − Q·x_i. */
+int crfconv_out16_bwd(const float* dO, const float* H3, const float* sc3, const float* sh3, const float* mu3, const float* is3,
+                      float slope3, const float* X, const float* W3, float* T, int64_t M, float* part, unsigned int* counter,
+                      float* k1, float* k2, float* dgamma, float* dbeta, float* dW3, float* Q, float* a0, void* stream);
+/* crfconv_crf_step_bwd for F = K = 16 with GC/GM accumulated in-kernel (slots), the out_nn correction g ← g − a0 − Q·xT applied on
+ * the fly (Q may be NULL) and the BatchNorm-backward constants of the y layer (gamma_y = its weight) finalized on the last
+ * launch (finalize != 0).  ysum: 8·16 zeroed floats shared by all steps of one backward. */
+int crfconv_crf_step_bwd_fused(const float* Hy, const float* sc_y, const float* z, const float* xprev, const int64_t* neighbor_idx,
+                               const float* Cm, const float* Minv, const float* g, const float* xT, const float* Q, const float* a0,
+                               float* Gz, int gz_acc, float* gprev, float* Gy, float* GC, float* GM, int64_t slot_stride,
+                               float* ysum, int64_t B, int64_t N, int K, int F, int finalize, unsigned int* counter,
+                               const float* gamma_y, float* k1, float* k2, float* dgamma, float* dbeta, void* stream);
+/* crfconv_crf_upsample_bwd for F = 16 + the BatchNorm-backward constants of unary_nn[1] (Hu = its pre-BN output). */
+int crfconv_crf_upsample_bwd_fused(const float* Gz, const float* G0, const int64_t* up_idx, const float* Hu, const float* mu,
+                                   const float* is, float* Gu, int64_t B, int64_t N, int64_t Nc, float* part, unsigned int* counter,
+                                   float* k1, float* k2, float* dgamma, float* dbeta, void* stream);
+
 /* ------------------------------------------------------- neighbour gather / point-conv aggregation
  * Replaces PointConv.gather_neighbors / _compute_weights / forward (models/point_conv_big.py:25-58),
  * ResNetBBlock.max_pooling (:74-77) and the backward of Upsampling.upsampling (:97-101).  idx [B,Nq,K] i64 indexes the
