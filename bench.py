@@ -1,24 +1,33 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the CRFConv hot path (BASELINE.json metric: CRFConv fwd+bwd points/s at N=40,960, k=16).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--clouds B] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config S1|C3|C4|C5] [--clouds B] [--impl reference]
 
-One *step* = forward + backward of ONE ``ContinuousGaussianCRFConv(128, 64, 64, steps=1)`` layer (SURVEY.md §8 config S1:
-N=40,960 points, Nc=10,240 coarse points, K=16, Cu=128, Cp=Co=64, hidden F=16) over a batch of B synthetic S3DIS-room-shaped
-clouds per GPU.  Clouds are independent ⇒ ranks hold different clouds (weak scaling); the only exchange is the NCCL
-all-reduce of the layer's flat fp32 parameter gradient (13,440 floats), inside the timed step when N > 1.
+--config S1 (default; SURVEY.md §8 S1 = BASELINE configs[0] shape on the GPU): one *step* = forward + backward of ONE
+``ContinuousGaussianCRFConv(128, 64, 64, steps=1)`` layer (N=40,960 points, Nc=10,240 coarse points, K=16, Cu=128, Cp=Co=64,
+hidden F=16) over a batch of B = 6 synthetic S3DIS-room-shaped clouds per GPU.
+--config C3 / C4 / C5 (BASELINE configs[2..4]): one step = forward + cross-entropy + backward of the whole ``PointConvResNet``
+(6 input channels, use_crf=True) on B clouds per GPU of 40,960 points / 13 classes (C3, B=6), 45,056 points / 19 classes
+(C4, SemanticKITTI-shaped, B=8) or 65,536 points / 8 classes (C5, Semantic3D-shaped, B=2); the 5-level kNN pyramid is an input.
+Clouds are independent ⇒ ranks hold different clouds (weak scaling); the only exchange is the NCCL all-reduce of the flat fp32
+parameter gradient, inside the timed step when N > 1.
 
-value   : points/s with inputs resident in HBM (CUDA-event timed, max over ranks).
-e2e     : same metric through the public module API with HOST (pinned) inputs: H2D of unary/pairwise/up_idx/neighbor_idx and
-          a D2H read of the loss every step.
-roofline: the dominant kernel (per-call CUDA-event timing of every C-ABI launch in a separate instrumented pass) and, as
-          `roofline_step`, the whole layer against SURVEY.md §8(d)'s algorithmic bytes (79,298,560 B per cloud fwd+bwd).
-cpu_baseline / --impl reference: the CPU port of the reference layer (oracle/layers.py, PyTorch CPU, all host threads) on a
-          bounded sample of the same workload.  The reference itself is Python and is not present on the GPU box.
+value        : points/s with inputs resident in HBM (CUDA-event timed, max over ranks), the step replayed as a CUDA graph.
+e2e          : same metric through the public API with HOST (pinned) inputs: H2D of every input of the step (S1: unary / pairwise /
+               up_idx / neighbor_idx; C3-C5: points, features, labels — the pyramid is then built on the GPU inside the timed
+               region) and a D2H read of the loss every step.  Ranks bind to their GPU's NUMA node before allocating pinned memory;
+               `e2e.h2d_gbs_per_gpu` and `e2e.h2d_probe_gbs_per_gpu` (all ranks copying at once, no compute) locate the host-side ceiling.
+roofline     : the WHOLE step against SURVEY.md §8(d)'s algorithmic bytes (S1: 79,298,560 B per cloud fwd+bwd; C3-C5: the shape
+               walker `network_algo_bytes`) — `frac` is the north_star fraction.  `roofline.dominant_kernel` names the single
+               kernel with the largest share of the step; `kernels` lists every kernel call with its own bytes and GB/s.
+cpu_baseline / --impl reference: the CPU port of the reference (oracle/layers.py, PyTorch CPU, all host threads) on the SAME
+               workload (S1: the same 6 clouds per step; C3-C5: a bounded 2-cloud sample).  The reference itself is Python and is
+               not present on the GPU box.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -33,6 +42,39 @@ sys.path.insert(0, ROOT)
 N_POINTS, K_NBR, CU, CP, RATIO = 40960, 16, 128, 64, 4
 ALGO_BYTES_PER_CLOUD = 4 * (2 * N_POINTS * CP + 3 * (N_POINTS // RATIO) * CU + 3 * N_POINTS * CP) + 16 * N_POINTS * (K_NBR + 1)  # 79,298,560
 L2_BYTES = 126 * 2**20
+METRIC = "CRFConv fwd+bwd points/s (N=40960,k=16)"
+
+# BASELINE.json configs[2..4]: the full segmentation network (in_channels = 6: xyz + rgb, trainval.py:33-35,61)
+NET_CONFIGS = {
+    "C3": {"points": 40960, "classes": 13, "clouds": 6, "name": "S3DIS-shaped batch of 6 x 40,960 points, 13 classes (BASELINE configs[2])"},
+    "C4": {"points": 45056, "classes": 19, "clouds": 8, "name": "SemanticKITTI-shaped scans, 45,056 points, 19 classes, 8 clouds per GPU (BASELINE configs[3])"},
+    "C5": {"points": 65536, "classes": 8, "clouds": 2, "name": "Semantic3D-shaped crops, 65,536 points, 8 classes, 2 clouds per GPU (BASELINE configs[4])"},
+}
+
+
+def crf_layer_algo_bytes(N, Nc, Cu, Cp, Co, K=16):
+    """every API-boundary tensor crosses HBM once per pass; fwd+bwd of one dense CRF layer, per cloud."""
+    return 4 * (2 * N * Co + 3 * Nc * Cu + 3 * N * Cp) + 16 * N * (K + 1)
+
+
+def network_algo_bytes(N0, n_classes, in_channels=6, K=16):
+    """Shape walker over PointConvResNet (models/point_conv_big.py:110-167) with SURVEY.md §8(d)'s per-layer formulas: fwd+bwd
+    algorithmic bytes per cloud = 10 ResNetBBlocks + 4 CRF layers + classifier (hidden activations excluded: they may be recomputed)."""
+    ratios = (4, 4, 4, 4, 2)
+    Ns = [N0]
+    for r in ratios[:4]:
+        Ns.append(Ns[-1] // r)
+    C = [32, 64, 128, 256, 512]
+
+    def block(n_in, n_out, cin, cout):
+        return 4 * n_in * 3 * cin + 4 * n_out * 2 * cout + 2 * (12 * (n_in + n_out) + 8 * n_out * K)
+    total = block(Ns[0], Ns[0], in_channels, C[0]) + block(Ns[0], Ns[0], C[0], C[0])
+    for l in range(1, 5):
+        total += block(Ns[l - 1], Ns[l], C[l - 1], C[l]) + block(Ns[l], Ns[l], C[l], C[l])
+    for l in (3, 2, 1, 0):                                 # deconv4..deconv1: unary = level l+1 (C[l+1]), pairwise = skip at level l (C[l])
+        total += crf_layer_algo_bytes(Ns[l], Ns[l + 1], C[l + 1], C[l], C[l], K)
+    total += 4 * Ns[0] * (3 * C[0] + 2 * n_classes)        # classifier: x read (fwd, bwd) + dx written, logits written + their gradient read
+    return total
 
 
 def measured_peaks():
@@ -78,10 +120,58 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Pins this process to the CPUs of its GPU's NUMA node and prefers that node's memory BEFORE any pinned allocation, so that
+    each rank's H2D copies read local DRAM instead of crossing the socket interconnect.  Returns a description for the bench line."""
+    info = {"numa_node": None, "cpus": None, "mempolicy": None}
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = f"{getattr(pr, 'pci_domain_id', 0):04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        info["pci"] = bus
+        if node < 0:
+            info["numa_node"] = -1
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        info["numa_node"], info["cpus"] = node, len(cpus)
+        try:                                            # set_mempolicy(MPOL_PREFERRED = 1, nodemask, maxnode): x86_64 syscall 238
+            mask = (ctypes.c_ulong * 16)()
+            mask[node // 64] = 1 << (node % 64)
+            rc = ctypes.CDLL(None, use_errno=True).syscall(238, 1, mask, 16 * 64)
+            info["mempolicy"] = "preferred" if rc == 0 else f"errno {ctypes.get_errno()}"
+        except Exception as exc:                         # noqa: BLE001
+            info["mempolicy"] = f"unavailable ({type(exc).__name__})"
+    except Exception as exc:                             # noqa: BLE001
+        info["error"] = f"{type(exc).__name__}: {exc}"[:120]
+    return info
+
+
+def h2d_probe(torch, dev, host_tensors, barrier, reps=8):
+    """H2D bandwidth of this rank's pinned input set with every rank copying at the same time and no compute: the host-side ceiling."""
+    dst = {k: torch.empty_like(v, device=dev) for k, v in host_tensors.items()}
+    nbytes = sum(v.numel() * v.element_size() for v in host_tensors.values())
+    for k, v in host_tensors.items():
+        dst[k].copy_(v, non_blocking=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        for k, v in host_tensors.items():
+            dst[k].copy_(v, non_blocking=True)
+    e1.record()
+    barrier()
+    return reps * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_layer_points_per_s(clouds=2, repeats=6, warm=1):
+def cpu_layer_points_per_s(clouds=6, repeats=4, warm=1):
     """Reference layer restated on CPU (oracle/layers.py) fwd+bwd; kNN indices from the compiled reference when shipped."""
-    import numpy as np
     import torch
     from oracle import layers as ol
     from oracle import native as on
@@ -104,20 +194,60 @@ def cpu_layer_points_per_s(clouds=2, repeats=6, warm=1):
         layer.zero_grad(); u.grad = None; p.grad = None
     t = statistics.median(ts)
     return clouds * n / t, t, {"value": clouds * n / t, "unit": "points/s", "cores": torch.get_num_threads(), "kind": "port",
-                               "sample": f"{clouds} clouds x {n} points, CRF layer fwd+bwd, median of {repeats} after {warm} warm-up "
-                                         f"(oracle/layers.py on torch CPU, {torch.get_num_threads()} threads)"}
+                               "sample": f"{clouds} clouds x {n} points (the GPU arm's step), CRF layer fwd+bwd, median of {repeats} after {warm} "
+                                         f"warm-up (oracle/layers.py on torch CPU, {torch.get_num_threads()} threads)"}
+
+
+def cpu_network_points_per_s(cfg, clouds=2, repeats=2, warm=1):
+    """Reference network restated on CPU (oracle/layers.py PointConvResNet) fwd + cross-entropy + bwd on a bounded sample."""
+    import types
+    import torch
+    import torch.nn.functional as Fn
+    from oracle import layers as ol
+    from oracle import native as on
+    from oracle import synthetic
+    torch.set_num_threads(os.cpu_count() or 1)
+    knn = (lambda s, q, k: on.ref_knn_batch(s, q, k, omp=True)) if on.have_ref_knn() else on.knn_batch
+    n, ncls = cfg["points"], cfg["classes"]
+    pos = synthetic.room_cloud(clouds, n, seed=0)
+    ms = synthetic.build_multiscale(pos, knn)
+    g = torch.Generator().manual_seed(0)
+    x = torch.cat([torch.from_numpy(pos), torch.rand(clouds, n, 3, generator=g)], -1)
+    y = torch.randint(0, ncls, (clouds * n,), generator=g)
+    torch.manual_seed(0)
+    net = ol.PointConvResNet(6, ncls).train()
+    data = types.SimpleNamespace(x=x, multiscale=ms)
+    ts = []
+    for i in range(warm + repeats):
+        t0 = time.perf_counter()
+        Fn.cross_entropy(net(data), y).backward()
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            ts.append(dt)
+        net.zero_grad()
+    t = statistics.median(ts)
+    return clouds * n / t, t, {"value": clouds * n / t, "unit": "points/s", "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": f"{clouds} clouds x {n} points, PointConvResNet fwd + CE + bwd, median of {repeats} after {warm} warm-up "
+                                         f"(oracle/layers.py on torch CPU, {torch.get_num_threads()} threads; pyramid prebuilt)"}
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     steps = max(args.steps, 1)
-    v, t, cb = cpu_layer_points_per_s(clouds=2, repeats=min(steps, 8), warm=min(max(args.warmup, 1), 2))
-    line = {"impl": "reference", "metric": "CRFConv fwd+bwd points/s (N=40960,k=16)", "value": v, "unit": "points/s", "n_gpus": args.gpus,
+    if args.config == "S1":
+        v, t, cb = cpu_layer_points_per_s(clouds=args.clouds or 6, repeats=max(2, min(steps, 6)), warm=min(max(args.warmup, 1), 2))
+        workload = (f"single ContinuousGaussianCRFConv(128,64,64,steps=1) fwd+bwd, N=40960, Nc=10240, K=16, {args.clouds or 6} clouds per step "
+                    "(the same step as the GPU arm)")
+        metric = METRIC
+    else:
+        cfg = NET_CONFIGS[args.config]
+        v, t, cb = cpu_network_points_per_s(cfg, clouds=2, repeats=max(1, min(steps, 3)), warm=1)
+        workload = f"PointConvResNet(6,{cfg['classes']},use_crf=True) fwd+CE+bwd, {cfg['name']}; CPU arm: 2 clouds per step (bounded sample)"
+        metric = "PointConvResNet fwd+bwd points/s"
+    line = {"impl": "reference", "metric": metric, "value": v, "unit": "points/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "single ContinuousGaussianCRFConv(128,64,64,steps=1) fwd+bwd, N=40960, Nc=10240, K=16; CPU arm: "
-                                   "2 clouds per step (bounded sample of the same workload)"},
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": workload, "config": args.config},
             "cpu_baseline": cb, "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -136,6 +266,41 @@ def make_inputs(torch, B, dev, seed):
     return {"pos": pos, "unary": unary, "pairwise": pair, "up_idx": up, "neighbor_idx": nbr}
 
 
+def _single_kernel_name(call):
+    """C-ABI call label of ops.profile_calls → the CUDA kernel(s) it launches (for `roofline.dominant_kernel`)."""
+    table = {"crf_step_bwd_fused": "cl::step_bwd_kernel", "crf_step_fwd[16]": "mf::step_fwd_kernel<16>", "out16_bwd": "cl::out_bwd_kernel",
+             "linear_fwd_bn[128->64]": "lin3::fwd3_kernel<64>", "linear_fwd_bn[16->64]": "lin3::fwd3_kernel<64>",
+             "linear_bwd[64<-128]": "lin3d::dgrad3_kernel<128> + lin3w::wgrad3_kernel<64>", "bn_bwd_reduce_fin[64]": "lin::bn_bwd_reduce_kernel",
+             "mid16_bwd": "cl::mid16_bwd_kernel", "lin16_fwd[64]": "cl::lin16_fwd_kernel<64>", "lin16_fwd[128]": "cl::lin16_fwd_kernel<128>",
+             "lin16_fwd[16]": "cl::lin16_fwd_kernel<16>", "in16_dgrad[64]": "cl::in16_dgrad_kernel<64>", "in16_wgrad[64]": "cl::in16_wgrad_kernel<64>"}
+    return table.get(call, call)
+
+
+def _timed(torch, dist, world, dev, step, steps, barrier):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def _ncu_traffic(name):
+    """DRAM bytes (read + write) of one step from the committed ncu capture (profiles/ncu_r02_metrics.json), or None."""
+    try:
+        met = json.load(open(os.path.join(ROOT, "profiles", "ncu_r02_metrics.json")))
+        return met.get(name)
+    except Exception:
+        return None
+
+
 def run_gpu(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -143,13 +308,16 @@ def run_gpu(args, rank, local_rank, world):
         raise RuntimeError("bench.py needs a CUDA device: crfconv_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank)          # before the first pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.config != "S1":
+        return run_gpu_network(args, rank, local_rank, world, dev, numa)
     from crfconv_b200 import ops
     from crfconv_b200.continuous_crf_conv_big import ContinuousGaussianCRFConv
     from crfconv_b200 import nearest_neighbors as nn_
 
-    B = args.clouds
+    B = args.clouds or 6
     torch.manual_seed(1234)
     layer = ContinuousGaussianCRFConv(CU, CP, CP, steps=1).to(dev).train()
     with torch.no_grad():
@@ -178,9 +346,9 @@ def run_gpu(args, rank, local_rank, world):
         s["unary"].grad = None
         s["pairwise"].grad = None
 
-    # The ~50 kernel launches of one fwd+bwd are captured ONCE per input set into a CUDA graph and replayed: with ≈1.4 ms of GPU
-    # work per step the Python/ctypes launch path (≈1.8 ms per step) would otherwise be the bottleneck.  The gradient all-reduce
-    # stays outside the graph.
+    # The kernel launches of one fwd+bwd are captured ONCE per input set into a CUDA graph and replayed: with < 1 ms of GPU work
+    # per step the Python/ctypes launch path (≈1.8 ms per step) would otherwise be the bottleneck.  The gradient all-reduce
+    # (ReduceOp.AVG: no separate scaling kernel) stays outside the graph.
     graphs, launches_per_step = [], 0
     if args.graph:
         side = torch.cuda.Stream()
@@ -230,20 +398,9 @@ def run_gpu(args, rank, local_rank, world):
             torch.cuda.synchronize()
     barrier()
     ops.COUNTERS["launches"] = 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        step(i)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms = _timed(torch, dist, world, dev, step, args.steps, barrier)
     launches = ops.COUNTERS["launches"]
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     ms_step = ms / args.steps
     value = world * B * N_POINTS / (ms_step * 1e-3)
 
@@ -311,6 +468,7 @@ def run_gpu(args, rank, local_rank, world):
             cur.synchronize()                                   # the caller reads the loss on the host every step
 
     e2e_run(3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     e2e_run(args.steps)
@@ -322,6 +480,11 @@ def run_gpu(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item())
     e2e_value = world * B * N_POINTS / (ms_e2e / args.steps * 1e-3)
+    probe = h2d_probe(torch, dev, host[0], barrier)              # every rank copies at once, no compute: the host-side ceiling
+    if world > 1:
+        t = torch.tensor([probe], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        probe = float(t.item())
 
     if rank != 0:
         if world > 1:
@@ -333,24 +496,22 @@ def run_gpu(args, rank, local_rank, world):
     prof = ops.profile_calls(lambda: eager_step(0, reduce=False), repeats=3)    # rank 0 only: no collectives from here on
     total_k = sum(v["ms"] for v in prof.values())
     top = max(prof.items(), key=lambda kv: kv[1]["ms"])
-    kernels = {k: {"ms_per_step": round(v["ms"], 4), "calls_per_step": v["calls"], "share": round(v["ms"] / total_k, 4),
+    kernels = {k: {"kernel": _single_kernel_name(k), "ms_per_step": round(v["ms"], 4), "calls_per_step": v["calls"], "share": round(v["ms"] / total_k, 4),
                    "algo_bytes_per_step": v["bytes"], "achieved_gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None}
                for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
     top_ach = top[1]["bytes"] / (top[1]["ms"] * 1e-3) / 1e9
-    traffic = None
-    try:      # DRAM bytes (read + write) per launch of the same call, from the committed `ncu --set full` capture (profiles/)
-        met = json.load(open(os.path.join(ROOT, "profiles", "ncu_r01_metrics.json")))
-        traffic = met["calls"].get(top[0], {}).get("traffic_bytes")
-    except Exception:
-        pass
-    roofline = {"kernel": top[0], "bound": "hbm", "achieved": round(top_ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": round(top_ach / peaks["hbm_gbs"], 4), "traffic": traffic, "peak_source": peak_src,
-                "share_of_step": round(top[1]["ms"] / total_k, 4),
-                "note": "achieved = algorithmic bytes of this kernel's calls in one step / their CUDA-event time"}
     step_ach = ALGO_BYTES_PER_CLOUD * B / (ms_step * 1e-3) / 1e9
-    roofline_step = {"bound": "hbm", "achieved": round(step_ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": round(step_ach / peaks["hbm_gbs"], 4), "frac_of_nominal_8TBs": round(step_ach / 8000.0, 4),
-                     "algo_bytes_per_cloud": ALGO_BYTES_PER_CLOUD, "peak_source": peak_src}
+    roofline = {"bound": "hbm", "achieved": round(step_ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": round(step_ach / peaks["hbm_gbs"], 4), "frac_of_nominal_8TBs": round(step_ach / 8000.0, 4),
+                "traffic": _ncu_traffic("step_dram_bytes"), "peak_source": peak_src,
+                "scope": f"whole layer step (fwd+bwd, {launches_per_step or '?'} kernels in one CUDA graph): SURVEY.md §8(d) algorithmic bytes "
+                         f"{ALGO_BYTES_PER_CLOUD} B per cloud x {B} clouds / CUDA-event step time",
+                "algo_bytes_per_cloud": ALGO_BYTES_PER_CLOUD,
+                "dominant_kernel": {"kernel": _single_kernel_name(top[0]), "call": top[0], "share_of_step": round(top[1]["ms"] / total_k, 4),
+                                    "achieved": round(top_ach, 1), "frac": round(top_ach / peaks["hbm_gbs"], 4), "unit": "GB/s",
+                                    "algo_bytes_per_launch": top[1]["bytes"] / max(top[1]["calls"], 1),
+                                    "traffic": _ncu_traffic(top[0]),
+                                    "note": "this kernel's own algorithmic bytes / its CUDA-event time in an eager instrumented pass"}}
 
     # ---- secondary metric of BASELINE.json: kNN queries/s (device-resident) on the same clouds
     pos = sets[0]["pos"]
@@ -364,58 +525,132 @@ def run_gpu(args, rank, local_rank, world):
     torch.cuda.synchronize()
     knn_qps = 10 * B * N_POINTS / (e0.elapsed_time(e1) * 1e-3)
 
-    # ---- secondary: the whole PointConvResNet (BASELINE configs[2]) fwd+bwd on the same clouds, replayed as one CUDA graph.
-    # Reported next to the headline, never instead of it; any failure here leaves the bench line intact.
-    network = None
-    if args.graph and world == 1:
-        try:
-            import torch.nn.functional as Fn
-            from crfconv_b200 import train_dp
-            from crfconv_b200.graphs import GraphedStep
-            from crfconv_b200.point_conv_big import PointConvResNet
-            net = PointConvResNet(6, 13).to(dev).train()
-            ngr = FlatGradients(net)
-            npos, nfeat, nlab, ngen = train_dp.synthetic_shard(B, N_POINTS, 13, dev, seed=77)
-            ndata = train_dp.make_batch(npos, nfeat, nlab, generator=ngen)
-
-            def net_step():
-                ngr.zero()
-                loss = Fn.cross_entropy(net(ndata), ndata.y.reshape(-1) - 1)
-                loss.backward()
-                return loss.detach()
-
-            gs = GraphedStep(net_step)
-            for _ in range(2):
-                gs.replay()
-            torch.cuda.synchronize()
-            e0.record()
-            for _ in range(5):
-                gs.replay()
-            e1.record()
-            torch.cuda.synchronize()
-            net_ms = e0.elapsed_time(e1) / 5
-            network = {"metric": "PointConvResNet fwd+bwd points/s", "value": B * N_POINTS / (net_ms * 1e-3), "unit": "points/s", "ms_per_step": net_ms,
-                       "config": f"PointConvResNet(6, 13, use_crf=True), B={B}, N=40960, 5-level pyramid prebuilt on the device, one CUDA graph"}
-            del gs, net, ngr, ndata
-        except Exception as exc:                                     # noqa: BLE001
-            network = {"error": f"{type(exc).__name__}: {exc}"[:200]}
-
-    _, _, cb = cpu_layer_points_per_s(clouds=2, repeats=6, warm=1)
-    line = {"metric": "CRFConv fwd+bwd points/s (N=40960,k=16)", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+    _, _, cb = cpu_layer_points_per_s(clouds=B, repeats=4, warm=1)
+    line = {"metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"single ContinuousGaussianCRFConv(128,64,64,steps=1) fwd+bwd, N=40960, Nc=10240, K=16, "
                                    f"{B} clouds per GPU per step (SURVEY.md §8 S1 / BASELINE configs[0] shape on the GPU)",
-                       "clouds_per_gpu": B, "precision": "3xTF32 tensor-core contractions, fp32 elsewhere" if ops.PRECISION == 0 else "TF32",
+                       "config": "S1", "clouds_per_gpu": B, "precision": "3xTF32 tensor-core contractions, fp32 elsewhere" if ops.PRECISION == 0 else "TF32",
                        "launch": "one CUDA graph per input set, replayed" if args.graph else "eager (per-kernel launches from Python)",
                        "l2": f"rotating {nsets} input sets of {in_bytes / 2**20:.0f} MiB each (> {L2_BYTES / 2**20:.0f} MiB L2)",
-                       "parallelism": f"dp{world}: clouds sharded, one NCCL all-reduce of the flat gradient" if world > 1 else "single GPU"},
+                       "parallelism": f"dp{world}: clouds sharded, one NCCL all-reduce (AVG) of the flat gradient" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_step": roofline_step, "kernels": kernels,
+                    "ms_per_step": ms_e2e / args.steps, "h2d_gbs_per_gpu": round(h2d / (ms_e2e / args.steps * 1e-3) / 1e9, 2),
+                    "h2d_probe_gbs_per_gpu": round(probe, 2), "numa": numa},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,
             "knn": {"metric": "kNN queries/s", "value": knn_qps, "unit": "queries/s", "config": f"B={B}, N=Q=40960, K=16, device-resident"},
-            "network": network,
             "cpu_baseline": cb}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_gpu_network(args, rank, local_rank, world, dev, numa):
+    """--config C3 / C4 / C5: the whole PointConvResNet fwd + cross-entropy + bwd."""
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as Fn
+    from crfconv_b200 import ops, train_dp
+    from crfconv_b200.distributed import FlatGradients
+    from crfconv_b200.graphs import GraphedStep
+    from crfconv_b200.point_conv_big import PointConvResNet
+    cfg = NET_CONFIGS[args.config]
+    B, N, ncls = args.clouds or cfg["clouds"], cfg["points"], cfg["classes"]
+    torch.manual_seed(1234)
+    net = PointConvResNet(6, ncls).to(dev).train()
+    grads = FlatGradients(net)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    pos, feat, lab, gen = train_dp.synthetic_shard(B, N, ncls, dev, seed=77 + rank)
+    data = train_dp.make_batch(pos, feat, lab, generator=gen)
+    target = (lab.reshape(-1) - 1).contiguous()
+
+    def net_step():
+        grads.zero()
+        loss = Fn.cross_entropy(net(data), target)
+        loss.backward()
+        return loss.detach()
+
+    ops.COUNTERS["launches"] = 0
+    gs = GraphedStep(net_step) if args.graph else None
+    launches_per_step = 0
+
+    def step(i):
+        if gs is not None:
+            gs.replay()
+        else:
+            net_step()
+        if world > 1:
+            grads.all_reduce()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t_w = time.perf_counter()
+    i = 0
+    while i < max(args.warmup, 3) or time.perf_counter() - t_w < 0.5:
+        step(i)
+        i += 1
+    barrier()
+    ms = _timed(torch, dist, world, dev, step, args.steps, barrier)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms / args.steps
+    value = world * B * N / (ms_step * 1e-3)
+    ops.COUNTERS["launches"] = 0
+    net_step()                                                           # one eager step: counts this package's kernel launches
+    launches_per_step = ops.COUNTERS["launches"]
+    torch.cuda.synchronize()
+
+    # ---- e2e: points, features and labels come from pinned host memory every step; the pyramid (10 kNN calls + subsampling) is
+    # built on the GPU inside the timed region; the loss is read back on the host
+    hp, hf, hl = pos.cpu().pin_memory(), feat.cpu().pin_memory(), lab.cpu().pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in (hp, hf, hl))
+    loss_host = torch.zeros(1).pin_memory()
+
+    def e2e_step(i):
+        p, f, l = hp.to(dev, non_blocking=True), hf.to(dev, non_blocking=True), hl.to(dev, non_blocking=True)
+        d = train_dp.make_batch(p, f, l, generator=gen)
+        grads.zero()
+        loss = Fn.cross_entropy(net(d), l.reshape(-1) - 1)
+        loss.backward()
+        if world > 1:
+            grads.all_reduce()
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for i in range(2):
+        e2e_step(i)
+    n_e2e = max(3, min(args.steps, 10))
+    ms_e2e = _timed(torch, dist, world, dev, e2e_step, n_e2e, barrier)
+    e2e_value = world * B * N / (ms_e2e / n_e2e * 1e-3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks, peak_src = measured_peaks()
+    A = network_algo_bytes(N, ncls)
+    ach = A * B / (ms_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(ach / peaks["hbm_gbs"], 4),
+                "traffic": _ncu_traffic(f"{args.config}_step_dram_bytes"), "peak_source": peak_src, "algo_bytes_per_cloud": A,
+                "scope": "whole network step: shape walker over 10 ResNetBBlocks + 4 CRF layers + classifier with SURVEY.md §8(d)'s formulas"}
+    _, _, cb = cpu_network_points_per_s(cfg, clouds=2, repeats=2, warm=1)
+    line = {"metric": "PointConvResNet fwd+bwd points/s", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"PointConvResNet(6,{ncls},use_crf=True,steps=1) fwd + cross-entropy + bwd, {cfg['name']}; {B} clouds per GPU per step, "
+                                   "5-level kNN pyramid (K=16, ratios 4/4/4/4/2) prebuilt on the device for `value`, rebuilt every step for `e2e`",
+                       "config": args.config, "clouds_per_gpu": B, "points": N, "classes": ncls,
+                       "launch": "one CUDA graph, replayed" if args.graph else "eager",
+                       "l2": f"working set of a step ({A * B / 2**20:.0f} MiB algorithmic) exceeds the {L2_BYTES / 2**20:.0f} MiB L2",
+                       "parallelism": f"dp{world}: clouds sharded, one NCCL all-reduce (AVG) of the flat gradient" if world > 1 else "single GPU"},
+            "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / n_e2e,
+                    "steps": n_e2e, "numa": numa, "note": "eager launches (the pyramid's shapes are data independent but its kNN workspace is rebuilt per step)"},
+            "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cb}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -426,7 +661,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--clouds", type=int, default=6, help="clouds per GPU per step")
+    ap.add_argument("--config", default="S1", choices=["S1", "C3", "C4", "C5"])
+    ap.add_argument("--clouds", type=int, default=0, help="clouds per GPU per step (default: 6 for S1/C3, 8 for C4, 2 for C5)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every kernel from Python instead of replaying CUDA graphs")
     args = ap.parse_args()
@@ -440,7 +676,7 @@ def main():
         # launched without torchrun: re-launch under torch.distributed.run, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", str(29500 + os.getpid() % 2000), os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps),
-               "--warmup", str(args.warmup), "--clouds", str(args.clouds)] + ([] if args.graph else ["--no-graph"])
+               "--warmup", str(args.warmup), "--config", args.config, "--clouds", str(args.clouds)] + ([] if args.graph else ["--no-graph"])
         sys.exit(subprocess.call(cmd))
     run_gpu(args, rank, local_rank, world)
 

@@ -279,9 +279,10 @@ class _CRFConvFusedFunction(torch.autograd.Function):
         NP = ops.fused_max_parts()
 
         # one zero-filled allocation: [tcgen05 statistics slots of out_nn and fusion_nn | 8 counters]; partial-sum scratches need no init
-        zf = ops.Flat(2 * ops.STAT_SLOTS * 2 * Co + 8, torch.float32, dev)
+        CI = ops.counter_ints()
+        zf = ops.Flat(2 * ops.STAT_SLOTS * 2 * Co + 8 * CI, torch.float32, dev)
         st_o, st_f = zf.take(ops.STAT_SLOTS * 2 * Co), zf.take(ops.STAT_SLOTS * 2 * Co)
-        cnt = zf.take(8).view(torch.int32)
+        cnt = zf.take(8 * CI).view(torch.int32).view(8, CI)
         parts = torch.empty((4, NP * 32), dtype=torch.float32, device=dev)
         s1u, s2u, s1p, s2p = (ops.BN(F, dev, alloc_stats=False) for _ in range(4))
         so, sf = ops.BN(Co, dev, st_o), ops.BN(Co, dev, st_f)
@@ -299,19 +300,19 @@ class _CRFConvFusedFunction(torch.autograd.Function):
             ops.crf_compat_fwd(cc, out=(Cm, Minv), scratch=cscr)
             join_aux.record(aux)
         with torch.cuda.stream(side):                  # unary_nn (:58)
-            ops.lin16_fwd(U, W1u, s1u, bns[0], parts[0], cnt[0:1], out=H1u)
-            ops.lin16_fwd(H1u, W2u, s2u, bns[1], parts[1], cnt[1:2], pre=s1u, pslope=sl[0], out=H2u)
+            ops.lin16_fwd(U, W1u, s1u, bns[0], parts[0], cnt[0], out=H1u)
+            ops.lin16_fwd(H1u, W2u, s2u, bns[1], parts[1], cnt[1], pre=s1u, pslope=sl[0], out=H2u)
             join.record(side)
-        ops.lin16_fwd(P, W1p, s1p, bns[2], parts[2], cnt[2:3], out=H1p)          # pairwise_nn (:59)
-        ops.lin16_fwd(H1p, W2p, s2p, bns[3], parts[3], cnt[3:4], pre=s1p, pslope=sl[2], out=H2p)
+        ops.lin16_fwd(P, W1p, s1p, bns[2], parts[2], cnt[2], out=H1p)          # pairwise_nn (:59)
+        ops.lin16_fwd(H1p, W2p, s2p, bns[3], parts[3], cnt[3], pre=s1p, pslope=sl[2], out=H2p)
         main.wait_event(join)
         main.wait_event(join_aux)
         z = ops.crf_upsample_fwd(H2u, s2u, up, B, N, Nc)                          # (:60)
         xs = [z]
         for _ in range(steps):                                                    # (:68-72)
             xs.append(ops.crf_step_fwd(H2p, s2p.scale, z, xs[-1], nbr, Cm, Minv, B, N, K))
-        H3 = ops.linear_fwd_bn(xs[-1], Wo, so, bns[4], cnt[4:5])                  # out_nn (:74)
-        Hf = ops.linear_fwd_bn(H3, Wf, sf, bns[5], cnt[5:6], scale1=so.scale, shift1=so.shift, slope1=sl[4], X2=P)   # fusion_nn (:76)
+        H3 = ops.linear_fwd_bn(xs[-1], Wo, so, bns[4], cnt[4])                  # out_nn (:74)
+        Hf = ops.linear_fwd_bn(H3, Wf, sf, bns[5], cnt[5], scale1=so.scale, shift1=so.shift, slope1=sl[4], X2=P)   # fusion_nn (:76)
         out = ops.bn_act_fwd(Hf, sf, sl[5])
         nbt = [b.num_batches_tracked for b in bns if b.track_running_stats and b.num_batches_tracked is not None]
         if nbt:
@@ -342,13 +343,14 @@ class _CRFConvFusedFunction(torch.autograd.Function):
         n_out = ops.out_bwd_part_floats()
         n_big = (steps + 1) * M * F + Mc * F
         # ONE zero-filled allocation: [small grads | weight-grad partial slots | fusion BN Σ slots | out_nn partials | y sums | counters | scatter targets]
-        flat = ops.Flat(n_small * (1 + ops.GRAD_SLOTS) + ops.STAT_SLOTS * 2 * Co + n_out + 128 + 8 + n_big, torch.float32, dev)
+        CI = ops.counter_ints()
+        flat = ops.Flat(n_small * (1 + ops.GRAD_SLOTS) + ops.STAT_SLOTS * 2 * Co + n_out + 128 + 8 * CI + n_big, torch.float32, dev)
         small = flat.take(n_small)
         wscr = flat.take(ops.GRAD_SLOTS * n_small)
         sums_f = flat.take(ops.STAT_SLOTS * 2 * Co)
         out_part = flat.take(n_out)
         ysum = flat.take(128)
-        cnt = flat.take(8).view(torch.int32)
+        cnt = flat.take(8 * CI).view(torch.int32).view(8, CI)
         big = ops.Flat.__new__(ops.Flat); big.buf, big.off = flat.take(n_big), 0
         parts = torch.empty((3, NP * 32), dtype=torch.float32, device=dev)
         cursor = [0]
@@ -369,13 +371,13 @@ class _CRFConvFusedFunction(torch.autograd.Function):
         dg = {k: take_small(n) for k, n in cl}
         db = {k: take_small(n) for k, n in cl}
         # fusion_nn (:76): BatchNorm backward sums (+ finalize), input gradients dO | dP and weight gradient on tcgen05
-        ops.bn_backward_prepare_fin(g2, Hf, sf, sl[5], dg["f"], db["f"], sums_f, cnt[0:1])
+        ops.bn_backward_prepare_fin(g2, Hf, sf, sl[5], dg["f"], db["f"], sums_f, cnt[0])
         dO = torch.empty((M, Co), dtype=torch.float32, device=dev)
         dP = torch.empty((M, Cp), dtype=torch.float32, device=dev)
         ops.linear_bwd(g2, Hf, sf, sl[5], H3, Wf, scale1=so.scale, shift1=so.shift, slope1=sl[4], X2=P, dX1=dO, dX2=dP, dW=dW["f"], scratch=scr(dW["f"]), scratch_stride=n_small)
         # out_nn (:74) in one pass over dO
         Q, a0 = torch.empty((F, F), dtype=torch.float32, device=dev), torch.empty(F, dtype=torch.float32, device=dev)
-        T = ops.out16_bwd(dO, H3, so, sl[4], xs[-1], Wo, out_part, cnt[1:2], dg["o"], db["o"], dW["o"], Q, a0)
+        T = ops.out16_bwd(dO, H3, so, sl[4], xs[-1], Wo, out_part, cnt[1], dg["o"], db["o"], dW["o"], Q, a0)
         # mean-field steps, last to first (:68-72)
         Gy = big.take(M, F)
         Gz = torch.empty((M, F), dtype=torch.float32, device=dev)
@@ -385,7 +387,7 @@ class _CRFConvFusedFunction(torch.autograd.Function):
             first = t == steps
             ops.crf_step_bwd_fused(H2p, s2p, z, xs[t - 1], nbr, Cm, Minv, g, xs[-1] if first else None, Q if first else None,
                                    a0 if first else None, Gz, not first, gprev, Gy, scr(GC), scr(GM), n_small, ysum, B, N, K,
-                                   t == 1, cnt[2:3], ctx.gamma_y, dg["2p"], db["2p"])
+                                   t == 1, cnt[2], ctx.gamma_y, dg["2p"], db["2p"])
             g = gprev
         ops.grad_slots_reduce(wscr, small, 2 * F * F, n_small)    # fold the GC / GM partial slots
         Gc = take_small(F, F)
@@ -399,7 +401,7 @@ class _CRFConvFusedFunction(torch.autograd.Function):
             ops.crf_compat_bwd(cc, Minv, GC, GM, Gc, scratch=bscr)
             join_aux.record(aux)
         Gu = big.take(Mc, F)
-        ops.crf_upsample_bwd_fused(Gz, g, up, H2u, s2u, Gu, B, N, Nc, parts[0], cnt[3:4], dg["2u"], db["2u"])   # dL/dz = Σ_t h^t + g^0
+        ops.crf_upsample_bwd_fused(Gz, g, up, H2u, s2u, Gu, B, N, Nc, parts[0], cnt[3], dg["2u"], db["2u"])   # dL/dz = Σ_t h^t + g^0
         need_u, need_p = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         dV1u = torch.empty((Mc, F), dtype=torch.float32, device=dev)
         dV1p = torch.empty((M, F), dtype=torch.float32, device=dev)
@@ -409,13 +411,13 @@ class _CRFConvFusedFunction(torch.autograd.Function):
         fork.record(main)
         side.wait_event(fork)
         with torch.cuda.stream(side):                            # unary_nn
-            ops.mid16_bwd(Gu, H2u, s2u, H1u, s1u, sl[0], W2u, scr(dW["2u"]), n_small, parts[1], cnt[4:5], dg["1u"], db["1u"], out=dV1u)
+            ops.mid16_bwd(Gu, H2u, s2u, H1u, s1u, sl[0], W2u, scr(dW["2u"]), n_small, parts[1], cnt[4], dg["1u"], db["1u"], out=dV1u)
             ops.in16_wgrad(dV1u, H1u, s1u, U, scr(dW["1u"]), n_small)
             if need_u:
                 ops.in16_dgrad(dV1u, H1u, s1u, W1u, dU, False)
             join.record(side)
         # pairwise_nn (its input gradient accumulates onto the fusion_nn branch)
-        ops.mid16_bwd(Gy, H2p, s2p, H1p, s1p, sl[2], W2p, scr(dW["2p"]), n_small, parts[2], cnt[5:6], dg["1p"], db["1p"], out=dV1p)
+        ops.mid16_bwd(Gy, H2p, s2p, H1p, s1p, sl[2], W2p, scr(dW["2p"]), n_small, parts[2], cnt[5], dg["1p"], db["1p"], out=dV1p)
         fork3.record(main)
         third.wait_event(fork3)
         with torch.cuda.stream(third):

@@ -656,7 +656,6 @@ __global__ void __launch_bounds__(kThreads, 1) out_bwd_kernel(const OutBwdArgs a
         for (int b = 0; b < 16; ++b) wxx = fmaf(__ldg(a.W3 + ch * 16 + b), Sxx[b * 16 + xc], wxx);
         a.dW3[i] += s_sc[ch] * (S[i] - f_k1[ch] * Sx[xc] - f_c2[ch] * (wxx - s_mu[ch] * Sx[xc]));
     }
-    if (tid == 0) *a.counter = 0u;
 }
 
 // =========================================================================================== mean-field backward, fused
@@ -881,7 +880,6 @@ __global__ void __launch_bounds__(128, MINB) step_bwd_kernel(const StepBwdArgs a
         if (a.dgamma) a.dgamma[tid] += (float)s2;
         (void)a.dbeta;                                         // dβ += 0
     }
-    if (tid == 0) *a.counter = 0u;
 }
 
 // =========================================================================================== upsample backward + BN sums
@@ -943,7 +941,8 @@ using namespace crf::cl;
 
 extern "C" {
 
-int crfconv_fused_max_parts(void) { return kNumSMs * 4; }
+int crfconv_fused_max_parts(void) { return kMaxTicketGrid; }
+int crfconv_fused_counter_ints(void) { return kTicketInts; }
 
 int crfconv_fused_tune(int key, int value) {
     if (key < 0 || key >= 8) return -1;
@@ -1076,7 +1075,7 @@ int crfconv_crf_upsample_bwd_fused(const float* Gz, const float* G0, const int64
     UpBwdArgs a{};
     a.Gz = Gz; a.G0 = G0; a.up = up_idx; a.Hu = Hu; a.mu = mu; a.is = is; a.Gu = Gu; a.total = B * N; a.N = N; a.Nc = Nc;
     a.fin = BwdFin{part, counter, (double)(B * Nc), k1, k2, dgamma, dbeta};
-    upsample_bwd_kernel<<<grid_for(a.total * 4, kThreads * 4, 4), kThreads, 0, (cudaStream_t)stream>>>(a);
+    upsample_bwd_kernel<<<grid_for(a.total * 4, kThreads * 4, 3), kThreads, 0, (cudaStream_t)stream>>>(a);
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }

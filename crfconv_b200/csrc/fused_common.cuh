@@ -18,7 +18,7 @@ namespace cl {
 // ------------------------------------------------------------------------------------------------ BatchNorm finalize blocks
 struct FwdFin {                 // forward, training mode (batch statistics).  part == nullptr ⇒ disabled
     float* part;                // [nparts][2C] partial Σ | Σ²
-    unsigned int* counter;      // zero on entry; the finishing CTA resets it
+    unsigned int* counter;      // kTicketInts zeroed uint32 (arrive_is_last); left zero
     const float* gamma; const float* beta;   // may be null (1 / 0)
     float* running_mean; float* running_var; // may be null
     float eps, momentum;
@@ -36,13 +36,29 @@ struct BwdFin {                 // backward: s1 = Σ dV, s2 = Σ dV·Ĥ.  part =
 
 // Every thread of the CTA calls this after its partial results are written to global memory.  Returns true in exactly one CTA
 // of the grid: the one that arrives last, at which point all partials of all CTAs are visible to it.
-__device__ __forceinline__ bool arrive_is_last(unsigned int* counter) {
-    __shared__ unsigned int s_ticket;
+// Tickets are two-level: same-address atomics serialise at ≈40 ns each in L2, and the CTAs of a persistent grid all finish within
+// a microsecond of each other — a single counter turned every kernel's tail into (#CTAs × 40 ns) ≈ 6-50 us.  CTAs draw a ticket
+// from the counter of their group of 16; the last of each group draws one from the second-level counter: ≤ 16 + 32 serialised
+// atomics.  `counters` = kTicketInts zeroed uint32 (left zero); gridDim.x ≤ 16·(kTicketInts − 1).
+constexpr int kTicketInts = 40;
+constexpr int kMaxTicketGrid = 16 * (kTicketInts - 1);
+__device__ __forceinline__ bool arrive_is_last(unsigned int* counters) {
+    __shared__ unsigned int s_last;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_ticket = atomicAdd(counter, 1u);
+    if (threadIdx.x == 0) {
+        const unsigned grp = blockIdx.x >> 4, ngrp = (gridDim.x + 15) >> 4;
+        const unsigned in_grp = min(16u, gridDim.x - (grp << 4));
+        unsigned last = 0;
+        if (atomicAdd(counters + 1 + grp, 1u) == in_grp - 1) {
+            counters[1 + grp] = 0u;                              // nobody else touches this counter again in this launch
+            __threadfence();
+            if (atomicAdd(counters, 1u) == ngrp - 1) { counters[0] = 0u; last = 1u; }
+        }
+        s_last = last;
+    }
     __syncthreads();
-    const bool last = s_ticket == gridDim.x - 1;
+    const bool last = s_last != 0u;
     if (last) __threadfence();
     return last;
 }
@@ -115,14 +131,12 @@ __device__ __forceinline__ void fwd_fin_tail(const FwdFin& f, int nparts, double
     if (!arrive_is_last(f.counter)) return;
     sum_parts<2 * C, NT>(f.part, nparts, red);
     if (threadIdx.x < C) bn_fwd_finalize(f, red[threadIdx.x], red[C + threadIdx.x], threadIdx.x);
-    if (threadIdx.x == 0) *f.counter = 0u;
 }
 template <int C, int NT>
 __device__ __forceinline__ void bwd_fin_tail(const BwdFin& f, int nparts, double* red) {
     if (!arrive_is_last(f.counter)) return;
     sum_parts<2 * C, NT>(f.part, nparts, red);
     if (threadIdx.x < C) bn_bwd_finalize(f, red[threadIdx.x], red[C + threadIdx.x], threadIdx.x);
-    if (threadIdx.x == 0) *f.counter = 0u;
 }
 
 // ------------------------------------------------------------------------------------------------ 3xTF32 mma.sync helpers

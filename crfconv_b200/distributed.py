@@ -48,13 +48,17 @@ class FlatGradients:
                  fused CRF layer returns views of a single flat allocation — that storage is all-reduced in place; otherwise
                  they are packed with one foreach-copy, reduced and copied back."""
 
-    def __init__(self, module: torch.nn.Module, bind: bool = True):
+    def __init__(self, module: torch.nn.Module, bind: bool = True, extra: int = 0):
         self.params = [p for p in module.parameters() if p.requires_grad]
         if not self.params:
             raise ValueError("module has no trainable parameters")
         self.bind = bind
         dev = self.params[0].device
-        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
+        self.numel = sum(p.numel() for p in self.params)
+        # `extra` trailing floats travel with the gradients in the same collective (e.g. the local loss normaliser, so that a
+        # class-weighted / ignore_index cross-entropy is normalised by the GLOBAL weight sum like the reference's single-process batch)
+        self.flat = torch.zeros(self.numel + extra, dtype=torch.float32, device=dev)
+        self.extra = self.flat[self.numel:]
         if bind:
             self._bind()
 
@@ -83,29 +87,32 @@ class FlatGradients:
             return None
         lo = min(g.storage_offset() for g in gs)
         hi = max(g.storage_offset() + g.numel() for g in gs)
-        if hi - lo > 4 * sum(g.numel() for g in gs):                 # mostly foreign data in between: pack instead
+        if hi - lo != sum(g.numel() for g in gs):                    # the views must tile the span exactly: nothing foreign is reduced / scaled
             return None
         return torch.as_strided(gs[0], (hi - lo,), (1,), lo)
 
     def all_reduce(self, average: bool = True):
-        """Sums the gradients over the ranks with ONE collective; divides by world size if `average`."""
+        """Sums the gradients over the ranks with ONE collective; divides by world size if `average` (NCCL: folded into the
+        collective as ReduceOp.AVG — no separate scaling kernel on the step)."""
         world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         if world == 1:
             return self.flat if self.bind else None
+        avg_op = average and dist.get_backend() == "nccl"
+        op = dist.ReduceOp.AVG if avg_op else dist.ReduceOp.SUM
         if self.bind:
             buf = self.flat
         else:
             buf = self._shared_span()
             if buf is None:
-                gs = [p.grad.reshape(-1) for p in self.params]
-                torch._foreach_copy_(list(self.flat.split([g.numel() for g in gs])), gs)
-                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-                if average:
+                chunks = list(self.flat[:self.numel].split([p.numel() for p in self.params]))
+                torch._foreach_copy_([c.view_as(p.grad) for c, p in zip(chunks, self.params)], [p.grad for p in self.params])
+                dist.all_reduce(self.flat, op=op)
+                if average and not avg_op:
                     self.flat.div_(world)
-                torch._foreach_copy_(gs, list(self.flat.split([g.numel() for g in gs])))
+                torch._foreach_copy_([p.grad for p in self.params], [c.view_as(p.grad) for c, p in zip(chunks, self.params)])
                 return self.flat
-        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
-        if average:
+        dist.all_reduce(buf, op=op)
+        if average and not avg_op:
             buf.div_(world)
         return buf
 

@@ -25,17 +25,13 @@ def _is_cuda_tensor(x):
     return hasattr(x, "is_cuda") and x.is_cuda
 
 
-_ws_cache = {}
-
-
 def _workspace(nbytes, device):
+    """Scratch for one kNN / grid-subsampling call.  Allocated per call from torch's caching allocator, which is stream-ordered:
+    a block is only handed out again to work queued behind its previous use on the same stream, calls on different streams
+    (a prefetch stream building the next pyramid, a CUDA-graph capture with its private pool) never share cell tables, and the
+    allocator recycles the block without a cudaMalloc."""
     import torch
-    key = (device.index if device.index is not None else torch.cuda.current_device())
-    buf = _ws_cache.get(key)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
-        _ws_cache[key] = buf
-    return buf
+    return torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
 
 
 def knn_batch_cuda(pts, queries, K):

@@ -344,6 +344,11 @@ def fused_max_parts():
     return int(_lib.lib().crfconv_fused_max_parts())
 
 
+def counter_ints():
+    """uint32 per `counter` argument of the fused kernels (two-level arrival tickets); zeroed by the caller, left zero."""
+    return int(_lib.lib().crfconv_fused_counter_ints())
+
+
 def out_bwd_part_floats():
     return int(_lib.lib().crfconv_out_bwd_part_floats())
 

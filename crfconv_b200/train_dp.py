@@ -32,16 +32,33 @@ def make_batch(pos, feats, labels, generator=None):
 
 
 def train_step(model, grads: FlatGradients, optimizer, data, class_weights=None, ignore_index=-1, world_size=1):
-    """One optimisation step on this rank's shard; returns the local loss (a CUDA scalar, no host sync)."""
+    """One optimisation step on this rank's shard; returns the local loss (a CUDA scalar, no host sync).
+
+    The reference's loss is a class-weighted mean over the non-ignored points of the WHOLE batch (trainval.py:100-104).  With the
+    batch sharded, each rank back-propagates the weighted SUM over its shard; its normaliser (Σ of the class weights of its
+    non-ignored points) rides in the trailing slot of the flat gradient buffer, so the one all-reduce yields both the summed
+    gradient and the global normaliser — uneven shards, ignore_index and class weights all reproduce the single-process gradient."""
     grads.zero()
     y_pred = model(data)
     y_target = data.y.reshape(-1) - 1                                    # trainval.py:100
-    loss = F.cross_entropy(y_pred, y_target, weight=class_weights, ignore_index=ignore_index)
-    loss.backward()
-    if world_size > 1:
-        grads.all_reduce()                                               # the only collective of the step
+    loss_sum = F.cross_entropy(y_pred, y_target, weight=class_weights, ignore_index=ignore_index, reduction="sum")
+    valid = y_target != ignore_index
+    if class_weights is not None:
+        norm = (class_weights[y_target.clamp(min=0)] * valid).sum()
+    else:
+        norm = valid.sum().to(torch.float32)
+    loss_sum.backward()
+    if world_size > 1 and grads.extra.numel():
+        grads.extra[0] = norm
+        grads.all_reduce(average=False)                                  # the only collective of the step
+        grads.flat[:grads.numel].div_(grads.extra[0].clamp(min=1e-12))
+    else:
+        if world_size > 1:
+            grads.all_reduce(average=False)
+            norm = norm * world_size                                     # equal shards assumed when no normaliser slot was reserved
+        grads.flat[:grads.numel].div_(norm.clamp(min=1e-12))
     optimizer.step()
-    return loss.detach()
+    return (loss_sum / norm.clamp(min=1e-12)).detach()
 
 
 def synthetic_shard(clouds, points, n_classes, device, seed):
@@ -63,6 +80,7 @@ def main(argv=None):
     ap.add_argument("--momentum", type=float, default=0.98)
     ap.add_argument("--weight-decay", type=float, default=1e-4)
     ap.add_argument("--gamma", type=float, default=0.95)
+    ap.add_argument("--epoch-steps", type=int, default=500, help="optimisation steps per epoch: ExponentialLR steps once per epoch (trainval.py)")
     ap.add_argument("--checkpoint", default="")
     args = ap.parse_args(argv)
 
@@ -70,7 +88,7 @@ def main(argv=None):
     dev = torch.device("cuda", local_rank)
     torch.manual_seed(0)                                                 # identical initial weights on every rank
     model = PointConvResNet(in_channels=6, n_classes=args.classes, use_crf=True, steps=1).to(dev).train()
-    grads = FlatGradients(model)
+    grads = FlatGradients(model, extra=1)
     opt = torch.optim.SGD(model.parameters(), lr=args.lr, momentum=args.momentum, weight_decay=args.weight_decay)
     sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=args.gamma)
     pos, feats, labels, gen = synthetic_shard(args.clouds_per_gpu, args.points, args.classes, dev, seed=1000 + rank)
@@ -81,7 +99,8 @@ def main(argv=None):
         if step == 0:
             torch.cuda.synchronize(dev)
             t0 = time.time()                                             # first step pays for lazy initialisation
-    sched.step()
+        if (step + 1) % args.epoch_steps == 0:
+            sched.step()                                                 # once per epoch, like the reference's Trainer
     torch.cuda.synchronize(dev)
     dt = (time.time() - t0) / max(args.steps - 1, 1)
     if world > 1:

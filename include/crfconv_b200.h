@@ -149,11 +149,12 @@ int crfconv_crf_step_bwd(const float* Hy, const float* scale_y, const float* z, 
  * boundaries so that each boundary costs ONE streaming pass: the BatchNorm bookkeeping (crfconv_bn_finalize_fwd / _bwd) runs in
  * the tail of the producing kernel (last CTA to finish), the backward sums of the NEXT BatchNorm are emitted by the kernel that
  * produces its upstream gradient, and out_nn's backward (:74) collapses to a per-point affine map (see csrc/crf_fused.cu).
- * `part` scratches hold per-CTA partial sums (no initialisation needed unless stated); every `counter` is one zeroed uint32
- * that the kernel leaves zero.  Weight gradients go to CRFCONV_GRAD_SLOTS zero-initialised partial slots (slot_stride floats
+ * `part` scratches hold per-CTA partial sums (no initialisation needed unless stated); every `counter` points at
+ * crfconv_fused_counter_ints() zeroed uint32 (two-level arrival tickets) that the kernel leaves zero.  Weight gradients go to CRFCONV_GRAD_SLOTS zero-initialised partial slots (slot_stride floats
  * apart) that crfconv_grad_slots_reduce folds. */
 
 int crfconv_fused_max_parts(void);        /* rows of a `part` scratch: part = max_parts · 32 floats */
+int crfconv_fused_counter_ints(void);     /* uint32 per `counter` argument */
 int crfconv_out_bwd_part_floats(void);    /* floats of crfconv_out16_bwd's `part` (zero-initialised) */
 /* Tuning knobs for experiments (key 0: CTAs/SM of the mean-field backward, 2 or 3).  Returns the previous value. */
 int crfconv_fused_tune(int key, int value);

@@ -34,7 +34,7 @@ def _bn_state(ops, C, H64, gamma, beta, eps=1e-5):
 
 
 def _scratch(ops, dev):
-    return torch.empty(ops.fused_max_parts() * 32, device=dev), torch.zeros(1, dtype=torch.int32, device=dev)
+    return torch.empty(ops.fused_max_parts() * 32, device=dev), torch.zeros(ops.counter_ints(), dtype=torch.int32, device=dev)
 
 
 @pytest.mark.parametrize("M,Cin,pro", [(5003, 64, False), (40960, 64, False), (2571, 128, False), (30001, 16, True), (7, 16, True)])
@@ -70,7 +70,7 @@ def test_lin16_fwd(M, Cin, pro):
                 "running_mean": _rel(bnm.running_mean, 0.9 * rm0 + 0.1 * mu),
                 "running_var": _rel(bnm.running_var, 0.9 * rv0 + 0.1 * (var * M / max(M - 1, 1)))}
         _check(errs)
-        assert int(cnt.item()) == 0
+        assert int(cnt.abs().sum().item()) == 0
 
 
 @pytest.mark.parametrize("M,C1,C2,Cout", [(40960, 16, 0, 64), (20000, 64, 64, 64), (9000, 64, 0, 16), (600, 16, 0, 64)])
@@ -84,7 +84,7 @@ def test_linear_fwd_bn(M, C1, C2, Cout):
     W = (torch.randn(Cout, C1 + C2, generator=g) / (C1 + C2) ** 0.5).to(dev)
     bnm = torch.nn.BatchNorm1d(Cout).to(dev)
     st = ops.BN(Cout, dev)
-    cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    cnt = torch.zeros(ops.counter_ints(), dtype=torch.int32, device=dev)
     H = ops.linear_fwd_bn(X1, W, st, bnm, cnt, X2=X2)
     A = torch.cat([X1, X2], 1).double() if C2 else X1.double()
     He = A @ W.double().T
@@ -93,7 +93,7 @@ def test_linear_fwd_bn(M, C1, C2, Cout):
     _check({"H": _rel(H, He), "mean": _rel(st.mean, mu, floor=1e-3), "invstd": _rel(st.invstd, istd), "scale": _rel(st.scale, istd),
             "shift": _rel(st.shift, -mu * istd, floor=1e-2), "running_mean": _rel(bnm.running_mean, 0.1 * mu, floor=1e-4),
             "running_var": _rel(bnm.running_var, 0.9 + 0.1 * var * M / (M - 1))})
-    assert int(cnt.item()) == 0
+    assert int(cnt.abs().sum().item()) == 0
 
 
 def test_bn_backward_prepare_fin():
@@ -105,14 +105,14 @@ def test_bn_backward_prepare_fin():
     gamma, beta = (1 + 0.2 * torch.randn(C, generator=g)).to(dev), (0.2 * torch.randn(C, generator=g)).to(dev)
     st = _bn_state(ops, C, H.double(), gamma, beta)
     sums = torch.zeros(ops.STAT_SLOTS * 2 * C, device=dev)
-    cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    cnt = torch.zeros(ops.counter_ints(), dtype=torch.int32, device=dev)
     dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
     ops.bn_backward_prepare_fin(dY, H, st, 0.1, dg, db, sums, cnt)
     pre = H.double() * st.scale.double() + st.shift.double()
     dV = torch.where(pre > 0, dY.double(), 0.1 * dY.double())
     Hh = (H.double() - st.mean.double()) * st.invstd.double()
     _check({"k1": _rel(st.k1, dV.mean(0)), "k2": _rel(st.k2, (dV * Hh).mean(0)), "dgamma": _rel(dg, (dV * Hh).sum(0)), "dbeta": _rel(db, dV.sum(0))})
-    assert int(cnt.item()) == 0
+    assert int(cnt.abs().sum().item()) == 0
 
 
 def _bn_train64(H, gamma, beta, eps=1e-5):
@@ -167,7 +167,7 @@ def test_mid16_bwd_and_in16(M):
         errs.update({"dX(+=)": _rel(dXp, dX0.double() + Xd.grad), "dX(=)": _rel(dXq, Xd.grad), "dW2": _rel(dW[:256].view(16, 16), W2d.grad),
                      "dW1": _rel(dW[256:].view(16, Cin), W1d.grad)})
         _check(errs)
-        assert int(cnt.item()) == 0
+        assert int(cnt.abs().sum().item()) == 0
 
 
 @pytest.mark.parametrize("M", [3001, 40960])
@@ -186,14 +186,14 @@ def test_out16_bwd(M):
     (o * dO.double()).sum().backward()
     bn3 = _bn_state(ops, 64, H3.detach(), gm, bt)
     part = torch.zeros(ops.out_bwd_part_floats(), device=dev)
-    cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    cnt = torch.zeros(ops.counter_ints(), dtype=torch.int32, device=dev)
     dg, db, dW3 = torch.zeros(64, device=dev), torch.zeros(64, device=dev), torch.zeros(64, 16, device=dev)
     Q, a0 = torch.empty(16, 16, device=dev), torch.empty(16, device=dev)
     T = ops.out16_bwd(dO, H3.detach().float(), bn3, 0.1, x, W3, part, cnt, dg, db, dW3, Q, a0)
     gx = T.double() - a0.double() - x.double() @ Q.double().T
     _check({"dx": _rel(gx, xd.grad), "dW3": _rel(dW3, Wd.grad), "dgamma": _rel(dg, gd.grad), "dbeta": _rel(db, bd.grad),
             "Q symmetric": _rel(Q, Q.T)})
-    assert int(cnt.item()) == 0
+    assert int(cnt.abs().sum().item()) == 0
 
 
 @pytest.mark.parametrize("B,N,corr", [(2, 1500, False), (3, 4096, True), (1, 40960, True)])
@@ -226,7 +226,7 @@ def test_step_bwd_fused_matches_the_generic_kernels(B, N, corr):
     slots = torch.zeros(ops.GRAD_SLOTS * n_small, device=dev)
     Gz1, gp1, Gy1 = torch.empty(M, F, device=dev), torch.zeros(M, F, device=dev), torch.zeros(M, F, device=dev)
     ysum = torch.zeros(128, device=dev)
-    cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    cnt = torch.zeros(ops.counter_ints(), dtype=torch.int32, device=dev)
     dg, db = torch.zeros(F, device=dev), torch.zeros(F, device=dev)
     for variant in (2, 3):
         ops._lib.lib().crfconv_fused_tune(0, variant)
@@ -239,7 +239,7 @@ def test_step_bwd_fused_matches_the_generic_kernels(B, N, corr):
         _check({"Gz": _rel(Gz1, Gz0), "gprev": _rel(gp1, gp0), "Gy": _rel(Gy1, Gy0), "GC": _rel(S[:F * F].view(F, F), GC0),
                 "GM": _rel(S[F * F:].view(F, F), GM0), "k2_y": _rel(bny.k2, s2 / M, floor=float(s2.abs().max()) / M * 1e-2),
                 "dgamma_y": _rel(dg, s2, floor=float(s2.abs().max()) * 1e-2), "k1_y": float(bny.k1.abs().max())})
-        assert int(cnt.item()) == 0
+        assert int(cnt.abs().sum().item()) == 0
     ops._lib.lib().crfconv_fused_tune(0, 2)
 
 
@@ -261,7 +261,7 @@ def test_upsample_bwd_fused():
     Hh = (Hu.double() - bnu.mean.double()) * bnu.invstd.double()
     _check({"Gu": _rel(Gu, Ge), "k1": _rel(bnu.k1, Ge.mean(0), floor=1e-3), "k2": _rel(bnu.k2, (Ge * Hh).mean(0), floor=1e-3),
             "dgamma": _rel(dg, (Ge * Hh).sum(0)), "dbeta": _rel(db, Ge.sum(0))})
-    assert int(cnt.item()) == 0
+    assert int(cnt.abs().sum().item()) == 0
 
 
 @pytest.mark.parametrize("B,N,Cu,steps", [(2, 3000, 128, 1), (1, 9000, 64, 2)])
@@ -303,4 +303,5 @@ def test_fused_layer_matches_generic_layer(B, N, Cu, steps):
             errs[k + "(l2)"] = rel_l2(a, b)
         else:
             errs[k] = _rel(res[True][k], res[False][k], floor if k.startswith("g.") else 0.0)
-    _check(errs, tol=5e-4)
+    # parameter gradients of the two paths differ by summation order only; the BatchNorm biases are sums with heavy cancellation
+    _check(errs, tol=1e-3)
