@@ -110,8 +110,63 @@ def metrics(rep, out):
               f"{m.get('lts_pct', 0):.0f} | {m.get('l1tex_pct', 0):.0f} | {m.get('issue_active_pct', 0):.0f} | {m.get('tensor_pipe_pct', 0):.0f} | {int(m.get('regs', 0))} |")
 
 
+# ---- `ncu --set full --csv --page raw --log-file x.csv` (no .ncu-rep: they exceed gpurun's 64 MiB return limit)
+CSV_KEYS = [("us", ["gpu__time_duration.sum"]), ("rd_MB", ["dram__bytes_read.sum"]), ("wr_MB", ["dram__bytes_write.sum"]),
+            ("dram%", ["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]),
+            ("L2%", ["lts__throughput.avg.pct_of_peak_sustained_elapsed"]),
+            ("L1TEX%", ["l1tex__throughput.avg.pct_of_peak_sustained_elapsed"]),
+            ("lsu_wavefronts%", ["l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"]),
+            ("issue%", ["smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_realtime.avg.pct_of_peak_sustained_elapsed"]),
+            ("tensor%", ["sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed"]),
+            ("regs", ["launch__registers_per_thread"]), ("grid", ["launch__grid_size"]),
+            ("L1 hit%", ["l1tex__t_sector_hit_rate.pct"]), ("L2 hit%", ["lts__t_sector_hit_rate.pct"])]
+
+
+def metrics_csv(path, out_json=None, skip_prefixes=("at::", "knn::")):
+    rows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))]
+    hdr, units, rows = rows[0], rows[1], rows[2:]
+
+    def col(names):
+        for n in names:
+            for i, h in enumerate(hdr):
+                if h == n or h.endswith("." + n):
+                    return i
+        return None
+    cols = [(k, col(v)) for k, v in CSV_KEYS]
+    iK = hdr.index("Kernel Name")
+    table, total_dram = [], 0.0
+    for r in rows:
+        name = short(r[iK])
+        rec = {"kernel": name}
+        for k, i in cols:
+            if i is None or r[i] in ("", "n/a"):
+                continue
+            v = float(r[i].replace(",", ""))
+            u = units[i]
+            if k == "us":
+                v = v / 1e3 if u in ("ns", "nsecond") else (v * 1e3 if u in ("ms", "msecond") else v)
+            if k in ("rd_MB", "wr_MB"):
+                v = {"byte": v / 1e6, "Kbyte": v / 1e3, "Mbyte": v, "Gbyte": v * 1e3}.get(u, v)
+            rec[k] = round(v, 2)
+        table.append(rec)
+    keep = [t for t in table if not t["kernel"].startswith(skip_prefixes)]
+    print("| kernel | " + " | ".join(k for k, _ in CSV_KEYS) + " |\n|---|" + "---|" * len(CSV_KEYS))
+    for t in keep:
+        print(f"| `{t['kernel'][:60]}` | " + " | ".join(str(t.get(k, "")) for k, _ in CSV_KEYS) + " |")
+    step = [t for t in table if not t["kernel"].startswith("knn::")]
+    tot_us = sum(t.get("us", 0) for t in keep)
+    tot_mb = sum(t.get("rd_MB", 0) + t.get("wr_MB", 0) for t in keep)
+    print(f"\nlayer kernels: {len(keep)}; summed time {tot_us:.1f} us; DRAM traffic {tot_mb:.1f} MB (read + write)")
+    if out_json:
+        json.dump({"source": f"ncu --set full --clock-control none --csv --page raw ({path})", "kernels": keep,
+                   "step_dram_bytes": round(tot_mb * 1e6), "step_sum_us": round(tot_us, 1)}, open(out_json, "w"), indent=1)
+
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
+    elif sys.argv[1] == "csv":
+        metrics_csv(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
     else:
         metrics(sys.argv[2], sys.argv[3])

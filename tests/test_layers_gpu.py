@@ -13,6 +13,7 @@ from tests._util import grad_floor, rel_err, rel_err_trimmed, rel_l2
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
+NOISE_FACTOR = 3.0     # see test_crf_layer_full_size_vs_fp64_oracle
 
 
 def _load(module, g, tag):
@@ -196,11 +197,25 @@ def test_crf_layer_full_size_vs_fp64_oracle(steps, smooth):
         assert all(v < TOL for v in mx.values()), {k: v for k, v in mx.items() if v >= TOL}
         print(f"full size T={steps} kink-free: out {e_out:.1e}, all gradients max-norm <= {max(mx.values()):.1e}")
     else:
-        l2i = {k: rel_l2(a.cpu().numpy(), b.numpy(), floor) for k, (a, b) in ins.items()}
-        l2p = {k: rel_l2(a.cpu().numpy(), b.numpy(), floor) for k, (a, b) in par.items()}
-        assert all(v < TOL for v in l2i.values()), l2i
-        assert all(v < 1e-2 for v in l2p.values()), {k: v for k, v in l2p.items() if v >= 1e-2}
-        print(f"full size T={steps}: out {e_out:.1e}, input grads L2 {max(l2i.values()):.1e}, param grads L2 {max(l2p.values()):.1e}")
+        # Bounds anchored on the reference arithmetic's own noise: the SAME oracle run in float32 on the CPU is compared with the
+        # float64 truth, tensor by tensor; the product must be within NOISE_FACTOR x that error, or within the strict 1e-3 bar where
+        # the fp32 oracle itself is quieter than that.  (NOISE_FACTOR = 3: the product's pre-activations carry ~1e-6 relative error
+        # (3xTF32 products, fp32 statistics) against ~3e-7 for the oracle's fp32 FMA chains, hence proportionally more kink flips.)
+        m32 = ol.ContinuousGaussianCRFConv(128, 64, 64, steps=steps)
+        m32.load_state_dict({k: v.float() for k, v in mo.state_dict().items()})
+        m32 = m32.train()
+        u2, p2 = inp.unary.clone().requires_grad_(True), inp.pairwise.clone().requires_grad_(True)
+        o2 = m32(u2, p2, inp.up_idx, inp.neighbor_idx)
+        (o2 * cot).sum().backward()
+        p32 = dict(m32.named_parameters())
+        noise = {"d_unary": rel_l2(u2.grad.numpy(), u0.grad.numpy(), floor), "d_pairwise": rel_l2(p2.grad.numpy(), p0.grad.numpy(), floor)}
+        noise.update({n: rel_l2(p32[n].grad.numpy(), po[n].grad.numpy(), floor) for n in po})
+        l2 = {k: rel_l2(a.cpu().numpy(), b.numpy(), floor) for k, (a, b) in {**ins, **par}.items()}
+        bad = {k: (v, noise[k]) for k, v in l2.items() if not v < max(TOL, NOISE_FACTOR * noise[k])}
+        assert not bad, f"(product error, fp32-oracle error) vs the float64 oracle: {bad}"
+        worst = max(l2, key=lambda k: l2[k] / max(noise[k], 1e-12))
+        print(f"full size T={steps}: out {e_out:.1e}; gradients L2 vs fp64: product max {max(l2.values()):.1e}, fp32 oracle max {max(noise.values()):.1e}, "
+              f"worst ratio {l2[worst] / max(noise[worst], 1e-12):.2f} ({worst})")
 
 
 # ------------------------------------------------------------------------------ ResNet blocks, Upsampling, full network
@@ -261,23 +276,38 @@ def test_full_network_vs_reference_golden(golden):
     net = PointConvResNet(6, 13, use_crf=True, steps=1)
     _perturb(net, 43)
     net.classifier[1].p = 0.0
-    net = net.cuda().train()
     for lvl in ms:
         for k in ("pos", "neighbor_idx", "sub_idx", "up_idx"):
             setattr(lvl, k, getattr(lvl, k).cuda())
     data = types.SimpleNamespace(x=torch.from_numpy(g["x"]).cuda(), multiscale=ms)
+    # float64 truth (the oracle restatement with the same weights) — the yardstick for BOTH the reference's fp32 golden vectors and
+    # the product: every bound below is NOISE_FACTOR x the reference's own distance from the truth (or the strict 1e-3 bar if larger)
+    onet = ol.PointConvResNet(6, 13, use_crf=True, steps=1)
+    onet.load_state_dict(net.state_dict())
+    onet.classifier[1].p = 0.0
+    onet = onet.double().train()
+    cpu_ms = synthetic.build_multiscale(g["pos"], lambda s, q, k: nearest_neighbors.knn_batch(s, q, k, omp=True), num_scales=5, K=16, seed=41)
+    lo = onet(types.SimpleNamespace(x=torch.from_numpy(g["x"]).double(), multiscale=[
+        types.SimpleNamespace(pos=l.pos.double(), neighbor_idx=l.neighbor_idx, sub_idx=l.sub_idx, up_idx=l.up_idx) for l in cpu_ms]))
+    torch.nn.functional.cross_entropy(lo, torch.from_numpy(g["y"])).backward()
+    truth = {n: p.grad.numpy() for n, p in onet.named_parameters()}
+    net = net.cuda().train()
     logits = net(data)
     loss = torch.nn.functional.cross_entropy(logits, torch.from_numpy(g["y"]).cuda())
     loss.backward()
-    assert rel_err(logits.detach().cpu().numpy(), g["logits"]) < 5e-3       # 14 stacked BN'd blocks; measured ~1e-4
+    lt = lo.detach().numpy()
+    e_log, n_log = rel_err(logits.detach().cpu().numpy(), lt), rel_err(g["logits"], lt)
+    assert e_log < max(TOL, NOISE_FACTOR * n_log), (e_log, n_log)
+    assert rel_err(logits.detach().cpu().numpy(), g["logits"]) < max(TOL, (1 + NOISE_FACTOR) * n_log)
     assert abs(float(loss) - float(g["loss"])) < 1e-3 * abs(float(g["loss"]))
     params = dict(net.named_parameters())
-    errs = {k[2:]: rel_l2(params[k[2:]].grad.cpu().numpy(), v) for k, v in g.items() if k.startswith("g.")}
-    # With the reference's LeakyReLU slopes the parameter gradients of a 14-block network carry kink-flip noise (a branch
-    # decided differently where |pre-activation| is within rounding of 0; ~20M activations here): ~1-2e-2 in relative L2.
-    # The arithmetic itself is checked to 1e-3 max-norm by the kink-free test below.
-    assert all(v < 5e-2 for v in errs.values()), errs
-    print(f"full net: logits {rel_err(logits.detach().cpu().numpy(), g['logits']):.1e}, loss {float(loss):.6f} vs {float(g['loss']):.6f}, grads L2 max {max(errs.values()):.1e}")
+    floor = 1e-2 * max(float(np.abs(v).max()) for v in truth.values())
+    errs = {k[2:]: rel_l2(params[k[2:]].grad.cpu().numpy(), truth[k[2:]], floor) for k in g if k.startswith("g.")}
+    noise = {k[2:]: rel_l2(v, truth[k[2:]], floor) for k, v in g.items() if k.startswith("g.")}
+    bad = {k: (v, noise[k]) for k, v in errs.items() if not v < max(TOL, NOISE_FACTOR * noise[k])}
+    assert not bad, f"(product error, reference fp32 golden error) vs the float64 oracle: {bad}"
+    print(f"full net: logits {e_log:.1e} (reference golden {n_log:.1e}) vs fp64, loss {float(loss):.6f} vs {float(g['loss']):.6f}, "
+          f"grads L2 vs fp64: product max {max(errs.values()):.1e}, reference golden max {max(noise.values()):.1e}")
 
 
 def test_full_network_kink_free_vs_fp64_oracle():
