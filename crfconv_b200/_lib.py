@@ -41,10 +41,12 @@ SIGNATURES = {
     "crfconv_add_inplace": (_int, [_vp, _vp, _i64, _vp]),
     "crfconv_scatter_add_rows": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
     "crfconv_fused_max_parts": (_int, []),
+    "crfconv_fused_part_floats": (_int, []),
     "crfconv_fused_counter_ints": (_int, []),
     "crfconv_out_bwd_part_floats": (_int, []),
     "crfconv_fused_tune": (_int, [_int, _int]),
     "crfconv_lin16_fwd": (_int, [_vp, _int, _vp, _vp, _vp, _f32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp]),
+    "crfconv_up16_fwd": (_int, [_vp, _vp, _int, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp]),
     "crfconv_linear_fwd_bn": (_int, [_vp, _int, _vp, _vp, _f32, _vp, _int, _vp, _vp, _vp, _i64, _int, _int, _vp, _vp, _vp, _vp, _vp, _f32, _f32,
                                      _vp, _vp, _vp, _vp, _vp]),
     "crfconv_bn_bwd_reduce_fin": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -276,14 +276,14 @@ class _CRFConvFusedFunction(torch.autograd.Function):
         nbr = neighbor_idx.detach().contiguous().to(torch.int64)
         Mc, M = B * Nc, B * N
         F, Co = 16, 64
-        NP = ops.fused_max_parts()
+        NP = ops.fused_part_floats()
 
         # one zero-filled allocation: [tcgen05 statistics slots of out_nn and fusion_nn | 8 counters]; partial-sum scratches need no init
         CI = ops.counter_ints()
         zf = ops.Flat(2 * ops.STAT_SLOTS * 2 * Co + 8 * CI, torch.float32, dev)
         st_o, st_f = zf.take(ops.STAT_SLOTS * 2 * Co), zf.take(ops.STAT_SLOTS * 2 * Co)
         cnt = zf.take(8 * CI).view(torch.int32).view(8, CI)
-        parts = torch.empty((4, NP * 32), dtype=torch.float32, device=dev)
+        parts = torch.empty((4, NP), dtype=torch.float32, device=dev)
         s1u, s2u, s1p, s2p = (ops.BN(F, dev, alloc_stats=False) for _ in range(4))
         so, sf = ops.BN(Co, dev, st_o), ops.BN(Co, dev, st_f)
         H1u, H2u = torch.empty((Mc, F), dtype=torch.float32, device=dev), torch.empty((Mc, F), dtype=torch.float32, device=dev)
@@ -311,7 +311,7 @@ class _CRFConvFusedFunction(torch.autograd.Function):
         xs = [z]
         for _ in range(steps):                                                    # (:68-72)
             xs.append(ops.crf_step_fwd(H2p, s2p.scale, z, xs[-1], nbr, Cm, Minv, B, N, K))
-        H3 = ops.linear_fwd_bn(xs[-1], Wo, so, bns[4], cnt[4])                  # out_nn (:74)
+        H3 = ops.up16_fwd(xs[-1], Wo, so, bns[4], cnt[4])                       # out_nn (:74)
         Hf = ops.linear_fwd_bn(H3, Wf, sf, bns[5], cnt[5], scale1=so.scale, shift1=so.shift, slope1=sl[4], X2=P)   # fusion_nn (:76)
         out = ops.bn_act_fwd(Hf, sf, sl[5])
         nbt = [b.num_batches_tracked for b in bns if b.track_running_stats and b.num_batches_tracked is not None]
@@ -335,7 +335,7 @@ class _CRFConvFusedFunction(torch.autograd.Function):
         Mc, M = B * Nc, B * N
         z = xs[0]
         g2 = ops.as2d(gout)
-        NP = ops.fused_max_parts()
+        NP = ops.fused_part_floats()
 
         wl = (("1u", W1u), ("2u", W2u), ("1p", W1p), ("2p", W2p), ("o", Wo), ("f", Wf))
         cl = (("1u", F), ("2u", F), ("1p", F), ("2p", F), ("o", Co), ("f", Co))
@@ -352,7 +352,7 @@ class _CRFConvFusedFunction(torch.autograd.Function):
         ysum = flat.take(128)
         cnt = flat.take(8 * CI).view(torch.int32).view(8, CI)
         big = ops.Flat.__new__(ops.Flat); big.buf, big.off = flat.take(n_big), 0
-        parts = torch.empty((3, NP * 32), dtype=torch.float32, device=dev)
+        parts = torch.empty((3, NP), dtype=torch.float32, device=dev)
         cursor = [0]
 
         def take_small(*shape):
@@ -389,7 +389,6 @@ class _CRFConvFusedFunction(torch.autograd.Function):
                                    a0 if first else None, Gz, not first, gprev, Gy, scr(GC), scr(GM), n_small, ysum, B, N, K,
                                    t == 1, cnt[2], ctx.gamma_y, dg["2p"], db["2p"])
             g = gprev
-        ops.grad_slots_reduce(wscr, small, 2 * F * F, n_small)    # fold the GC / GM partial slots
         Gc = take_small(F, F)
         aux = _aux_stream(dev)
         fork_aux, join_aux = torch.cuda.Event(), torch.cuda.Event()
@@ -397,7 +396,8 @@ class _CRFConvFusedFunction(torch.autograd.Function):
         main = torch.cuda.current_stream(dev)
         fork_aux.record(main)
         aux.wait_event(fork_aux)
-        with torch.cuda.stream(aux):
+        with torch.cuda.stream(aux):                             # off the critical path: Gc is only needed when backward returns
+            ops.grad_slots_reduce(wscr, small, 2 * F * F, n_small)    # fold the GC / GM partial slots
             ops.crf_compat_bwd(cc, Minv, GC, GM, Gc, scratch=bscr)
             join_aux.record(aux)
         Gu = big.take(Mc, F)

@@ -33,6 +33,7 @@ namespace crf {
 namespace cl {
 
 constexpr int kThreads = 256, kWarps = 8;
+constexpr int kFinSlots = 16;             // statistics slots used by kernels that finalize in their own tail (<= kStatSlots; the rest stay zero)
 constexpr int kGradSlotsF = kGradSlots;   // weight-gradient partial slots shared with the generic kernels (folded by grad_slots_reduce)
 
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
@@ -156,7 +157,89 @@ __global__ void __launch_bounds__(kThreads, CIN > 64 ? 1 : 2) lin16_fwd_kernel(c
         for (int w = 0; w < kWarps; ++w) tot += s_part[w][tid];
         a.fin.part[(size_t)blockIdx.x * 32 + tid] = tot;
     }
-    fwd_fin_tail<16, kThreads>(a.fin, (int)gridDim.x, s_red);
+    if (grid_reduce_rows<32, kThreads>(a.fin.part, part_group_rows(a.fin.part), a.fin.counter, s_red) && tid < 16)
+        bn_fwd_finalize(a.fin, s_red[tid], s_red[16 + tid], tid);
+}
+
+// =========================================================================================== forward: X[M,16] → H[M,COUT]
+// out_nn's Linear (16 → 64, continuous_crf_conv_big.py:28,74): K = 16, so the pass is a pure stream of the 64-wide output.  Same
+// fragment scheme as in16_dgrad (output columns permuted so that a thread owns 4 consecutive ones ⇒ 128-bit stores); Σ/Σ² go to
+// kStatSlots zeroed slots with one atomic per CTA and column, and the last CTA finalizes the BatchNorm.
+struct Up16FwdArgs {
+    const float* X;                                           // [M, 16]
+    const float* W;                                           // [COUT, 16]
+    float* Y;                                                 // [M, COUT]
+    int64_t M;
+    FwdFin fin;                                               // fin.part = statistics slots [kStatSlots][2·COUT], zeroed
+};
+
+template <int COUT>
+__global__ void __launch_bounds__(kThreads, 2) up16_fwd_kernel(const Up16FwdArgs a) {
+    constexpr int NB = COUT / 8, NQ = COUT / 16;
+    __shared__ float2 Bh[2 * NB * 32], Bl[2 * NB * 32];        // [k8 step][n block][lane]
+    __shared__ float s_part[2 * COUT];
+    __shared__ double s_red[kThreads];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    for (int i = tid; i < 2 * NB * 32; i += kThreads) {
+        const int s = i / (NB * 32), nb = (i / 32) % NB, gg = (i & 31) >> 2, tt = i & 3;
+        const int in = 4 * tt + 2 * s, out = phys_col(nb, gg);
+        store_split(Bh, Bl, i, __ldg(a.W + out * 16 + in), __ldg(a.W + out * 16 + in + 1));
+    }
+    for (int i = tid; i < 2 * COUT; i += kThreads) s_part[i] = 0.f;
+    __syncthreads();
+    float4 ssum[NQ], ssq[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) { ssum[q] = zero4(); ssq[q] = zero4(); }
+    const int64_t ntiles = (a.M + 15) >> 4;
+    const int64_t stride = (int64_t)gridDim.x * kWarps;
+    int64_t tile = (int64_t)blockIdx.x * kWarps + warp;
+    auto load = [&](int64_t tl, float4& v0, float4& v1) {
+        const int64_t r0 = tl * 16 + g, r1 = r0 + 8;
+        v0 = r0 < a.M ? ldg4(a.X + r0 * 16 + 4 * t) : zero4();
+        v1 = r1 < a.M ? ldg4(a.X + r1 * 16 + 4 * t) : zero4();
+    };
+    float4 c0, c1;
+    load(tile, c0, c1);
+    for (; tile < ntiles; tile += stride) {
+        const int64_t r0 = tile * 16 + g, r1 = r0 + 8;
+        const bool ok0 = r0 < a.M, ok1 = r1 < a.M;
+        float4 n0, n1;
+        load(tile + stride, n0, n1);
+        FragA f0, f1;
+        make_a(f0, c0.x, c1.x, c0.y, c1.y);
+        make_a(f1, c0.z, c1.z, c0.w, c1.w);
+        float* p0 = a.Y + r0 * COUT + 4 * t;
+        float* p1 = a.Y + r1 * COUT + 4 * t;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int nb = 2 * q + e;
+                mma3(acc[e], f0, Bh[(0 * NB + nb) * 32 + lane], Bl[(0 * NB + nb) * 32 + lane]);
+                mma3(acc[e], f1, Bh[(1 * NB + nb) * 32 + lane], Bl[(1 * NB + nb) * 32 + lane]);
+            }
+            const float4 o0 = make_float4(acc[0][0], acc[0][1], acc[1][0], acc[1][1]);
+            const float4 o1 = make_float4(acc[0][2], acc[0][3], acc[1][2], acc[1][3]);
+            if (ok0) *reinterpret_cast<float4*>(p0 + 16 * q) = o0;
+            if (ok1) *reinterpret_cast<float4*>(p1 + 16 * q) = o1;
+            ssum[q] = add4(ssum[q], add4(o0, o1));             // rows beyond M are exact zeros
+            ssq[q] = fma4(o0, o0, fma4(o1, o1, ssq[q]));
+        }
+        c0 = n0; c1 = n1;
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        const float v1[4] = {ssum[q].x, ssum[q].y, ssum[q].z, ssum[q].w}, v2[4] = {ssq[q].x, ssq[q].y, ssq[q].z, ssq[q].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float x1 = group8_sum(v1[e]), x2 = group8_sum(v2[e]);
+            if (g == 0) { atomicAdd(&s_part[16 * q + 4 * t + e], x1); atomicAdd(&s_part[COUT + 16 * q + 4 * t + e], x2); }
+        }
+    }
+    __syncthreads();
+    if (tid < 2 * COUT) atomicAdd(a.fin.part + (size_t)(blockIdx.x % kFinSlots) * 2 * COUT + tid, s_part[tid]);
+    fwd_fin_tail<COUT, kThreads>(a.fin, kFinSlots, s_red);
 }
 
 // =========================================================================================== backward of a 16→16 layer
@@ -295,7 +378,8 @@ __global__ void __launch_bounds__(kThreads, 2) mid16_bwd_kernel(const Mid16BwdAr
         for (int w = 0; w < kWarps; ++w) tot += s_part[w][tid];
         a.fin.part[(size_t)blockIdx.x * 32 + tid] = tot;
     }
-    bwd_fin_tail<16, kThreads>(a.fin, (int)gridDim.x, s_red);
+    if (grid_reduce_rows<32, kThreads>(a.fin.part, part_group_rows(a.fin.part), a.fin.counter, s_red) && tid < 16)
+        bn_bwd_finalize(a.fin, s_red[tid], s_red[16 + tid], tid);
 }
 
 // =========================================================================================== first layers: dX (+)= dH1·W1
@@ -477,7 +561,16 @@ struct OutBwdArgs {
     int64_t M;
 };
 
+// Each warp streams its 16-row tiles of dO and H3 through a private double-buffered cp.async ring (the next tile's 8 KB are in
+// flight while this one is contracted; no register staging, no CTA-wide barrier).  The row-major pass turns the dO tile into dv3
+// IN PLACE in shared memory; the contraction over rows (S = dv3ᵀ·x) then reads it back transposed, conflict-free (row pitch 72).
+// Σ dv3·Ĥ3 is not accumulated per row: H3 = x·W3ᵀ, so Σ_r dv3[r,c]·H3[r,c] = Σ_a W3[c,a]·S[c,a] — the finalize derives it from S.
+constexpr int kOutPitch = 72;                                   // floats per staged row (64 + 8: bank = 8·row + col)
+constexpr int kOutStage = 2 * 16 * kOutPitch;                   // floats per stage: dO tile | H3 tile
+constexpr size_t kOutSmem = (size_t)kWarps * 2 * kOutStage * sizeof(float);
+
 __global__ void __launch_bounds__(kThreads, 1) out_bwd_kernel(const OutBwdArgs a) {
+    extern __shared__ __align__(16) float ring[];               // [warp][stage][dO | H3][16][72]
     __shared__ float2 Bh[8 * 2 * 32], Bl[8 * 2 * 32];          // t-GEMM: [k8 step over the 64 channels][n block][lane]
     __shared__ __align__(16) float s_sc[64], s_sh[64], s_mu[64], s_is[64];
     __shared__ float s_acc[kOutPart];
@@ -492,9 +585,9 @@ __global__ void __launch_bounds__(kThreads, 1) out_bwd_kernel(const OutBwdArgs a
     }
     __syncthreads();
 
-    float4 s1[4], s2[4];
+    float4 s1[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { s1[j] = zero4(); s2[j] = zero4(); }
+    for (int j = 0; j < 4; ++j) s1[j] = zero4();
     float accS[4][2][4], accXX[2][4], sx[2] = {0.f, 0.f};
 #pragma unroll
     for (int mb = 0; mb < 4; ++mb)
@@ -507,28 +600,60 @@ __global__ void __launch_bounds__(kThreads, 1) out_bwd_kernel(const OutBwdArgs a
 #pragma unroll
         for (int e = 0; e < 4; ++e) accXX[nb][e] = 0.f;
 
+    float* wring = ring + (size_t)warp * 2 * kOutStage;
     const int64_t ntiles = (a.M + 15) >> 4;
-    for (int64_t tile = (int64_t)blockIdx.x * kWarps + warp; tile < ntiles; tile += (int64_t)gridDim.x * kWarps) {
+    const int64_t stride = (int64_t)gridDim.x * kWarps;
+    auto issue = [&](int64_t tl, int st) {                     // 16 rows x 256 B of dO and of H3 → stage st (rows beyond M: zeros)
+        float* dst = wring + st * kOutStage;
+        if (tl < ntiles) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int c = lane + 32 * i, row = c >> 4, cc = c & 15;
+                const int64_t r = tl * 16 + row;
+                const bool ok = r < a.M;
+                const int64_t off = (ok ? r : 0) * 64 + 4 * cc;
+                cp_async16(dst + row * kOutPitch + 4 * cc, a.dO + off, ok);
+                cp_async16(dst + 16 * kOutPitch + row * kOutPitch + 4 * cc, a.H3 + off, ok);
+            }
+        }
+        cp_async_commit();
+    };
+    int64_t tile = (int64_t)blockIdx.x * kWarps + warp;
+    int st = 0;
+    issue(tile, 0);
+    for (; tile < ntiles; tile += stride, st ^= 1) {
+        issue(tile + stride, st ^ 1);
         const int64_t r0 = tile * 16 + g, r1 = r0 + 8;
         const bool ok0 = r0 < a.M, ok1 = r1 < a.M;
-        // ---- row-major pass: dv3, column sums, t = dv3·(sc3 ⊙ W3)
-        float4 d0[4], d1[4], h0[4], h1[4];
+        // x values for the transposed pass (global, 4-byte loads: 8 lanes = one sector) — issued before the wait
+        float xv[2][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            d0[j] = ok0 ? ldg4(a.dO + r0 * 64 + 16 * j + 4 * t) : zero4();
-            d1[j] = ok1 ? ldg4(a.dO + r1 * 64 + 16 * j + 4 * t) : zero4();
-            h0[j] = ok0 ? ldg4(a.H3 + r0 * 64 + 16 * j + 4 * t) : zero4();
-            h1[j] = ok1 ? ldg4(a.H3 + r1 * 64 + 16 * j + 4 * t) : zero4();
+        for (int ks = 0; ks < 2; ++ks) {
+            const int64_t ra = tile * 16 + 8 * ks + t, rb = ra + 4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int64_t r = (q & 2) ? rb : ra;
+                xv[ks][q] = r < a.M ? __ldg(a.X + r * 16 + g + 8 * (q & 1)) : 0.f;     // x[ra][g], x[ra][g+8], x[rb][g], x[rb][g+8]
+            }
         }
+        cp_async_wait<1>();                                    // this tile has landed (the newest group may still be in flight)
+        __syncwarp();
+        float* dOs = wring + st * kOutStage;
+        const float* H3s = dOs + 16 * kOutPitch;
+        // ---- row-major pass: dv3 (written back in place), column sums, t = dv3·(sc3 ⊙ W3)
         float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
+            float* q0 = dOs + g * kOutPitch + 16 * j + 4 * t;
+            float* q1 = q0 + 8 * kOutPitch;
+            const float4 d0 = *reinterpret_cast<const float4*>(q0), d1 = *reinterpret_cast<const float4*>(q1);
+            const float4 h0 = *reinterpret_cast<const float4*>(H3s + g * kOutPitch + 16 * j + 4 * t);
+            const float4 h1 = *reinterpret_cast<const float4*>(H3s + (g + 8) * kOutPitch + 16 * j + 4 * t);
             const float4 sc = *reinterpret_cast<const float4*>(s_sc + 16 * j + 4 * t), sh = *reinterpret_cast<const float4*>(s_sh + 16 * j + 4 * t);
-            const float4 mu = *reinterpret_cast<const float4*>(s_mu + 16 * j + 4 * t), is = *reinterpret_cast<const float4*>(s_is + 16 * j + 4 * t);
-            const float4 v0 = mask4(d0[j], fma4(h0[j], sc, sh), a.slope3), v1 = mask4(d1[j], fma4(h1[j], sc, sh), a.slope3);   // zero rows stay zero
+            const float4 v0 = mask4(d0, fma4(h0, sc, sh), a.slope3), v1 = mask4(d1, fma4(h1, sc, sh), a.slope3);   // zero rows stay zero
+            *reinterpret_cast<float4*>(q0) = v0;
+            *reinterpret_cast<float4*>(q1) = v1;
             s1[j] = add4(s1[j], add4(v0, v1));
-            s2[j] = fma4(v0, mul4(sub4(h0[j], mu), is), s2[j]);
-            s2[j] = fma4(v1, mul4(sub4(h1[j], mu), is), s2[j]);
             FragA f;
             make_a(f, v0.x, v1.x, v0.y, v1.y);
 #pragma unroll
@@ -539,53 +664,40 @@ __global__ void __launch_bounds__(kThreads, 1) out_bwd_kernel(const OutBwdArgs a
         }
         if (ok0) *reinterpret_cast<float4*>(a.T + r0 * 16 + 4 * t) = make_float4(acc[0][0], acc[0][1], acc[1][0], acc[1][1]);
         if (ok1) *reinterpret_cast<float4*>(a.T + r1 * 16 + 4 * t) = make_float4(acc[0][2], acc[0][3], acc[1][2], acc[1][3]);
-        // ---- transposed pass (k = rows): S += dv3ᵀ·x, Sxx += xᵀ·x, Sx += x      (the tile's lines are in L1 now)
+        __syncwarp();                                          // dv3 tile complete
+        // ---- transposed pass (k = rows): S += dv3ᵀ·x, Sxx += xᵀ·x, Sx += x
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
-            const int64_t ra = tile * 16 + 8 * ks + t, rb = ra + 4;
-            const bool oka = ra < a.M, okb = rb < a.M;
-            float xv[4];                                       // x[ra][g], x[ra][g+8], x[rb][g], x[rb][g+8]
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const bool ok = (q & 2) ? okb : oka;
-                xv[q] = ok ? __ldg(a.X + ((q & 2) ? rb : ra) * 16 + g + 8 * (q & 1)) : 0.f;
-            }
-            sx[0] += xv[0] + xv[2];
-            sx[1] += xv[1] + xv[3];
+            sx[0] += xv[ks][0] + xv[ks][2];
+            sx[1] += xv[ks][1] + xv[ks][3];
             FragB xb[2];
-            make_b(xb[0], xv[0], xv[2]);                       // n block 0: x-channel g      (b0 = row ra, b1 = row rb)
-            make_b(xb[1], xv[1], xv[3]);                       // n block 1: x-channel g + 8
+            make_b(xb[0], xv[ks][0], xv[ks][2]);               // n block 0: x-channel g      (b0 = row ra, b1 = row rb)
+            make_b(xb[1], xv[ks][1], xv[ks][3]);               // n block 1: x-channel g + 8
             FragA fx;
-            make_a(fx, xv[0], xv[1], xv[2], xv[3]);            // A = xᵀ: (m = g, k = ra) (m = g+8, k = ra) (g, rb) (g+8, rb)
+            make_a(fx, xv[ks][0], xv[ks][1], xv[ks][2], xv[ks][3]);   // A = xᵀ: (m = g, k = ra) (m = g+8, k = ra) (g, rb) (g+8, rb)
 #pragma unroll
             for (int nb = 0; nb < 2; ++nb) mma3(accXX[nb], fx, xb[nb]);
+            const float* ra_ = dOs + (8 * ks + t) * kOutPitch + g;
+            const float* rb_ = ra_ + 4 * kOutPitch;
 #pragma unroll
             for (int mb = 0; mb < 4; ++mb) {
-                float av[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const bool ok = (q & 2) ? okb : oka;
-                    const int ch = mb * 16 + g + 8 * (q & 1);
-                    const int64_t off = ((q & 2) ? rb : ra) * 64 + ch;
-                    const float d = ok ? __ldg(a.dO + off) : 0.f;
-                    const float h = ok ? __ldg(a.H3 + off) : 0.f;
-                    av[q] = fmaf(h, s_sc[ch], s_sh[ch]) > 0.f ? d : d * a.slope3;
-                }
-                FragA f;
-                make_a(f, av[0], av[1], av[2], av[3]);
+                FragA f;                                       // A = dv3ᵀ: (ch = 16mb+g, ra) (ch+8, ra) (ch, rb) (ch+8, rb)
+                make_a(f, ra_[16 * mb], ra_[16 * mb + 8], rb_[16 * mb], rb_[16 * mb + 8]);
 #pragma unroll
                 for (int nb = 0; nb < 2; ++nb) mma3(accS[mb][nb], f, xb[nb]);
             }
         }
+        __syncwarp();                                          // stage free for the copy issued two iterations from now
     }
+    cp_async_wait<0>();
     // ---- CTA reduction in shared memory, then one atomic per value into a slot
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const float v1[4] = {s1[j].x, s1[j].y, s1[j].z, s1[j].w}, v2[4] = {s2[j].x, s2[j].y, s2[j].z, s2[j].w};
+        const float v1[4] = {s1[j].x, s1[j].y, s1[j].z, s1[j].w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const float x1 = group8_sum(v1[e]), x2 = group8_sum(v2[e]);
-            if (g == 0) { atomicAdd(&s_acc[16 * j + 4 * t + e], x1); atomicAdd(&s_acc[64 + 16 * j + 4 * t + e], x2); }
+            const float x1 = group8_sum(v1[e]);
+            if (g == 0) atomicAdd(&s_acc[16 * j + 4 * t + e], x1);
         }
     }
 #pragma unroll
@@ -614,7 +726,8 @@ __global__ void __launch_bounds__(kThreads, 1) out_bwd_kernel(const OutBwdArgs a
     __syncthreads();
     {
         float* dst = a.part + (size_t)(blockIdx.x % kOutSlots) * kOutPart;
-        for (int i = tid; i < kOutPart; i += kThreads) atomicAdd(dst + i, s_acc[i]);
+        for (int i = tid; i < kOutPart; i += kThreads)
+            if (i < 64 || i >= 128) atomicAdd(dst + i, s_acc[i]);      // [64, 128) (Σ dv3·Ĥ3) is derived in the finalize
     }
     if (!arrive_is_last(a.counter)) return;
     // ---- finalize (one CTA): fold the slots, then the small algebra above
@@ -628,12 +741,17 @@ __global__ void __launch_bounds__(kThreads, 1) out_bwd_kernel(const OutBwdArgs a
         s_acc[i] = tot;
     }
     __syncthreads();
-    const float* S1 = s_acc; const float* S2 = s_acc + 64; const float* Sx = s_acc + 128; const float* Sxx = s_acc + 144; const float* S = s_acc + 400;
+    const float* S1 = s_acc; float* S2 = s_acc + 64; const float* Sx = s_acc + 128; const float* Sxx = s_acc + 144; const float* S = s_acc + 400;
     __shared__ float f_k1[64], f_c2[64];
     if (tid < 64) {
-        const float k1 = (float)((double)S1[tid] / a.count), k2 = (float)((double)S2[tid] / a.count);
+        float hs = 0.f;                                        // Σ_rows dv3·H3 for channel tid
+#pragma unroll
+        for (int b = 0; b < 16; ++b) hs = fmaf(__ldg(a.W3 + tid * 16 + b), S[tid * 16 + b], hs);
+        const float s2 = s_is[tid] * (hs - s_mu[tid] * S1[tid]);
+        S2[tid] = s2;
+        const float k1 = (float)((double)S1[tid] / a.count), k2 = (float)((double)s2 / a.count);
         a.k1[tid] = k1; a.k2[tid] = k2;
-        if (a.dgamma) a.dgamma[tid] += S2[tid];
+        if (a.dgamma) a.dgamma[tid] += s2;
         if (a.dbeta) a.dbeta[tid] += S1[tid];
         f_k1[tid] = k1; f_c2[tid] = s_is[tid] * k2;
     }
@@ -922,7 +1040,8 @@ __global__ void __launch_bounds__(kThreads, 4) upsample_bwd_kernel(const UpBwdAr
         for (int w = 0; w < kWarps; ++w) tot += s_part[w][tid];
         a.fin.part[(size_t)blockIdx.x * 32 + tid] = tot;
     }
-    bwd_fin_tail<16, kThreads>(a.fin, (int)gridDim.x, s_red);
+    if (grid_reduce_rows<32, kThreads>(a.fin.part, part_group_rows(a.fin.part), a.fin.counter, s_red) && tid < 16)
+        bn_bwd_finalize(a.fin, s_red[tid], s_red[16 + tid], tid);
 }
 
 static int g_tune[8] = {2, 0, 0, 0, 0, 0, 0, 0};   // [0] CTAs/SM of step_bwd
@@ -942,6 +1061,7 @@ using namespace crf::cl;
 extern "C" {
 
 int crfconv_fused_max_parts(void) { return kMaxTicketGrid; }
+int crfconv_fused_part_floats(void) { return kPartFloats; }
 int crfconv_fused_counter_ints(void) { return kTicketInts; }
 
 int crfconv_fused_tune(int key, int value) {
@@ -973,6 +1093,20 @@ int crfconv_lin16_fwd(const float* X, int Cin, const float* W, const float* psca
     } else {
         return CRF_ERR_UNSUPPORTED;
     }
+    CRF_LAUNCH_CHECK();
+    return CRF_OK;
+}
+
+// H[M,64] = X[M,16]·Wᵀ + BatchNorm finalize of H (out_nn's Linear).  stats: [CRFCONV_STAT_SLOTS][128] zeroed floats.
+int crfconv_up16_fwd(const float* X, const float* W, int Cout, float* Y, int64_t M, float* stats, unsigned int* counter, const float* gamma,
+                     const float* beta, float* running_mean, float* running_var, float eps, float momentum, float* scale, float* shift,
+                     float* mean, float* invstd, void* stream) {
+    if (!X || !W || !Y || !stats || !counter || !scale || !shift || M <= 0 || !al16(X) || !al16(Y)) return CRF_ERR_INVALID_ARG;
+    if (Cout != 64) return CRF_ERR_UNSUPPORTED;
+    Up16FwdArgs a{};
+    a.X = X; a.W = W; a.Y = Y; a.M = M;
+    a.fin = FwdFin{stats, counter, gamma, beta, running_mean, running_var, eps, momentum, (double)M, scale, shift, mean, invstd};
+    up16_fwd_kernel<64><<<grid_for(ceil_div(M, 16), kWarps * 2, 2), kThreads, 0, (cudaStream_t)stream>>>(a);
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }
@@ -1039,7 +1173,12 @@ int crfconv_out16_bwd(const float* dO, const float* H3, const float* sc3, const 
     a.dO = dO; a.H3 = H3; a.sc3 = sc3; a.sh3 = sh3; a.mu3 = mu3; a.is3 = is3; a.slope3 = slope3;
     a.X = X; a.W3 = W3; a.T = T; a.part = part; a.counter = counter; a.count = (double)M;
     a.k1 = k1; a.k2 = k2; a.dgamma = dgamma; a.dbeta = dbeta; a.dW3 = dW3; a.Q = Q; a.a0 = a0; a.M = M;
-    out_bwd_kernel<<<grid_for(ceil_div(M, 16), kWarps * 2, 1), kThreads, 0, (cudaStream_t)stream>>>(a);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CRF_CUDA(cudaFuncSetAttribute(out_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOutSmem));
+        attr_set = true;
+    }
+    out_bwd_kernel<<<grid_for(ceil_div(M, 16), kWarps * 2, 1), kThreads, kOutSmem, (cudaStream_t)stream>>>(a);
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }

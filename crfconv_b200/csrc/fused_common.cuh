@@ -124,8 +124,8 @@ __device__ __forceinline__ void bn_bwd_finalize(const BwdFin& f, double s1, doub
     if (f.dbeta) f.dbeta[c] += (float)s1;
 }
 
-// Tail of a kernel whose CTAs have written part[blockIdx.x (or slot)][2C]: the last CTA to arrive finalizes.  `nparts` = number
-// of partial rows to fold.  Must be reached by every thread of every CTA.
+// Tail of a kernel whose CTAs have added into `nparts` zero-initialised slot rows part[slot][2C] (atomics): the last CTA to arrive
+// folds the slots and finalizes.  Must be reached by every thread of every CTA.
 template <int C, int NT>
 __device__ __forceinline__ void fwd_fin_tail(const FwdFin& f, int nparts, double* red) {
     if (!arrive_is_last(f.counter)) return;
@@ -138,6 +138,101 @@ __device__ __forceinline__ void bwd_fin_tail(const BwdFin& f, int nparts, double
     sum_parts<2 * C, NT>(f.part, nparts, red);
     if (threadIdx.x < C) bn_bwd_finalize(f, red[threadIdx.x], red[C + threadIdx.x], threadIdx.x);
 }
+
+// Deterministic grid reduction of per-CTA rows (V floats each, written with plain stores to rows[blockIdx.x][V]) with the two-level
+// arrival of arrive_is_last: the last CTA of each group of 16 folds its group's rows — fixed order, double precision — into one group
+// row, and the last group folds the ≤ kTicketInts − 1 group rows.  Compared with one CTA folding gridDim.x rows this cuts the serial
+// tail of a kernel from ≈(gridDim.x / 8) dependent L2 round trips to 2-3.  On return true (exactly one CTA) red[0..V) holds the totals.
+// rows: gridDim.x·V floats;  grows: (kTicketInts − 1)·V doubles;  red: NT doubles of shared memory;  NT % V == 0, blockDim.x ≥ NT.
+template <int V, int NT>
+__device__ __forceinline__ bool grid_reduce_rows(const float* rows, double* grows, unsigned int* counters, double* red) {
+    __shared__ unsigned int s_flag;
+    constexpr int NSUB = NT / V;
+    static_assert(NT % V == 0, "NT must be a multiple of V");
+    const int tid = threadIdx.x;
+    const unsigned grp = blockIdx.x >> 4, ngrp = (gridDim.x + 15) >> 4;
+    const unsigned in_grp = min(16u, gridDim.x - (grp << 4));
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const bool glast = atomicAdd(counters + 1 + grp, 1u) == in_grp - 1;
+        if (glast) counters[1 + grp] = 0u;
+        s_flag = glast ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_flag == 0u) return false;
+    __threadfence();
+    // ---- fold this group's rows (≤ 16) in CTA order
+    if (tid < NT) {
+        const int v = tid % V, sub = tid / V;
+        float x[(16 + NSUB - 1) / NSUB];
+#pragma unroll
+        for (int u = 0; u < (16 + NSUB - 1) / NSUB; ++u) {
+            const unsigned r = sub + u * NSUB;
+            x[u] = r < in_grp ? __ldcg(rows + ((size_t)(grp << 4) + r) * V + v) : 0.f;
+        }
+        double acc = 0.0;
+#pragma unroll
+        for (int u = 0; u < (16 + NSUB - 1) / NSUB; ++u) acc += (double)x[u];
+        red[tid] = acc;
+    }
+    __syncthreads();
+    if (tid < V) {
+        double t = 0.0;
+#pragma unroll
+        for (int s = 0; s < NSUB; ++s) t += red[s * V + tid];
+        grows[(size_t)grp * V + tid] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const bool last = atomicAdd(counters, 1u) == ngrp - 1;
+        if (last) counters[0] = 0u;
+        s_flag = last ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_flag == 0u) return false;
+    __threadfence();
+    // ---- fold the group rows in group order
+    if (tid < NT) {
+        const int v = tid % V, sub = tid / V;
+        double acc = 0.0;
+        for (unsigned r0 = sub; r0 < ngrp; r0 += NSUB * 4) {
+            double x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned r = r0 + u * NSUB;
+                x[u] = r < ngrp ? __ldcg(grows + (size_t)r * V + v) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc += x[u];
+        }
+        red[tid] = acc;
+    }
+    __syncthreads();
+    if (tid < V) {
+        double t = 0.0;
+#pragma unroll
+        for (int s = 0; s < NSUB; ++s) t += red[s * V + tid];
+        red[tid] = t;
+    }
+    __syncthreads();
+    return true;
+}
+// layout of a `part` scratch used with grid_reduce_rows: [kMaxTicketGrid][V] floats, then [kTicketInts − 1][V] doubles (V ≤ 32)
+__device__ __forceinline__ double* part_group_rows(float* part) { return reinterpret_cast<double*>(part + (size_t)kMaxTicketGrid * 32); }
+constexpr int kPartFloats = kMaxTicketGrid * 32 + (kTicketInts - 1) * 32 * 2;
+
+// ------------------------------------------------------------------------------------------------ cp.async (warp-private tile rings)
+// 16-byte asynchronous global→shared copy; !pred ⇒ the destination is zero-filled and the source is not read
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int sz = pred ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // ------------------------------------------------------------------------------------------------ 3xTF32 mma.sync helpers
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }

@@ -307,11 +307,11 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
         float tot = 0.0f;
         for (int r = 0; r < rows_per_it; ++r) tot += red[(r * tpr + cs) * 8 + e];
         const int c = cs * 4 + (e & 3);
-        atomicAdd(sums + (size_t)(blockIdx.x % kStatSlots) * 2 * C + (e < 4 ? 0 : C) + c, tot);
+        atomicAdd(sums + (size_t)(blockIdx.x % (fin.part ? 32 : kStatSlots)) * 2 * C + (e < 4 ? 0 : C) + c, tot);
     }
     if (fin.part) {                                               // k1 / k2 / dγ / dβ by the last CTA (C == 64, checked by the launcher)
         __shared__ double s_red[256];
-        cl::bwd_fin_tail<64, 256>(fin, kStatSlots, s_red);
+        cl::bwd_fin_tail<64, 256>(fin, 32, s_red);
     }
 }
 

@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd3_kernel(const FwdArgs a, cons
             if (tid == 0) CRF_TRACE(9, ti);                    // tile stored
         }
         if (a.stats && scol < a.Cout) {
-            float* st = a.stats + (size_t)(blockIdx.x % kStatSlots) * 2 * a.Cout;
+            float* st = a.stats + (size_t)(blockIdx.x % 16) * 2 * a.Cout;      // 16 of the kStatSlots rows: ≤ 10 CTAs per row, short fold
             atomicAdd(st + scol, ssum);
             atomicAdd(st + a.Cout + scol, ssq);
         }
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd3_kernel(const FwdArgs a, cons
     if (a.fin.part) {                                              // BatchNorm finalize by the last CTA (Cout == BN, checked by the launcher)
         constexpr int NT = (kThreads / (2 * BN)) * (2 * BN);
         __shared__ double s_red[NT];
-        cl::fwd_fin_tail<BN, NT>(a.fin, kStatSlots, s_red);
+        cl::fwd_fin_tail<BN, NT>(a.fin, 16, s_red);
     }
 }
 

@@ -344,6 +344,10 @@ def fused_max_parts():
     return int(_lib.lib().crfconv_fused_max_parts())
 
 
+def fused_part_floats():
+    return int(_lib.lib().crfconv_fused_part_floats())
+
+
 def counter_ints():
     """uint32 per `counter` argument of the fused kernels (two-level arrival tickets); zeroed by the caller, left zero."""
     return int(_lib.lib().crfconv_fused_counter_ints())
@@ -375,6 +379,20 @@ def lin16_fwd(X, W, bn: BN, bn_module, part, counter, pre: BN = None, pslope=1.0
                                  _p(Y), int(M), _p(part), _p(counter), gm, bt, rm, rv, eps, mom, _p(bn.scale), _p(bn.shift), _p(bn.mean),
                                  _p(bn.invstd), _lib.stream_ptr())
     _lib.check(rc, "lin16_fwd")
+    return Y
+
+
+def up16_fwd(X, W, bn: BN, bn_module, counter, out=None):
+    """H[M,Cout] = X[M,16]·Wᵀ (Cout = 64) with `bn` finalized by the same launch; bn.stats zeroed."""
+    L = _lib.lib()
+    M, Cout = X.shape[0], W.shape[0]
+    Y = out if out is not None else torch.empty((M, Cout), dtype=torch.float32, device=X.device)
+    gm, bt, rm, rv, eps, mom = _bn_fin_args(bn_module)
+    bn.count, bn.training = int(M), True
+    with _call(f"up16_fwd[{Cout}]", 1, _nbytes(X, Y)):
+        rc = L.crfconv_up16_fwd(_p(X), _p(W), int(Cout), _p(Y), int(M), _p(bn.stats), _p(counter), gm, bt, rm, rv, eps, mom, _p(bn.scale),
+                                _p(bn.shift), _p(bn.mean), _p(bn.invstd), _lib.stream_ptr())
+    _lib.check(rc, "up16_fwd")
     return Y
 
 

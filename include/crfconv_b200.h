@@ -153,7 +153,8 @@ int crfconv_crf_step_bwd(const float* Hy, const float* scale_y, const float* z, 
  * crfconv_fused_counter_ints() zeroed uint32 (two-level arrival tickets) that the kernel leaves zero.  Weight gradients go to CRFCONV_GRAD_SLOTS zero-initialised partial slots (slot_stride floats
  * apart) that crfconv_grad_slots_reduce folds. */
 
-int crfconv_fused_max_parts(void);        /* rows of a `part` scratch: part = max_parts · 32 floats */
+int crfconv_fused_max_parts(void);        /* largest grid of a kernel with an arrival tail */
+int crfconv_fused_part_floats(void);      /* floats of every `part` scratch argument (per-CTA rows + per-group rows) */
 int crfconv_fused_counter_ints(void);     /* uint32 per `counter` argument */
 int crfconv_out_bwd_part_floats(void);    /* floats of crfconv_out16_bwd's `part` (zero-initialised) */
 /* Tuning knobs for experiments (key 0: CTAs/SM of the mean-field backward, 2 or 3).  Returns the previous value. */
@@ -164,6 +165,10 @@ int crfconv_fused_tune(int key, int value);
 int crfconv_lin16_fwd(const float* X, int Cin, const float* W, const float* pscale, const float* pshift, float pslope, float* Y, int64_t M,
                       float* part, unsigned int* counter, const float* gamma, const float* beta, float* running_mean,
                       float* running_var, float eps, float momentum, float* scale, float* shift, float* mean, float* invstd, void* stream);
+/* H[M,Cout] = X[M,16]·Wᵀ + BatchNorm finalize of H (MLP(16,Cout), Cout = 64: out_nn).  stats [CRFCONV_STAT_SLOTS][2·Cout] zeroed. */
+int crfconv_up16_fwd(const float* X, const float* W, int Cout, float* Y, int64_t M, float* stats, unsigned int* counter, const float* gamma,
+                     const float* beta, float* running_mean, float* running_var, float eps, float momentum, float* scale, float* shift,
+                     float* mean, float* invstd, void* stream);
 /* crfconv_linear_fwd (no gather, no bias) + BatchNorm finalize of its output; stats [CRFCONV_STAT_SLOTS][2·Cout] zeroed. */
 int crfconv_linear_fwd_bn(const float* X1, int C1, const float* scale1, const float* shift1, float slope1, const float* X2, int C2,
                           const float* W, float* Y, float* stats, int64_t M, int Cout, int precision, unsigned int* counter,

@@ -24,7 +24,7 @@ rnd = lambda *sh: torch.randn(*sh, device=dev)
 bnm16, bnm64 = torch.nn.BatchNorm1d(16).to(dev), torch.nn.BatchNorm1d(64).to(dev)
 CI = ops.counter_ints()
 cnt = torch.zeros(CI, dtype=torch.int32, device=dev)
-part = torch.empty(ops.fused_max_parts() * 32, device=dev)
+part = torch.empty(ops.fused_part_floats(), device=dev)
 
 
 def bn(C, H=None):
@@ -35,13 +35,23 @@ def bn(C, H=None):
 
 
 def timeit(name, fn, nbytes, reps=20):
-    for _ in range(3):
-        fn()
+    """`reps` back-to-back calls captured into ONE CUDA graph and replayed: no Python / ctypes launch overhead in the measurement."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(reps):
-        fn()
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / reps * 1e3
@@ -67,6 +77,7 @@ timeit("crf_step_fwd", lambda: ops.crf_step_fwd(H2p, b2.scale, z, z, nbr, Cm, Mi
 x1 = ops.crf_step_fwd(H2p, b2.scale, z, z, nbr, Cm, Minv, B, N, K)
 H3, Hf = torch.empty(M, Co, device=dev), torch.empty(M, Co, device=dev)
 b3.stats.zero_(); bf.stats.zero_()
+timeit("up16_fwd[64] (mma.sync + fin)", lambda: ops.up16_fwd(x1, Wo, b3, bnm64, cnt, out=H3), fb * M * (F + Co))
 timeit("linear_fwd_bn[16->64] (tcgen05 + fin)", lambda: ops.linear_fwd_bn(x1, Wo, b3, bnm64, cnt, out=H3), fb * M * (F + Co))
 timeit("  linear_fwd[16->64] (no fin)", lambda: ops.linear_fwd(x1, Wo, stats=b3.stats, out=H3), fb * M * (F + Co))
 timeit("linear_fwd_bn[128->64] (tcgen05 + fin)", lambda: ops.linear_fwd_bn(H3, Wf, bf, bnm64, cnt, scale1=b3.scale, shift1=b3.shift, slope1=0.1, X2=P, out=Hf), fb * M * 3 * Co)
@@ -102,19 +113,20 @@ for variant in (2, 3):
                                                                                  ysum, B, N, K, True, cnt, gam, d16, e16), fb * M * F * 7 + 8 * M * K)
 ops._lib.lib().crfconv_fused_tune(0, 2)
 mo, vo, ho = (torch.empty(M, F, device=dev) for _ in range(3))
+cgrad, w2grad, w1grad = torch.zeros(F, F, device=dev), torch.zeros(F, F, device=dev), torch.zeros(16, Co, device=dev)
 timeit("  generic crf_step_bwd + GC/GM GEMMs", lambda: (ops.crf_step_bwd(H2p, b2.scale, z, z, nbr, Cm, Minv, T, Gz, gp, Gy, mo, vo, ho, False, B, N, K),
-                                                        ops.linear_bwd(mo, None, None, 1.0, ho, c, dW=c.clone(), scratch=scr, scratch_stride=20000),
-                                                        ops.linear_bwd(vo, None, None, 1.0, T, c, dW=c.clone(), scratch=scr, scratch_stride=20000)), fb * M * F * 7 + 8 * M * K)
+                                                        ops.linear_bwd(mo, None, None, 1.0, ho, c, dW=cgrad, scratch=scr, scratch_stride=20000),
+                                                        ops.linear_bwd(vo, None, None, 1.0, T, c, dW=cgrad, scratch=scr, scratch_stride=20000)), fb * M * F * 7 + 8 * M * K)
 Gu = torch.zeros(Mc, F, device=dev)
 timeit("crf_upsample_bwd_fused", lambda: ops.crf_upsample_bwd_fused(Gz, gp, up, H2u, b2, Gu, B, N, Nc, part, cnt, d16, e16), fb * (2 * M * F + Mc * F) + 8 * M)
 dV1 = torch.empty(M, F, device=dev)
 timeit("mid16_bwd (pairwise)", lambda: ops.mid16_bwd(Gy, H2p, b2, H1p, b1, 0.1, W2, scr, 20000, part, cnt, d16, e16, out=dV1), fb * M * F * 4)
 timeit("  generic 16x16 bwd (reduce + narrow::bwd)", lambda: (ops.bn_backward_prepare(Gy, H2p, b2, 1.0, d16, e16, sums=sums[:ops.STAT_SLOTS * 32]),
-                                                            ops.linear_bwd(Gy, H2p, b2, 1.0, H1p, W2, scale1=b1.scale, shift1=b1.shift, slope1=0.1, dX1=dV1, dW=W2.clone(), scratch=scr, scratch_stride=20000)), fb * M * F * 4)
+                                                            ops.linear_bwd(Gy, H2p, b2, 1.0, H1p, W2, scale1=b1.scale, shift1=b1.shift, slope1=0.1, dX1=dV1, dW=w2grad, scratch=scr, scratch_stride=20000)), fb * M * F * 4)
 timeit("in16_dgrad[64] (+=)", lambda: ops.in16_dgrad(dV1, H1p, b1, W1p, dP, True), fb * M * (2 * F + 2 * Co))
 timeit("in16_wgrad[64]", lambda: ops.in16_wgrad(dV1, H1p, b1, P, scr, 20000), fb * M * (2 * F + Co))
 timeit("  generic P-layer bwd (reduce + dgrad + wgrad)", lambda: (ops.bn_backward_prepare(dV1, H1p, b1, 0.1, d16, e16, sums=sums[:ops.STAT_SLOTS * 32]),
-                                                                ops.linear_bwd(dV1, H1p, b1, 0.1, P, W1p, dX1=dP, acc1=True, dW=W1p.clone(), scratch=scr, scratch_stride=20000)), fb * M * (4 * F + 3 * Co))
+                                                                ops.linear_bwd(dV1, H1p, b1, 0.1, P, W1p, dX1=dP, acc1=True, dW=w1grad, scratch=scr, scratch_stride=20000)), fb * M * (4 * F + 3 * Co))
 dV1u, dU = torch.empty(Mc, F, device=dev), torch.empty(Mc, Cu, device=dev)
 timeit("in16_dgrad[128] (=)", lambda: ops.in16_dgrad(dV1u, H1u, b1, W1u, dU, False), fb * Mc * (2 * F + Cu))
 timeit("in16_wgrad[128]", lambda: ops.in16_wgrad(dV1u, H1u, b1, U, scr, 20000), fb * Mc * (2 * F + Cu))

@@ -34,7 +34,7 @@ def _bn_state(ops, C, H64, gamma, beta, eps=1e-5):
 
 
 def _scratch(ops, dev):
-    return torch.empty(ops.fused_max_parts() * 32, device=dev), torch.zeros(ops.counter_ints(), dtype=torch.int32, device=dev)
+    return torch.empty(ops.fused_part_floats(), device=dev), torch.zeros(ops.counter_ints(), dtype=torch.int32, device=dev)
 
 
 @pytest.mark.parametrize("M,Cin,pro", [(5003, 64, False), (40960, 64, False), (2571, 128, False), (30001, 16, True), (7, 16, True)])
@@ -88,6 +88,26 @@ def test_linear_fwd_bn(M, C1, C2, Cout):
     H = ops.linear_fwd_bn(X1, W, st, bnm, cnt, X2=X2)
     A = torch.cat([X1, X2], 1).double() if C2 else X1.double()
     He = A @ W.double().T
+    mu, var = He.mean(0), He.var(0, unbiased=False)
+    istd = 1 / torch.sqrt(var + bnm.eps)
+    _check({"H": _rel(H, He), "mean": _rel(st.mean, mu, floor=1e-3), "invstd": _rel(st.invstd, istd), "scale": _rel(st.scale, istd),
+            "shift": _rel(st.shift, -mu * istd, floor=1e-2), "running_mean": _rel(bnm.running_mean, 0.1 * mu, floor=1e-4),
+            "running_var": _rel(bnm.running_var, 0.9 + 0.1 * var * M / (M - 1))})
+    assert int(cnt.abs().sum().item()) == 0
+
+
+@pytest.mark.parametrize("M", [4099, 245760])
+def test_up16_fwd(M):
+    from crfconv_b200 import ops
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(M)
+    X = (torch.randn(M, 16, generator=g) + 0.3).to(dev)
+    W = (torch.randn(64, 16, generator=g) / 4).to(dev)
+    bnm = torch.nn.BatchNorm1d(64).to(dev)
+    st = ops.BN(64, dev)
+    cnt = torch.zeros(ops.counter_ints(), dtype=torch.int32, device=dev)
+    H = ops.up16_fwd(X, W, st, bnm, cnt)
+    He = X.double() @ W.double().T
     mu, var = He.mean(0), He.var(0, unbiased=False)
     istd = 1 / torch.sqrt(var + bnm.eps)
     _check({"H": _rel(H, He), "mean": _rel(st.mean, mu, floor=1e-3), "invstd": _rel(st.invstd, istd), "scale": _rel(st.scale, istd),
