@@ -888,7 +888,8 @@ int crfconv_bn_bwd_reduce_fin(const float* dY, const float* H, const float* act_
     }
     lin::BnBwd bn{scale, shift, mean, invstd, nullptr, nullptr, act_ref, slope};
     const int rows_per_it = 256 / (C / 4);
-    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(M, rows_per_it * 8), (int64_t)kNumSMs * 4);   // <= cl::kMaxTicketGrid
+    // 84 registers x 256 threads: 3 CTAs are resident per SM — exactly one wave (a 4th CTA per SM would run alone in a second wave)
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(M, rows_per_it * 8), (int64_t)kNumSMs * 3);   // <= cl::kMaxTicketGrid
     lin::bn_bwd_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dY, H, bn, sums, M, C, cl::BwdFin{sums, counter, (double)M, k1, k2, dgamma, dbeta});
     CRF_LAUNCH_CHECK();
     return CRF_OK;
