@@ -19,6 +19,17 @@ SIGNATURES = {
     "crfconv_knn_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64]),
     "crfconv_knn_batch": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _sz, _vp]),
     "crfconv_cpp_knn_batch": (_int, [_vp, _sz, _sz, _sz, _vp, _sz, _sz, _vp]),
+    "crfconv_knn_distance_pick_workspace_bytes": (_sz, [_i64, _i64]),
+    "crfconv_knn_batch_distance_pick": (_int, [_vp, _i64, _i64, _i64, _i64, C.c_uint32, _vp, _vp, _vp, _sz, _vp]),
+    "crfconv_cpp_knn_batch_distance_pick": (_int, [_vp, _sz, _sz, _sz, _vp, _sz, _sz, _vp, C.c_uint32]),
+    "crfconv_radius_batch": (_int, [_vp, _i64, _i64, _vp, _i64, _f32, _i64, _vp, _vp, _sz, _vp]),
+    "crfconv_fps": (_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "crfconv_edge_softmax_fwd": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp]),
+    "crfconv_edge_softmax_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp]),
+    "crfconv_edge_gauss_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _vp]),
+    "crfconv_edge_gauss_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _vp]),
+    "crfconv_spmm_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _vp]),
+    "crfconv_spmm_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp]),
     "crfconv_grid_subsample_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "crfconv_grid_subsample": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _f32, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "crfconv_grid_subsample_host": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _f32, _int, _vp, _vp, _vp, _vp]),

@@ -9,8 +9,11 @@
 It runs on the same sm_100a mean-field kernels as the dense layer (csrc/crf.cu).  Those kernels take a [N, K] neighbour table:
 a REGULAR edge list (every node the target of the same number of edges — what ``knn_graph(pos, k)`` produces, point_conv.py:267-280)
 maps onto it directly; a ragged one (``radius_graph`` with ``max_num_neighbors``) is padded to its largest in-degree with an extra
-node whose softmax weight is exactly zero (see ``dense_neighbours``).  ``GuideGaussianCRFConv`` (:9-69) builds its own radius graph
-with ``torch_cluster`` and is not provided (no radius search kernel yet).
+node whose softmax weight is exactly zero (see ``dense_neighbours``).
+
+``GuideGaussianCRFConv`` (:9-69) — the variant that builds its own ``radius_graph`` and runs the mean field at full width (out_channels
+up to 256) — is provided on the ragged edge-list kernels of csrc/graph.cu (edge softmax + weighted aggregation, any channel count)
+and the grid radius search of csrc/knn.cu (``graph_ops.radius_graph``).
 """
 from __future__ import annotations
 
@@ -150,3 +153,57 @@ class ContinuousGaussianCRFConv(nn.Module):
             xm = _MeanField.apply(z, e, nbr, self.c, self.steps)
         o = _lin_bn(xm, self.mlp[0], self.mlp[1], self.mlp[2].negative_slope, tr)
         return _lin_bn(o, self.fusion_net[0], self.fusion_net[1], self.fusion_net[2].negative_slope, tr, x2=y)
+
+
+class GuideGaussianCRFConv(nn.Module):
+    """Drop-in for models/continuous_crf_conv.py:9-69: ``forward(x, y, pos, batch)`` builds the radius graph itself
+    (``radius_graph(pos, r, batch, max_num_neighbors=kernel_size)``, :52), embeds x / y with one Linear + BatchNorm each (y also
+    through LeakyReLU(0.01)), runs ``steps`` mean-field updates at ``out_channels`` width and returns ``leaky_relu(x)``.
+    Sub-module names and ``state_dict`` keys are the reference's (``unary.{0,1}``, ``pairwise.{0,1}``, ``c``)."""
+
+    def __init__(self, in_n_channels, in_e_channels, out_channels=None, radius=0.1, kernel_size=32, steps=1):
+        super(GuideGaussianCRFConv, self).__init__()
+        self.in_n_channels = in_n_channels
+        self.in_e_channels = in_e_channels
+        self.out_channels = out_channels if out_channels is not None else in_e_channels
+        self.radius = radius
+        self.kernel_size = kernel_size
+        self.steps = steps
+        self.unary = nn.Sequential(nn.Linear(self.in_n_channels, self.out_channels, bias=False), nn.BatchNorm1d(self.out_channels))
+        self.pairwise = nn.Sequential(nn.Linear(self.in_e_channels, self.out_channels, bias=False), nn.BatchNorm1d(self.out_channels),
+                                      nn.LeakyReLU(inplace=True))
+        self.c = nn.Parameter(torch.Tensor(self.out_channels, self.out_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.eye_(self.c)
+
+    def _lin_bn(self, seq, t, slope):
+        lin, bn = seq[0], seq[1]
+        return _LinearBNAct.apply(t, None, None, None, lin.weight, None, bn.weight, bn.bias, bn, self.training or not bn.track_running_stats, slope)
+
+    def forward(self, x, y, pos, batch=None, edge_index=None):
+        """edge_index (optional, [source j, target i]) replaces the internally built radius graph — used by the parity tests."""
+        from . import graph_ops
+        if not x.is_cuda:
+            raise RuntimeError("crfconv_b200 layers run on CUDA tensors only (no CPU fallback)")
+        N = pos.shape[0]
+        if edge_index is None:
+            edge_index = graph_ops.radius_graph(pos, self.radius, batch, loop=False, max_num_neighbors=self.kernel_size)
+        col, row = edge_index[0], edge_index[1]                                  # (:52) col = source j, row = target i
+        eptr, colg, _ = graph_ops.csr_by_target(row.to(torch.int64), col.to(torch.int64), N)
+        x = self._lin_bn(self.unary, x, 1.0)                                     # (:53)
+        y = self._lin_bn(self.pairwise, y, float(self.pairwise[2].negative_slope))   # (:54)
+        s = graph_ops.EdgeSoftmax.apply(y, eptr, colg)                           # (:55-56)
+        z = x
+        eye = torch.eye(self.out_channels, dtype=torch.float32, device=x.device)
+        C = torch.mm(self.c.t(), self.c)                                         # (:60) F x F algebra stays in torch
+        Minv = torch.linalg.inv(eye + C)
+        for t in range(self.steps):                                              # (:62-66)
+            m = graph_ops.SpMM.apply(s, x, eptr, colg)
+            x = _LinearBNAct.apply(m, None, None, z, C.t(), None, None, None, None, False, 1.0)              # z + m·C
+            last = t == self.steps - 1
+            x = _LinearBNAct.apply(x, None, None, None, Minv.t(), None, None, None, None, False, 0.01 if last else 1.0)   # ·(I+C)^-1 (+ final leaky_relu, :69)
+        if self.steps == 0:
+            x = torch.nn.functional.leaky_relu(x)
+        return x

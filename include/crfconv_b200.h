@@ -20,7 +20,7 @@ extern "C" {
 #define CRFCONV_OK 0
 #define CRFCONV_ERR_INVALID_ARG (-1)
 #define CRFCONV_ERR_WORKSPACE (-2)   /* workspace_bytes smaller than the matching *_workspace_bytes() */
-#define CRFCONV_ERR_UNSUPPORTED (-3) /* e.g. K > 32 */
+#define CRFCONV_ERR_UNSUPPORTED (-3) /* e.g. K > 1024, dim != 3 */
 #define CRFCONV_ERR_NO_DEVICE (-4)
 
 int crfconv_abi_version(void);
@@ -30,7 +30,7 @@ const char* crfconv_status_string(int status);
 /* ------------------------------------------------------------------------------------------------- kNN
  * Replaces utils/nearest_neighbors/knn_.h:4-19 (cpp_knn, cpp_knn_omp, cpp_knn_batch, cpp_knn_batch_omp) and their
  * Cython callers knn.pyx:33-109.  Exact K nearest neighbours, squared L2 in f32 with nanoflann's operation order
- * (nanoflann.hpp:343-346), ascending (distance, index).  dim is fixed to 3.  K <= 32.  If K > npts the trailing
+ * (nanoflann.hpp:343-346), ascending (distance, index).  dim is fixed to 3.  K <= 1024 (passes of 32).  If K > npts the trailing
  * slots hold 0 (the observable behaviour of cpp_knn_omp, knn_.cxx:59-67).                                      */
 
 size_t crfconv_knn_workspace_bytes(int64_t batch_size, int64_t npts, int64_t nqueries, int64_t K);
@@ -44,6 +44,26 @@ int crfconv_knn_batch(const float* pts, int64_t batch_size, int64_t npts, const 
  * batch_size = 1, for cpp_knn (knn_.h:4-6): copies to the device, searches, copies back, synchronises. dim must be 3. */
 int crfconv_cpp_knn_batch(const float* batch_data, size_t batch_size, size_t npts, size_t dim, const float* queries,
                           size_t nqueries, size_t K, int64_t* batch_indices);
+
+/* Coverage sampler — replaces cpp_knn_batch_distance_pick / _omp (utils/nearest_neighbors/knn_.h:21-27, knn_.cxx:138-271) and
+ * knn.pyx:111-149: nqueries times per cloud, pick uniformly (std::mt19937 draw % count) among the points whose coverage counter
+ * is at the current minimum level, take its K nearest neighbours, bump their counters (+1; +100 for the picked point).  The
+ * reference seeds the generator with time(0); here the seed is an argument, and the single RNG stream of the reference's serial
+ * loop (one draw per query, clouds in order) is reproduced.  K <= 32. */
+size_t crfconv_knn_distance_pick_workspace_bytes(int64_t batch_size, int64_t npts);
+/* Device pointers.  pts [B,npts,3] f32 -> out_idx [B,nqueries,K] i64, out_queries [B,nqueries,3] f32 (the picked points). */
+int crfconv_knn_batch_distance_pick(const float* pts, int64_t batch_size, int64_t npts, int64_t nqueries, int64_t K, uint32_t seed,
+                                    int64_t* out_idx, float* out_queries, void* workspace, size_t workspace_bytes, void* stream);
+/* HOST pointers: the reference's C signature (knn_.h:21-23) plus the seed. */
+int crfconv_cpp_knn_batch_distance_pick(const float* batch_data, size_t batch_size, size_t npts, size_t dim, float* batch_queries,
+                                        size_t nqueries, size_t K, int64_t* batch_indices, uint32_t seed);
+
+/* Radius search on the kNN grid (device pointers): per query the up-to-K smallest indices of the support points within distance r,
+ * ascending, padded with -1 — torch_cluster.radius(x, y, r, max_num_neighbors = K), the graph builder of
+ * models/continuous_crf_conv.py:52, models/discrete_crf_conv.py:44 and models/point_conv.py:150,180 (third party; semantics
+ * restated).  Workspace: crfconv_knn_workspace_bytes. */
+int crfconv_radius_batch(const float* pts, int64_t batch_size, int64_t npts, const float* queries, int64_t nqueries, float r, int64_t K,
+                         int64_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------- grid subsampling
  * Replaces grid_subsampling() (utils/cpp_wrappers/cpp_subsampling/grid_subsampling/grid_subsampling.h:84-91,
@@ -230,6 +250,27 @@ int crfconv_lrelu_bwd(const float* g, const float* out, float slope, float* dS, 
 int crfconv_add_inplace(float* y, const float* x, int64_t numel, void* stream);
 /* dst[b·Ns + idx[b,m], :] += src[b·Nq + m, :]  — backward of a K=1 row gather (point_conv_big.py:97-101) */
 int crfconv_scatter_add_rows(const float* src, const int64_t* idx, float* dst, int64_t B, int64_t Nq, int64_t Ns, int C, void* stream);
+
+/* ------------------------------------------------------- graph builders and edge-list message passing (PyG-API family)
+ * models/continuous_crf_conv.py:9-133, models/discrete_crf_conv.py:11-63, models/point_conv.py:140-195.  All device pointers.
+ * Edge lists are grouped by TARGET node: node i owns edges [eptr[i], eptr[i+1]), col[e] = source node. */
+
+/* Farthest point sampling per cloud (ptr = CSR offsets of the clouds in pos [ptr[B],3]); out gets GLOBAL indices; dist_ws: ptr[B] floats. */
+int crfconv_fps(const float* pos, const int64_t* ptr, int64_t B, const int64_t* nsample, const int64_t* start, int64_t* out,
+                const int64_t* out_ptr, float* dist_ws, void* stream);
+/* s[e] = softmax over the edges of each target of -||y_i - y_col||^2 (+1e-16 in the denominator, torch_geometric.utils.softmax). */
+int crfconv_edge_softmax_fwd(const float* y, const int64_t* eptr, const int64_t* col, float* s, int64_t N, int C, void* stream);
+int crfconv_edge_softmax_bwd(const float* y, const int64_t* eptr, const int64_t* col, const float* s, const float* ds, float* dy, int64_t N,
+                             int C, void* stream);
+/* w[e] = sum_k Wk[k] exp(-||f_k[col] - f_k[row]||^2), f [N, Kk*H]; g [E, Kk] saves the exponentials (discrete_crf_conv.py:49-56). */
+int crfconv_edge_gauss_fwd(const float* f, const int64_t* eptr, const int64_t* col, const float* Wk, float* w, float* g, int64_t N, int Kk,
+                           int H, void* stream);
+int crfconv_edge_gauss_bwd(const float* f, const int64_t* eptr, const int64_t* col, const float* Wk, const float* g, const float* dw,
+                           float* df, float* dWk, int64_t N, int Kk, int H, void* stream);
+/* out[i,:] = sum over the edges of i of w[e] x[col[e],:]  (scatter_add of weighted messages) and its backward (dw / dx may be NULL). */
+int crfconv_spmm_fwd(const float* x, const int64_t* eptr, const int64_t* col, const float* w, float* out, int64_t N, int C, void* stream);
+int crfconv_spmm_bwd(const float* x, const int64_t* eptr, const int64_t* col, const float* w, const float* g, float* dw, float* dx, int64_t N,
+                     int C, void* stream);
 
 #ifdef __cplusplus
 }

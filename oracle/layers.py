@@ -245,3 +245,67 @@ class EdgeListPointConv(nn.Module):                       # point_conv.py:12-66 
         x = torch.zeros((n_dst, x.shape[1]), dtype=x.dtype).index_add(0, dst, msg)
         x = self.mlp3(x)
         return F.leaky_relu(x + residual)                                                                              # :58
+
+
+def _group_softmax(src, index, num_nodes):                     # torch_geometric.utils.softmax
+    mx = torch.full((num_nodes,) + src.shape[1:], -float("inf"), dtype=src.dtype).scatter_reduce(0, index.view(-1, *[1] * (src.dim() - 1)).expand_as(src), src, "amax")
+    ex = (src - mx[index]).exp()
+    den = torch.zeros((num_nodes,) + src.shape[1:], dtype=src.dtype).index_add_(0, index, ex)
+    return ex / (den[index] + 1e-16)
+
+
+class GuideGaussianCRFConv(nn.Module):                        # continuous_crf_conv.py:9-69 restated without PyG; the graph is an input
+    def __init__(self, in_n_channels, in_e_channels, out_channels=None, radius=0.1, kernel_size=32, steps=1):
+        super().__init__()
+        self.out_channels = out_channels if out_channels is not None else in_e_channels
+        self.radius, self.kernel_size, self.steps = radius, kernel_size, steps
+        self.unary = nn.Sequential(nn.Linear(in_n_channels, self.out_channels, bias=False), nn.BatchNorm1d(self.out_channels))
+        self.pairwise = nn.Sequential(nn.Linear(in_e_channels, self.out_channels, bias=False), nn.BatchNorm1d(self.out_channels),
+                                      nn.LeakyReLU(inplace=True))
+        self.c = nn.Parameter(torch.Tensor(self.out_channels, self.out_channels))
+        nn.init.eye_(self.c)
+
+    def forward(self, x, y, pos, batch=None, edge_index=None):
+        N = pos.shape[0]
+        col, row = edge_index[0], edge_index[1]                # :52  col, row = radius_graph(...)
+        x = self.unary(x)
+        y = self.pairwise(y)
+        s = torch.sum((y[row] - y[col]) ** 2, dim=1, keepdim=True)
+        s = _group_softmax(-s, row, N)
+        z = x
+        I = torch.eye(self.out_channels, dtype=x.dtype)
+        C = torch.mm(self.c.t(), self.c)
+        for _ in range(self.steps):
+            x = s * x[col]
+            x = torch.zeros((N, self.out_channels), dtype=x.dtype).index_add_(0, row, x)
+            x = z + torch.mm(x, C)
+            x = torch.mm(x, (I + C).inverse())
+        return F.leaky_relu(x)
+
+
+class DiscreteCRFConv(nn.Module):                             # discrete_crf_conv.py:11-63 restated without PyG; the graph is an input
+    def __init__(self, n_channels, e_channels, hidden_channels=64, num_kernels=5, radius=0.2, kernel_size=32, steps=5):
+        super().__init__()
+        self.num_kernels, self.steps = num_kernels, steps
+        self.F = nn.Parameter(torch.Tensor(num_kernels, e_channels, hidden_channels))
+        self.W = nn.Parameter(torch.Tensor(num_kernels, 1))
+        self.C = nn.Parameter(torch.Tensor(n_channels, n_channels))
+        nn.init.uniform_(self.F)
+        nn.init.constant_(self.W, 1 / num_kernels)
+        nn.init.eye_(self.C)
+
+    def forward(self, pos, p, f=None, batch=None, edge_index=None):
+        N = pos.shape[0]
+        col, row = edge_index[0], edge_index[1]
+        u = -torch.log(p)
+        f = f.unsqueeze(0).repeat(self.num_kernels, 1, 1)
+        f = torch.bmm(f, self.F).permute((1, 0, 2))
+        f = f[col] - f[row]
+        w = torch.exp(-torch.sum(f ** 2, dim=-1))
+        w = torch.mm(w, self.W)
+        q = p
+        for _ in range(self.steps):
+            q = torch.zeros_like(p).index_add_(0, row, q[col] * w)
+            q = torch.mm(q, self.C)
+            q = torch.softmax(-u - q, dim=-1)
+        return q

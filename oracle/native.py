@@ -34,6 +34,12 @@ def _lib():
         _oracle.oracle_grid_subsample.restype = C.c_int64
         _oracle.oracle_grid_subsample.argtypes = [_f32p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                                   C.c_float, C.c_int, _f32p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _oracle.oracle_knn_batch_distance_pick.restype = None
+        _oracle.oracle_knn_batch_distance_pick.argtypes = [_f32p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_uint32, _i64p, _f32p]
+        _oracle.oracle_fps.restype = None
+        _oracle.oracle_fps.argtypes = [_f32p, _i64p, C.c_int64, _i64p, _i64p, _i64p, _i64p]
+        _oracle.oracle_radius.restype = C.c_int64
+        _oracle.oracle_radius.argtypes = [_f32p, _i64p, _f32p, _i64p, C.c_int64, C.c_float, C.c_int64, _i64p, _i64p]
     return _oracle
 
 
@@ -48,6 +54,39 @@ def knn_batch(pts, queries, K, return_dist=False):
     dist = np.zeros((B, Q, K), dtype=np.float32) if return_dist else None
     _lib().oracle_knn_batch(pts, B, N, queries, Q, K, idx, dist.ctypes.data if return_dist else None)
     return (idx, dist) if return_dist else idx
+
+
+def knn_batch_distance_pick(pts, nqueries, K, seed):
+    """knn.pyx:111-149 / knn_.cxx:138-203 with an explicit mt19937 seed.  Returns (indices [B,Q,K], queries [B,Q,3])."""
+    pts = np.ascontiguousarray(pts, dtype=np.float32)
+    B, N, _ = pts.shape
+    idx = np.zeros((B, nqueries, K), dtype=np.int64)
+    q = np.zeros((B, nqueries, 3), dtype=np.float32)
+    _lib().oracle_knn_batch_distance_pick(pts, B, N, nqueries, K, int(seed) & 0xFFFFFFFF, idx, q)
+    return idx, q
+
+
+def fps(pos, ptr, nsample, start=None):
+    """Farthest point sampling per cloud (CSR offsets `ptr`); returns flat int64 indices into pos, cloud after cloud."""
+    pos = np.ascontiguousarray(pos, dtype=np.float32)
+    ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+    B = len(ptr) - 1
+    ns = np.ascontiguousarray(np.broadcast_to(np.asarray(nsample, dtype=np.int64), (B,)))
+    st = np.zeros(B, dtype=np.int64) if start is None else np.ascontiguousarray(start, dtype=np.int64)
+    optr = np.concatenate([[0], np.cumsum(ns)]).astype(np.int64)
+    out = np.zeros(int(optr[-1]), dtype=np.int64)
+    _lib().oracle_fps(pos, ptr, B, ns, st, out, optr)
+    return out
+
+
+def radius(x, ptr_x, y, ptr_y, r, max_num_neighbors):
+    """(rows = query index into y, cols = support index into x): first max_num_neighbors supports within r, ascending index."""
+    x, y = np.ascontiguousarray(x, dtype=np.float32), np.ascontiguousarray(y, dtype=np.float32)
+    ptr_x, ptr_y = np.ascontiguousarray(ptr_x, dtype=np.int64), np.ascontiguousarray(ptr_y, dtype=np.int64)
+    cap = y.shape[0] * int(max_num_neighbors)
+    rows, cols = np.zeros(cap, dtype=np.int64), np.zeros(cap, dtype=np.int64)
+    e = _lib().oracle_radius(x, ptr_x, y, ptr_y, len(ptr_x) - 1, float(r), int(max_num_neighbors), rows, cols)
+    return rows[:e].copy(), cols[:e].copy()
 
 
 def knn(pts, queries, K, return_dist=False):
@@ -131,6 +170,18 @@ def ref_knn(pts, queries, K, omp=False):
     out = np.zeros((queries.shape[0], K), dtype=np.int64)
     _refknn().ref_knn(pts, pts.shape[0], pts.shape[1], queries, queries.shape[0], K, out, int(omp))
     return out
+
+
+def ref_knn_batch_distance_pick(pts, nqueries, K, omp=False):
+    """The reference's nearest_neighbors.knn_batch_distance_pick (knn.pyx:111-149) minus Cython (seeded with time(0) inside)."""
+    pts = np.ascontiguousarray(pts, dtype=np.float32)
+    lib = _refknn()
+    lib.ref_knn_batch_distance_pick.restype = None
+    lib.ref_knn_batch_distance_pick.argtypes = [_f32p, C.c_size_t, C.c_size_t, C.c_size_t, _f32p, C.c_size_t, C.c_size_t, _i64p, C.c_int]
+    idx = np.zeros((pts.shape[0], nqueries, K), dtype=np.int64)
+    q = np.zeros((pts.shape[0], nqueries, 3), dtype=np.float32)
+    lib.ref_knn_batch_distance_pick(pts, pts.shape[0], pts.shape[1], pts.shape[2], q, nqueries, K, idx, int(omp))
+    return idx, q
 
 
 def ref_knn_batch(pts, queries, K, omp=False):

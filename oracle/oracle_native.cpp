@@ -181,3 +181,75 @@ int64_t oracle_grid_subsample(const float* pts, int64_t N, const float* feats, i
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Coverage sampler — knn_.cxx:138-203 (cpp_knn_batch_distance_pick) restated with the seed as an argument (the reference seeds
+// std::mt19937 with time(0)) and the canonical brute-force kNN above instead of the kd-tree.  One RNG stream runs through the
+// clouds in order, one draw per query, exactly like the reference's serial loop.
+#include <random>
+extern "C" void oracle_knn_batch_distance_pick(const float* pts, int64_t B, int64_t N, int64_t nq, int64_t K, uint32_t seed,
+                                               int64_t* out_idx, float* out_q) {
+    std::mt19937 mt_rand(seed);
+    for (int64_t b = 0; b < B; ++b) {
+        const float* P = pts + b * N * 3;
+        std::vector<int> used((size_t)N, 0);
+        int current_id = 0;
+        for (int64_t q = 0; q < nq; ++q) {
+            std::vector<size_t> possible;
+            while (possible.empty()) {                                     // knn_.cxx:160-170
+                for (int64_t i = 0; i < N; ++i)
+                    if (used[i] == current_id) possible.push_back((size_t)i);
+                if (possible.empty()) current_id = *std::min_element(used.begin(), used.end());
+            }
+            const size_t index = possible[mt_rand() % possible.size()];    // :173
+            const float* query = P + 3 * index;
+            std::vector<int64_t> ids((size_t)K);
+            knn_one_cloud(P, N, query, 1, K, ids.data(), nullptr);
+            for (int64_t k = 0; k < std::min(K, N); ++k) used[ids[k]]++;   // :186-188
+            used[index] += 100;                                            // :189
+            for (int64_t k = 0; k < K; ++k) out_idx[(b * nq + q) * K + k] = ids[k];
+            for (int c = 0; c < 3; ++c) out_q[(b * nq + q) * 3 + c] = query[c];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Farthest point sampling (the `fps` the reference imports from torch_points_kernels / torch_cluster — third party, not under
+// /root/reference, PARITY UNPINNED): start at `start`, then repeatedly take the point whose distance to the selected set is
+// largest; squared distances with the kNN arithmetic above (f32, no FMA), ties → smallest index.  ptr: CSR offsets of the clouds.
+extern "C" void oracle_fps(const float* pos, const int64_t* ptr, int64_t B, const int64_t* nsample, const int64_t* start, int64_t* out,
+                           const int64_t* out_ptr) {
+    for (int64_t b = 0; b < B; ++b) {
+        const int64_t n = ptr[b + 1] - ptr[b];
+        const float* P = pos + 3 * ptr[b];
+        std::vector<float> dist((size_t)n, INFINITY);
+        int64_t cur = start[b];
+        for (int64_t s = 0; s < nsample[b]; ++s) {
+            out[out_ptr[b] + s] = ptr[b] + cur;
+            float best = -1.0f;
+            int64_t arg = 0;
+            for (int64_t i = 0; i < n; ++i) {
+                const float d = std::min(dist[i], sqdist3(P + 3 * cur, P + 3 * i));
+                dist[i] = d;
+                if (d > best) { best = d; arg = i; }
+            }
+            cur = arg;
+        }
+    }
+}
+
+// Radius search with torch_cluster's CUDA semantics (third party, PARITY UNPINNED): for query i the first `max_nb` support points
+// j of the same cloud, in ascending index order, with squared distance <= r² (f32 arithmetic above).  Returns the number of pairs;
+// rows[e] = query, cols[e] = support point, grouped by query.
+extern "C" int64_t oracle_radius(const float* x, const int64_t* ptr_x, const float* y, const int64_t* ptr_y, int64_t B, float r, int64_t max_nb,
+                                 int64_t* rows, int64_t* cols) {
+    const float r2 = r * r;
+    int64_t e = 0;
+    for (int64_t b = 0; b < B; ++b)
+        for (int64_t i = ptr_y[b]; i < ptr_y[b + 1]; ++i) {
+            int64_t cnt = 0;
+            for (int64_t j = ptr_x[b]; j < ptr_x[b + 1] && cnt < max_nb; ++j)
+                if (sqdist3(y + 3 * i, x + 3 * j) <= r2) { rows[e] = i; cols[e] = j; ++e; ++cnt; }
+        }
+    return e;
+}

@@ -150,3 +150,35 @@ def test_crf_layer_oracle_accepts_batch_of_one(golden):
     out = m(torch.from_numpy(g["crf_s1.unary"][:1]), torch.from_numpy(g["crf_s1.pairwise"][:1]),
             torch.from_numpy(g["crf_s1.up_idx"][:1]), torch.from_numpy(g["crf_s1.neighbor_idx"][:1]))
     assert out.shape == (1, 512, 64)
+
+
+def test_distance_pick_oracle_against_the_compiled_reference():
+    """knn_.cxx:138-271: the reference seeds mt19937 with time(0), so its picks cannot be replayed — what is pinned is (i) that the
+    oracle's kNN of the reference's own picked queries equals the reference's neighbour lists, bit for bit, and (ii) that the seeded
+    oracle loop satisfies the reference's invariants (no point picked twice before all are covered; queries are support points)."""
+    import numpy as np
+    from oracle import native as on
+    from oracle import synthetic
+    pos = synthetic.room_cloud(2, 800, seed=11)
+    oi, oq = on.knn_batch_distance_pick(pos, 120, 12, seed=4)
+    assert np.array_equal(oi, on.knn_batch(pos, oq, 12))
+    for b in range(2):
+        assert len(set(oi[b, :, 0].tolist())) == 120 and np.array_equal(pos[b][oi[b, :, 0]], oq[b])
+    oi2, _ = on.knn_batch_distance_pick(pos, 120, 12, seed=4)
+    assert np.array_equal(oi, oi2)                                    # deterministic in the seed
+    if on.have_ref_knn():
+        for omp in (False, True):
+            ri, rq = on.ref_knn_batch_distance_pick(pos, 120, 12, omp=omp)
+            assert np.array_equal(ri, on.knn_batch(pos, rq, 12))
+            for b in range(2):
+                assert len(set(ri[b, :, 0].tolist())) == 120 and np.array_equal(pos[b][ri[b, :, 0]], rq[b])
+
+
+def test_large_k_oracle_against_the_compiled_reference():
+    import numpy as np
+    from oracle import native as on
+    from oracle import synthetic
+    if not on.have_ref_knn():
+        return
+    pos = synthetic.room_cloud(1, 3000, seed=12)
+    assert np.array_equal(on.knn_batch(pos, pos[:, :200], 64), on.ref_knn_batch(pos, pos[:, :200].copy(), 64))
