@@ -64,7 +64,7 @@ int crfconv_cpp_knn_batch(const float* batch_data, size_t batch_size, size_t npt
     if (dim != 3) return CRF_ERR_UNSUPPORTED;
     if (batch_size == 0 || nqueries == 0 || K == 0) return CRF_OK;
     if (!batch_data || !queries || !batch_indices || npts == 0) return CRF_ERR_INVALID_ARG;
-    if (K > 32) return CRF_ERR_UNSUPPORTED;
+    if (K > 1024) return CRF_ERR_UNSUPPORTED;
     const int64_t B = (int64_t)batch_size, N = (int64_t)npts, Q = (int64_t)nqueries, Kk = (int64_t)K;
     const size_t pts_b = align_up((size_t)B * N * 3 * sizeof(float), 256);
     const size_t q_b = align_up((size_t)B * Q * 3 * sizeof(float), 256);

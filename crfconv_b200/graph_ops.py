@@ -1,7 +1,7 @@
 """Graph builders of the reference's PyG-API family on the sm_100a kernels — the functions ``models/point_conv.py:140-195,267-280``,
 ``models/continuous_crf_conv.py:52`` and ``models/discrete_crf_conv.py:44`` import from torch_geometric / torch_cluster /
-torch_points_kernels (third-party packages that are not part of the reference tree; their semantics are restated here and in
-oracle/, parity unpinned):
+torch_points_kernels (third-party packages that are not part of the reference tree; their semantics are restated here and in the
+CPU checker used by the tests; parity with those packages is unpinned):
 
     furthest_point_sampling(pos[B,N,3], nsamples)                      -> int64 [B, nsamples]      (datasets/s3dis_dataset.py:435)
     fps(pos[N,3], batch, ratio, random_start=False)                    -> int64 [sum ceil(ratio·n_b)]

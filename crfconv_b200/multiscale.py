@@ -19,17 +19,24 @@ def build_multiscale(pos, num_scales=5, kernel_size=(16, 16, 16, 16, 16), ratio=
     """pos: [B, N, 3] CUDA float tensor.  `generator` (CPU torch.Generator) makes the random choices reproducible."""
     if not pos.is_cuda:
         raise RuntimeError("build_multiscale runs on CUDA tensors only (no CPU fallback)")
-    if sample_method.lower() != "random":
-        raise NotImplementedError("Only `random` sampling is implemented (the reference's `fps` needs torch_points_kernels)")
+    method = sample_method.lower()
+    if method not in ("random", "fps"):
+        raise NotImplementedError("Only `random` or `fps` sampling method is implemented!")       # the reference's message (:438)
     out = []
     pos = pos.float().contiguous()
     for i in range(num_scales):
         N = pos.shape[1]
         neighbor_idx = nearest_neighbors.knn_batch_cuda(pos, pos, kernel_size[i])          # [B, N, K]
         sample_num = N // ratio[i]
-        choice = torch.randperm(N, generator=generator)[:sample_num].to(pos.device)         # shared by the whole batch (:424)
-        sub_pos = pos[:, choice, :].contiguous()
-        sub_idx = neighbor_idx[:, choice, :].contiguous()
+        if method == "random":
+            choice = torch.randperm(N, generator=generator)[:sample_num].to(pos.device)     # shared by the whole batch (:424)
+            sub_pos = pos[:, choice, :].contiguous()
+            sub_idx = neighbor_idx[:, choice, :].contiguous()
+        else:                                                                               # farthest point sampling per cloud (:434-437)
+            from . import graph_ops
+            choice = graph_ops.furthest_point_sampling(pos, sample_num)                     # [B, S]
+            sub_pos = pos.gather(1, choice.unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+            sub_idx = neighbor_idx.gather(1, choice.unsqueeze(-1).expand(-1, -1, neighbor_idx.shape[-1])).contiguous()
         up_idx = nearest_neighbors.knn_batch_cuda(sub_pos, pos, 1)                          # [B, N, 1]
         out.append(types.SimpleNamespace(pos=pos, neighbor_idx=neighbor_idx, sub_idx=sub_idx, up_idx=up_idx))
         pos = sub_pos

@@ -166,7 +166,7 @@ def _graph_inputs(sizes, r, K, seed):
     return torch.from_numpy(pos), torch.from_numpy(batch), torch.from_numpy(np.stack([ec[keep], er[keep]]))
 
 
-@pytest.mark.parametrize("Cn,Ce,Co,steps", [(32, 16, 64, 1), (64, 64, 256, 2), (8, 6, 12, 3)])
+@pytest.mark.parametrize("Cn,Ce,Co,steps", [(32, 16, 64, 1), (64, 64, 256, 2), (8, 6, 16, 3)])
 def test_guide_crf_vs_oracle(Cn, Ce, Co, steps):
     """GuideGaussianCRFConv (continuous_crf_conv.py:9-69) incl. its internally built radius graph, forward + backward."""
     from crfconv_b200.continuous_crf_conv import GuideGaussianCRFConv
@@ -220,3 +220,21 @@ def test_discrete_crf_vs_oracle():
     po = dict(mo.named_parameters())
     errs.update({"g." + n: _rel(q.grad, po[n].grad) for n, q in mp.named_parameters()})
     assert all(v < TOL for v in errs.values()), errs
+
+
+def test_multiscale_builder_with_fps_matches_the_cpu_pipeline():
+    """build_multiscale(sample_method='fps') (datasets/s3dis_dataset.py:434-437) against the oracle FPS + oracle kNN pipeline."""
+    from crfconv_b200.multiscale import build_multiscale
+    B, N = 2, 2048
+    pos = synthetic.room_cloud(B, N, seed=9)
+    ms = build_multiscale(torch.from_numpy(pos).cuda(), num_scales=3, ratio=(4, 4, 2), sample_method="fps")
+    cur = pos
+    for lvl, r in zip(ms, (4, 4, 2)):
+        n = cur.shape[1]
+        assert np.array_equal(lvl.neighbor_idx.cpu().numpy(), on.knn_batch(cur, cur, 16))
+        ptr = np.arange(B + 1) * n
+        choice = on.fps(cur.reshape(-1, 3), ptr, n // r).reshape(B, n // r) - ptr[:-1, None]
+        sub = np.take_along_axis(cur, choice[..., None], 1)
+        assert np.array_equal(lvl.up_idx.cpu().numpy(), on.knn_batch(sub, cur, 1))
+        assert np.array_equal(lvl.sub_idx.cpu().numpy(), np.take_along_axis(on.knn_batch(cur, cur, 16), choice[..., None], 1))
+        cur = sub
