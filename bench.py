@@ -559,7 +559,7 @@ def run_gpu_network(args, rank, local_rank, world, dev, numa):
     B, N, ncls = args.clouds or cfg["clouds"], cfg["points"], cfg["classes"]
     torch.manual_seed(1234)
     net = PointConvResNet(6, ncls).to(dev).train()
-    grads = FlatGradients(net)
+    grads = FlatGradients(net, direct=True)
 
     def barrier():
         if world > 1:

@@ -67,7 +67,7 @@ class _LinearBNAct(torch.autograd.Function):
     R [B,N,Cout] or None (residual added before the activation, point_conv_big.py:88)."""
 
     @staticmethod
-    def forward(ctx, x1, x2, idx, R, W, bias, gamma, beta, bn_module, training, slope):
+    def forward(ctx, x1, x2, idx, R, W, bias, gamma, beta, bn_module, training, slope, gbuf=None):
         if not x1.is_cuda:
             raise RuntimeError("crfconv_b200 layers run on CUDA tensors only (no CPU fallback)")
         a1 = ops.as2d(x1)
@@ -99,6 +99,7 @@ class _LinearBNAct(torch.autograd.Function):
                 st.count, st.training = M, False
                 Y = ops.bn_act_fwd(H, st, slope, R=r2)
         ctx.has_bn, ctx.slope, ctx.st = bn_module is not None, slope, st
+        ctx.gbuf = gbuf        # (dW, dbias, dgamma, dbeta) accumulation targets owned by the caller (see direct_grad_buffers), or None
         ctx.has_bias, ctx.has_R = bias is not None, R is not None
         ctx.shapes = (x1.shape, x2.shape if x2 is not None else None, R.shape if R is not None else None)
         ctx.gather = (rows_dst, rows_src)
@@ -121,14 +122,17 @@ class _LinearBNAct(torch.autograd.Function):
             dR, slope = g2, 1.0
         dX1 = torch.empty((M, a1.shape[1]), dtype=torch.float32, device=dev) if nig[0] else None
         dX2 = torch.empty_like(a2) if (a2 is not None and nig[1]) else None
-        dW = torch.zeros_like(Wc)
+        gb = ctx.gbuf or (None, None, None, None)
+        direct = [b is not None for b in gb]                 # kernels accumulate (+=) straight into the caller's gradient buffers
+        dW = gb[0] if direct[0] else torch.zeros_like(Wc)
         dgamma = dbeta = dbias = None
         st = ctx.st
         if ctx.has_bn:
-            dgamma, dbeta = torch.zeros(Cout, device=dev), torch.zeros(Cout, device=dev)
+            dgamma = gb[2] if direct[2] else torch.zeros(Cout, device=dev)
+            dbeta = gb[3] if direct[3] else torch.zeros(Cout, device=dev)
             ops.bn_backward_prepare(g2, H, st, slope, dgamma, dbeta)
         else:
-            dbias = torch.zeros(Cout, device=dev) if ctx.has_bias else None
+            dbias = (gb[1] if direct[1] else torch.zeros(Cout, device=dev)) if ctx.has_bias else None
             if st is not None and slope != 1.0:
                 st.k1.zero_(); st.k2.zero_()   # activation without BN: fixed affine (scale 1)
             else:
@@ -141,8 +145,26 @@ class _LinearBNAct(torch.autograd.Function):
             ops.scatter_add_rows(dX1, gidx, full, s1[0], rows_dst, rows_src)
             dX1 = full
         return (dX1.view(s1) if dX1 is not None else None, dX2.view(s2) if dX2 is not None else None, None,
-                dR.view(sR) if (dR is not None and nig[3]) else None, dW if nig[4] else None, dbias if nig[5] else None,
-                dgamma if nig[6] else None, dbeta if nig[7] else None, None, None, None)
+                dR.view(sR) if (dR is not None and nig[3]) else None, dW if (nig[4] and not direct[0]) else None,
+                dbias if (nig[5] and not direct[1]) else None, dgamma if (nig[6] and not direct[2]) else None,
+                dbeta if (nig[7] and not direct[3]) else None, None, None, None, None)
+
+
+def direct_grad_buffers(*params):
+    """Gradient buffers that the backward kernels may accumulate into DIRECTLY, one per parameter (None where not applicable).
+
+    A parameter opts in through ``p._crf_direct_grad = True`` — set by ``FlatGradients(module, direct=True)`` on parameters whose
+    ``.grad`` is a pre-bound view of the flat gradient buffer.  The kernels already accumulate (dW += …, dγ += …), so handing them the
+    bound views removes, per parameter and step, a zero-fill of a temporary and autograd's AccumulateGrad add kernel (≈450 tiny
+    launches per PointConvResNet step).  The autograd Function then reports no gradient for that parameter; code that needs
+    ``torch.autograd.grad`` or parameter hooks must not opt in."""
+    out = []
+    for p in params:
+        g = getattr(p, "grad", None) if p is not None else None
+        ok = (p is not None and getattr(p, "_crf_direct_grad", False) and g is not None and g.is_cuda and g.dtype == torch.float32
+              and g.is_contiguous() and p.requires_grad and torch.is_grad_enabled())
+        out.append(g if ok else None)
+    return tuple(out) if any(b is not None for b in out) else None
 
 
 class MLP(nn.Module):
@@ -168,9 +190,11 @@ class MLP(nn.Module):
         if self.bn is not None:
             bnm = self.bn.batch_norm
             y = _LinearBNAct.apply(x, x2, gather_idx, residual, self.lin.weight, None, bnm.weight, bnm.bias, bnm,
-                                   self.training or not bnm.track_running_stats, fused)
+                                   self.training or not bnm.track_running_stats, fused,
+                                   direct_grad_buffers(self.lin.weight, None, bnm.weight, bnm.bias))
         else:
-            y = _LinearBNAct.apply(x, x2, gather_idx, residual, self.lin.weight, self.lin.bias, None, None, None, False, fused)
+            y = _LinearBNAct.apply(x, x2, gather_idx, residual, self.lin.weight, self.lin.bias, None, None, None, False, fused,
+                                   direct_grad_buffers(self.lin.weight, self.lin.bias, None, None))
         if own is None:
             y = self.activation(y)
         return y

@@ -46,15 +46,26 @@ def _aux_stream(dev):
     return _AUX[key]
 
 
+def _param_grads(gbuf, grads):
+    """Parameter gradients of a CRF layer: returned to autograd, or — when the parameters opted into direct accumulation
+    (common.direct_grad_buffers) — added into the bound .grad views with ONE multi-tensor kernel (instead of one AccumulateGrad add
+    per parameter) and reported as None."""
+    if gbuf is None:
+        return grads
+    torch._foreach_add_(list(gbuf), [g.view_as(b) for g, b in zip(grads, gbuf)])
+    return [None] * len(grads)
+
+
 def _mlp_params(m: MLP):
     return m.lin.weight, m.bn.batch_norm.weight, m.bn.batch_norm.bias
 
 
 class _CRFConvFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, unary, pairwise, up_idx, neighbor_idx, steps, training, mods, c, *params):
+    def forward(ctx, unary, pairwise, up_idx, neighbor_idx, steps, training, mods, gbuf, c, *params):
         if not (unary.is_cuda and pairwise.is_cuda):
             raise RuntimeError("crfconv_b200 layers run on CUDA tensors only (no CPU fallback)")
+        ctx.gbuf = gbuf
         (W1u, _, _, W2u, _, _, W1p, _, _, W2p, _, _, Wo, _, _, Wf, _, _) = [p.detach().contiguous().float() for p in params]
         bns = [m.bn.batch_norm for m in mods]          # order: u0, u1, p0, p1, out, fusion
         sl = [m.slope for m in mods]                   # LeakyReLU slopes (1.0 = no activation), reference: .1, 1, .1, 1, .1, .1
@@ -224,7 +235,7 @@ class _CRFConvFunction(torch.autograd.Function):
         for k in ("1u", "2u", "1p", "2p", "o", "f"):
             grads += [dW[k], dg[k], db[k]]
         return (dU.view(B, Nc, Cu) if dU is not None else None, dP.view(B, N, Cp) if need_p else None, None, None, None, None,
-                None, Gc, *grads)
+                None, None, *_param_grads(ctx.gbuf, [Gc, *grads]))
 
 
 _THIRD = {}
@@ -261,9 +272,10 @@ class _CRFConvFusedFunction(torch.autograd.Function):
     (was 24 + 33), every BatchNorm finalize folded into the producing kernel, out_nn's backward reduced to one pass."""
 
     @staticmethod
-    def forward(ctx, unary, pairwise, up_idx, neighbor_idx, steps, mods, c, *params):
+    def forward(ctx, unary, pairwise, up_idx, neighbor_idx, steps, mods, gbuf, c, *params):
         if not (unary.is_cuda and pairwise.is_cuda):
             raise RuntimeError("crfconv_b200 layers run on CUDA tensors only (no CPU fallback)")
+        ctx.gbuf = gbuf
         (W1u, _, _, W2u, _, _, W1p, _, _, W2p, _, _, Wo, _, _, Wf, _, _) = [p.detach().contiguous().float() for p in params]
         bns = [m.bn.batch_norm for m in mods]          # order: u0, u1, p0, p1, out, fusion
         sl = [m.slope for m in mods]
@@ -433,7 +445,7 @@ class _CRFConvFusedFunction(torch.autograd.Function):
         for k in ("1u", "2u", "1p", "2p", "o", "f"):
             grads += [dW[k], dg[k], db[k]]
         return (dU.view(B, Nc, Cu) if dU is not None else None, dP.view(B, N, Cp) if need_p else None, None, None, None, None,
-                Gc, *grads)
+                None, *_param_grads(ctx.gbuf, [Gc, *grads]))
 
 
 class ContinuousGaussianCRFConv(nn.Module):
@@ -468,6 +480,10 @@ class ContinuousGaussianCRFConv(nn.Module):
         params = []
         for m in (self.unary_nn[0], self.unary_nn[1], self.pairwise_nn[0], self.pairwise_nn[1], self.out_nn, self.fusion_nn):
             params += list(_mlp_params(m))
+        from .common import direct_grad_buffers
+        gbuf = direct_grad_buffers(self.c, *params)
+        if gbuf is not None and any(b is None for b in gbuf):
+            gbuf = None
         if USE_FUSED and fused_eligible(unary, pairwise, neighbor_idx, self.steps, self.training, mods, self.hidden_channels, self.out_channels):
-            return _CRFConvFusedFunction.apply(unary, pairwise, up_idx, neighbor_idx, self.steps, mods, self.c, *params)
-        return _CRFConvFunction.apply(unary, pairwise, up_idx, neighbor_idx, self.steps, self.training, mods, self.c, *params)
+            return _CRFConvFusedFunction.apply(unary, pairwise, up_idx, neighbor_idx, self.steps, mods, gbuf, self.c, *params)
+        return _CRFConvFunction.apply(unary, pairwise, up_idx, neighbor_idx, self.steps, self.training, mods, gbuf, self.c, *params)

@@ -48,7 +48,7 @@ class FlatGradients:
                  fused CRF layer returns views of a single flat allocation — that storage is all-reduced in place; otherwise
                  they are packed with one foreach-copy, reduced and copied back."""
 
-    def __init__(self, module: torch.nn.Module, bind: bool = True, extra: int = 0):
+    def __init__(self, module: torch.nn.Module, bind: bool = True, extra: int = 0, direct: bool = False):
         self.params = [p for p in module.parameters() if p.requires_grad]
         if not self.params:
             raise ValueError("module has no trainable parameters")
@@ -59,6 +59,9 @@ class FlatGradients:
         # class-weighted / ignore_index cross-entropy is normalised by the GLOBAL weight sum like the reference's single-process batch)
         self.flat = torch.zeros(self.numel + extra, dtype=torch.float32, device=dev)
         self.extra = self.flat[self.numel:]
+        # direct=True (needs bind): the crfconv_b200 backward kernels accumulate straight into the bound views (common.direct_grad_buffers)
+        # instead of returning temporaries for autograd to add — no per-parameter fill / add kernels on the step
+        self.direct = bool(direct and bind)
         if bind:
             self._bind()
 
@@ -66,6 +69,8 @@ class FlatGradients:
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)      # autograd accumulates in place into these views
+            if self.direct:
+                p._crf_direct_grad = True
             off += p.numel()
 
     def zero(self):

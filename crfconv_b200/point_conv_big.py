@@ -23,7 +23,7 @@ class _PointConvFunction(torch.autograd.Function):
     BatchNorm statistics run over all B·N'·K edges, like the reference's weight_nn on [B, N'·K, 3]."""
 
     @staticmethod
-    def forward(ctx, x, support, centres, idx, W1, g1, b1, W2, g2, b2, bn1, bn2, training, slope1):
+    def forward(ctx, x, support, centres, idx, W1, g1, b1, W2, g2, b2, bn1, bn2, training, slope1, gbuf=None):
         if not x.is_cuda:
             raise RuntimeError("crfconv_b200 layers run on CUDA tensors only (no CPU fallback)")
         B, Ns, d = x.shape
@@ -41,6 +41,7 @@ class _PointConvFunction(torch.autograd.Function):
         H2 = ops.linear_fwd(H1, W2c, scale1=st1.scale, shift1=st1.shift, slope1=slope1, stats=st2.stats); fin()
         out = ops.pointconv_aggregate_fwd(x2, H2, st2, nbr, B, Ns, Nq, K)
         ctx.dims, ctx.st, ctx.slope1 = (B, Ns, Nq, K, d), (st1, st2), slope1
+        ctx.gbuf = gbuf if (gbuf is not None and all(b is not None for b in gbuf)) else None     # direct accumulation targets (common.direct_grad_buffers)
         ctx.save_for_backward(x2, nbr, rel, H1, H2, W1c, W2c)
         return out.view(B, Nq, d)
 
@@ -51,9 +52,12 @@ class _PointConvFunction(torch.autograd.Function):
         st1, st2 = ctx.st
         dev = g.device
         g2 = ops.as2d(g)
-        small = ops.Flat(W1c.numel() + W2c.numel() + 4 * d, torch.float32, dev)
-        dW1, dW2 = small.take(*W1c.shape), small.take(*W2c.shape)
-        dg1, db1, dg2, db2 = (small.take(d) for _ in range(4))
+        if ctx.gbuf is not None:                                                          # the kernels accumulate into the bound .grad views
+            dW1, dg1, db1, dW2, dg2, db2 = ctx.gbuf
+        else:
+            small = ops.Flat(W1c.numel() + W2c.numel() + 4 * d, torch.float32, dev)
+            dW1, dW2 = small.take(*W1c.shape), small.take(*W2c.shape)
+            dg1, db1, dg2, db2 = (small.take(d) for _ in range(4))
         dx = torch.zeros_like(x2) if ctx.needs_input_grad[0] else None
         dWgt = ops.pointconv_aggregate_bwd(x2, H2, st2, nbr, g2, dx, B, Ns, Nq, K)        # [E, d]
         ops.bn_backward_prepare(dWgt, H2, st2, 1.0, dg2, db2)
@@ -61,7 +65,9 @@ class _PointConvFunction(torch.autograd.Function):
         ops.linear_bwd(dWgt, H2, st2, 1.0, H1, W2c, scale1=st1.scale, shift1=st1.shift, slope1=ctx.slope1, dX1=dA1, dW=dW2)
         ops.bn_backward_prepare(dA1, H1, st1, ctx.slope1, dg1, db1)
         ops.linear_bwd(dA1, H1, st1, ctx.slope1, rel, W1c, dW=dW1)                        # positions carry no gradient
-        return (dx.view(B, Ns, d) if dx is not None else None, None, None, None, dW1, dg1, db1, dW2, dg2, db2, None, None, None, None)
+        if ctx.gbuf is not None:
+            return (dx.view(B, Ns, d) if dx is not None else None,) + (None,) * 14
+        return (dx.view(B, Ns, d) if dx is not None else None, None, None, None, dW1, dg1, db1, dW2, dg2, db2, None, None, None, None, None)
 
 
 class _GatherMax(torch.autograd.Function):
@@ -117,8 +123,10 @@ class PointConv(nn.Module):
         if m1.slope is None or m2.slope != 1.0:
             raise RuntimeError("PointConv: weight_nn must keep the reference's (LeakyReLU, None) activations to be fused")
         b1, b2 = m1.bn.batch_norm, m2.bn.batch_norm
+        from .common import direct_grad_buffers
         return _PointConvFunction.apply(x, support, centres, neighbor_idx, m1.lin.weight, b1.weight, b1.bias, m2.lin.weight, b2.weight,
-                                        b2.bias, b1, b2, self.training, m1.slope)
+                                        b2.bias, b1, b2, self.training, m1.slope,
+                                        direct_grad_buffers(m1.lin.weight, b1.weight, b1.bias, m2.lin.weight, b2.weight, b2.bias))
 
 
 class ResNetBBlock(nn.Module):
@@ -231,4 +239,6 @@ class PointConvResNet(Base):
 def _classifier_head(lin: nn.Linear, x):
     """Final nn.Linear(128, n_classes) (point_conv_big.py:139) through the same kernels (plain Linear, bias, no BN)."""
     from .common import _LinearBNAct
-    return _LinearBNAct.apply(x, None, None, None, lin.weight, lin.bias, None, None, None, False, 1.0)
+    from .common import direct_grad_buffers
+    return _LinearBNAct.apply(x, None, None, None, lin.weight, lin.bias, None, None, None, False, 1.0,
+                              direct_grad_buffers(lin.weight, lin.bias, None, None))

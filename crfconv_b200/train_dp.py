@@ -88,7 +88,7 @@ def main(argv=None):
     dev = torch.device("cuda", local_rank)
     torch.manual_seed(0)                                                 # identical initial weights on every rank
     model = PointConvResNet(in_channels=6, n_classes=args.classes, use_crf=True, steps=1).to(dev).train()
-    grads = FlatGradients(model, extra=1)
+    grads = FlatGradients(model, extra=1, direct=True)
     opt = torch.optim.SGD(model.parameters(), lr=args.lr, momentum=args.momentum, weight_decay=args.weight_decay)
     sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=args.gamma)
     pos, feats, labels, gen = synthetic_shard(args.clouds_per_gpu, args.points, args.classes, dev, seed=1000 + rank)

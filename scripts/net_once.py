@@ -18,7 +18,7 @@ ncls = int(sys.argv[4]) if len(sys.argv) > 4 else 13
 dev = torch.device("cuda")
 torch.manual_seed(1234)
 net = PointConvResNet(6, ncls).to(dev).train()
-grads = FlatGradients(net)
+grads = FlatGradients(net, direct=True)
 pos, feat, lab, gen = train_dp.synthetic_shard(B, N, ncls, dev, seed=77)
 data = train_dp.make_batch(pos, feat, lab, generator=gen)
 target = (lab.reshape(-1) - 1).contiguous()

@@ -65,3 +65,35 @@ def test_graph_replay_matches_eager_gradients_for_the_full_network():
     loss2 = float(step.replay())
     ref2 = float(F.cross_entropy(model(data2), data2.y.reshape(-1) - 1))
     assert abs(loss2 - ref2) < 1e-3 * abs(ref2) and abs(loss2 - loss) > 1e-6
+
+
+def test_direct_gradient_accumulation_equals_autograd_accumulation():
+    """FlatGradients(direct=True): the backward kernels accumulate into the bound .grad views themselves; the gradients must equal
+    the ones autograd accumulates (same kernels, same order — only the per-parameter fill / add launches disappear)."""
+    import torch
+    import torch.nn.functional as F
+    from crfconv_b200 import train_dp
+    from crfconv_b200.distributed import FlatGradients
+    from crfconv_b200.point_conv_big import PointConvResNet
+    dev = torch.device("cuda")
+    torch.manual_seed(0)
+    net = PointConvResNet(6, 13).to(dev).train()
+    net.classifier[1].p = 0.0
+    pos, feat, lab, gen = train_dp.synthetic_shard(2, 2048, 13, dev, seed=5)
+    data = train_dp.make_batch(pos, feat, lab, generator=gen)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    flats = []
+    for direct in (False, True):
+        net.load_state_dict(sd)
+        for p in net.parameters():
+            p.grad = None
+            if hasattr(p, "_crf_direct_grad"):
+                del p._crf_direct_grad
+        fg = FlatGradients(net, direct=direct)
+        for _ in range(2):                      # second pass: buffers are re-zeroed and reused
+            fg.zero()
+            F.cross_entropy(net(data), lab.reshape(-1) - 1).backward()
+        flats.append(fg.flat.clone())
+    a, b = flats
+    assert float((a - b).abs().max()) <= 2e-4 * float(a.abs().max()), float((a - b).abs().max() / a.abs().max())
+    assert float(b.abs().max()) > 0
