@@ -51,6 +51,33 @@ struct Carver {
     }
 };
 
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------
+// A CRF layer step is ≈25 dependent kernels of 6-170 us; between two of them the GPU drains, launches, and runs the next kernel's
+// prologue (weight staging, TMEM allocation) before the first useful byte moves.  With PDL every kernel of the chain
+//   * calls pdl_trigger() first: the NEXT kernel in the stream may be scheduled as soon as all CTAs of this one have started and
+//     SM resources free up, so its launch latency and prologue overlap this kernel's tail (slow CTAs, last-CTA finalize);
+//   * calls pdl_wait() before it touches ANY global memory written by an earlier kernel of the stream (and before any global write):
+//     it returns once the preceding kernel has completed and its writes are visible.  Everything before the wait may only read
+//     parameters (weights) and write shared memory.
+// Every kernel launched through launch_k() executes pdl_wait(), which makes completion transitive along the chain.  Both
+// instructions are no-ops when the kernel was launched without the attribute.  Disabled by default; crfconv_fused_tune(1, 1) enables.
+inline int& pdl_flag() { static int v = 0; return v; }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_flag() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
 __device__ __forceinline__ float warp_sum(float v) {

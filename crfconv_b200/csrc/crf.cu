@@ -87,6 +87,8 @@ __device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a
 __global__ void __launch_bounds__(256) upsample_affine_kernel(const float* __restrict__ Hu, const float* __restrict__ scale,
                                                               const float* __restrict__ shift, const int64_t* __restrict__ up,
                                                               float* __restrict__ z, int64_t total, int64_t N, int64_t Nc, int F4) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total * F4) return;
     const int64_t m = i / F4;
@@ -138,6 +140,8 @@ __global__ void __launch_bounds__(256) step_fwd_kernel(const StepArgs a) {
     constexpr int LP = F / 4, PPW = 32 / LP;
     __shared__ __align__(16) float Cs[F * F];
     __shared__ __align__(16) float Ms[F * F];
+    pdl_trigger();
+    pdl_wait();
     for (int i = threadIdx.x; i < F * F; i += blockDim.x) { Cs[i] = a.Cm[i]; Ms[i] = a.Minv[i]; }
     __syncthreads();
     const int lane = lane_id();
@@ -386,6 +390,8 @@ __global__ void __launch_bounds__(128) step_bwd_reg_kernel(const StepArgs a) {
 // Cm = cᵀc ; Minv = (I + Cm)^{-1} by Gauss-Jordan (I + cᵀc is SPD with eigenvalues >= 1: no pivoting needed).
 __global__ void __launch_bounds__(256) compat_fwd_kernel(const float* __restrict__ c, float* __restrict__ Cm, float* __restrict__ Minv,
                                                          double* scratch, int F) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ double colp[128];
     __shared__ double piv;
     double* aug = scratch;   // [F][2F]
@@ -419,6 +425,8 @@ __global__ void __launch_bounds__(256) compat_fwd_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) compat_bwd_kernel(const float* __restrict__ c, const float* __restrict__ Minv,
                                                          const float* __restrict__ GC, const float* __restrict__ GM, float* Gc,
                                                          double* scratch, int F) {
+    pdl_trigger();
+    pdl_wait();
     double* T = scratch;            // T = Minvᵀ·GM
     double* G = scratch + F * F;    // G = GC − T·Minvᵀ
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -465,7 +473,7 @@ extern "C" {
 
 int crfconv_crf_compat_fwd(const float* c, float* Cm, float* Minv, double* scratch, int F, void* stream) {
     if (!c || !Cm || !Minv || !scratch || F <= 0 || F > 128) return CRF_ERR_INVALID_ARG;
-    mf::compat_fwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(c, Cm, Minv, scratch, F);
+    CRF_CUDA(launch_k(mf::compat_fwd_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, c, Cm, Minv, scratch, F));
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }
@@ -473,7 +481,7 @@ int crfconv_crf_compat_fwd(const float* c, float* Cm, float* Minv, double* scrat
 int crfconv_crf_compat_bwd(const float* c, const float* Minv, const float* GC, const float* GM, float* Gc, double* scratch, int F,
                            void* stream) {
     if (!c || !Minv || !GC || !GM || !Gc || !scratch || F <= 0 || F > 128) return CRF_ERR_INVALID_ARG;
-    mf::compat_bwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(c, Minv, GC, GM, Gc, scratch, F);
+    CRF_CUDA(launch_k(mf::compat_bwd_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, c, Minv, GC, GM, Gc, scratch, F));
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }
@@ -484,8 +492,8 @@ int crfconv_crf_upsample_fwd(const float* Hu, const float* scale, const float* s
     if (B < 0 || N < 0 || Nc <= 0 || F <= 0 || (F & 3)) return CRF_ERR_INVALID_ARG;
     const int64_t total = B * N;
     if (total == 0) return CRF_OK;
-    mf::upsample_affine_kernel<<<(unsigned)ceil_div(total * (F / 4), 256), 256, 0, (cudaStream_t)stream>>>(Hu, scale, shift, up_idx, z,
-                                                                                                    total, N, Nc, F / 4);
+    CRF_CUDA(launch_k(mf::upsample_affine_kernel, dim3((unsigned)ceil_div(total * (F / 4), 256)), dim3(256), 0, (cudaStream_t)stream, Hu, scale, shift,
+                      up_idx, z, total, N, Nc, F / 4));
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }
@@ -514,7 +522,7 @@ int crfconv_crf_step_fwd(const float* Hy, const float* scale_y, const float* z, 
         constexpr int FF = decltype(f)::value;
         constexpr int PPW = 32 / (FF / 4);
         const int64_t warps = ceil_div(a.total, PPW);
-        mf::step_fwd_kernel<FF><<<(unsigned)ceil_div(warps, 8), 256, 0, (cudaStream_t)stream>>>(a);
+        CRF_CUDA(launch_k(mf::step_fwd_kernel<FF>, dim3((unsigned)ceil_div(warps, 8)), dim3(256), 0, (cudaStream_t)stream, a));
         CRF_LAUNCH_CHECK();
         return CRF_OK;
     });

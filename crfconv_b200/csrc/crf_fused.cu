@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(kThreads, CIN > 64 ? 1 : 2) lin16_fwd_kernel(c
     __shared__ float s_part[kWarps][32];
     __shared__ double s_red[kThreads];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    pdl_trigger();
     // k-step s = 2j + h covers the physical columns {16j + 4t' + 2h, +1 : t' = 0..3}: fragment index k = t' ↔ column 16j+4t'+2h,
     // k = t'+4 ↔ the next column — exactly the (x,y) / (z,w) halves of the float4 a thread loads.
     for (int i = tid; i < NS * 2 * 32; i += kThreads) {
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(kThreads, CIN > 64 ? 1 : 2) lin16_fwd_kernel(c
         const int col = 16 * (s >> 1) + 4 * tt + 2 * (s & 1), n = nb * 8 + gg;
         store_split(Bh, Bl, i, __ldg(a.W + n * CIN + col), __ldg(a.W + n * CIN + col + 1));
     }
+    pdl_wait();                                                // weights above are parameters; everything below reads upstream results
     if (PRO) {
         for (int i = tid; i < CIN; i += kThreads) { s_sc[i] = a.pscale[i]; s_sh[i] = a.pshift[i]; }
     }
@@ -180,12 +182,14 @@ __global__ void __launch_bounds__(kThreads, 2) up16_fwd_kernel(const Up16FwdArgs
     __shared__ float s_part[2 * COUT];
     __shared__ double s_red[kThreads];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    pdl_trigger();
     for (int i = tid; i < 2 * NB * 32; i += kThreads) {
         const int s = i / (NB * 32), nb = (i / 32) % NB, gg = (i & 31) >> 2, tt = i & 3;
         const int in = 4 * tt + 2 * s, out = phys_col(nb, gg);
         store_split(Bh, Bl, i, __ldg(a.W + out * 16 + in), __ldg(a.W + out * 16 + in + 1));
     }
     for (int i = tid; i < 2 * COUT; i += kThreads) s_part[i] = 0.f;
+    pdl_wait();
     __syncthreads();
     float4 ssum[NQ], ssq[NQ];
 #pragma unroll
@@ -263,6 +267,7 @@ __global__ void __launch_bounds__(kThreads, 2) mid16_bwd_kernel(const Mid16BwdAr
     __shared__ float s_w[256];
     __shared__ double s_red[kThreads];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    pdl_trigger();
     // dgrad: contraction over the OUTPUT channel o of layer 2 (k-step s: k = t' ↔ o = 4t'+2s, k = t'+4 ↔ o = 4t'+2s+1), result
     // column n of block nb ↔ input channel phys_col(nb, n) ⇒ a thread ends up with input channels 4t..4t+3 of rows g, g+8.
     for (int i = tid; i < 2 * 2 * 32; i += kThreads) {
@@ -271,6 +276,7 @@ __global__ void __launch_bounds__(kThreads, 2) mid16_bwd_kernel(const Mid16BwdAr
         store_split(Bh, Bl, i, __ldg(a.W2 + o * 16 + in), __ldg(a.W2 + (o + 1) * 16 + in));
     }
     s_w[tid] = 0.f;
+    pdl_wait();
     __syncthreads();
     // row-major constants (channels 4t..4t+3)
     const float4 sc2 = ldg4(a.b2.sc + 4 * t), mu2 = ldg4(a.b2.mu + 4 * t), k12 = ldg4(a.b2.k1 + 4 * t);
@@ -395,11 +401,13 @@ __global__ void __launch_bounds__(kThreads, CIN > 64 ? 1 : 2) in16_dgrad_kernel(
     constexpr int NB = CIN / 8, NQ = CIN / 16;
     __shared__ float2 Bh[2 * NB * 32], Bl[2 * NB * 32];        // [k8 step][n block][lane]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    pdl_trigger();
     for (int i = tid; i < 2 * NB * 32; i += kThreads) {
         const int s = i / (NB * 32), nb = (i / 32) % NB, gg = (i & 31) >> 2, tt = i & 3;
         const int o = 4 * tt + 2 * s, in = phys_col(nb, gg);
         store_split(Bh, Bl, i, __ldg(a.W1 + o * CIN + in), __ldg(a.W1 + (o + 1) * CIN + in));
     }
+    pdl_wait();
     __syncthreads();
     const float4 sc = ldg4(a.b1.sc + 4 * t), mu = ldg4(a.b1.mu + 4 * t), k1 = ldg4(a.b1.k1 + 4 * t);
     const float4 c2 = mul4(ldg4(a.b1.is + 4 * t), ldg4(a.b1.k2 + 4 * t));
@@ -469,7 +477,9 @@ __global__ void __launch_bounds__(kThreads, CIN > 64 ? 1 : 2) in16_wgrad_kernel(
     constexpr int NB = CIN / 8;
     __shared__ float s_w[16 * CIN];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    pdl_trigger();
     for (int i = tid; i < 16 * CIN; i += kThreads) s_w[i] = 0.f;
+    pdl_wait();
     __syncthreads();
     float tsc[2], tmu[2], tk1[2], tc2[2];
 #pragma unroll
@@ -575,6 +585,8 @@ __global__ void __launch_bounds__(kThreads, 1) out_bwd_kernel(const OutBwdArgs a
     __shared__ __align__(16) float s_sc[64], s_sh[64], s_mu[64], s_is[64];
     __shared__ float s_acc[kOutPart];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    pdl_trigger();
+    pdl_wait();
     if (tid < 64) { s_sc[tid] = a.sc3[tid]; s_sh[tid] = a.sh3[tid]; s_mu[tid] = a.mu3[tid]; s_is[tid] = a.is3[tid]; }
     for (int i = tid; i < kOutPart; i += kThreads) s_acc[i] = 0.f;
     // B[k = channel][n ↔ x-channel phys_col(nb, n)] = sc3[ch]·W3[ch][x-channel];  k-step s = 2j+h: k = t' ↔ ch = 16j+4t'+2h, +1
@@ -833,6 +845,8 @@ __global__ void __launch_bounds__(128, MINB) step_bwd_kernel(const StepBwdArgs a
     __shared__ float s_gc[4][512];                               // per warp: running GC | GM (owned by the warp, no atomics)
     __shared__ float s_y[16];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_trigger();
+    pdl_wait();
     for (int i = tid; i < 256; i += 128) {
         const int r = i >> 4, c = i & 15;
         Cs[i] = a.Cm[i];
@@ -1014,6 +1028,8 @@ __global__ void __launch_bounds__(kThreads, 4) upsample_bwd_kernel(const UpBwdAr
     __shared__ float s_part[kWarps][32];
     __shared__ double s_red[kThreads];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = lane & 3, c0 = 4 * sub;
+    pdl_trigger();
+    pdl_wait();
     const float4 mu = ldg4(a.mu + c0), is = ldg4(a.is + c0);
     float4 s1 = zero4(), s2 = zero4();
     const int64_t nthr = (int64_t)gridDim.x * kThreads;
@@ -1044,7 +1060,7 @@ __global__ void __launch_bounds__(kThreads, 4) upsample_bwd_kernel(const UpBwdAr
         bn_bwd_finalize(a.fin, s_red[tid], s_red[16 + tid], tid);
 }
 
-static int g_tune[8] = {2, 0, 0, 0, 0, 0, 0, 0};   // [0] CTAs/SM of step_bwd
+static int g_tune[8] = {2, 0, 0, 0, 0, 0, 0, 0};   // [0] CTAs/SM of step_bwd, [1] programmatic dependent launch on/off
 
 inline int grid_for(int64_t units, int per_cta, int ctas_per_sm) {
     const int64_t want = ceil_div(units, per_cta);
@@ -1068,6 +1084,7 @@ int crfconv_fused_tune(int key, int value) {
     if (key < 0 || key >= 8) return -1;
     const int prev = g_tune[key];
     g_tune[key] = value;
+    if (key == 1) pdl_flag() = value ? 1 : 0;
     return prev;
 }
 
@@ -1085,11 +1102,11 @@ int crfconv_lin16_fwd(const float* X, int Cin, const float* W, const float* psca
     const int64_t tiles = ceil_div(M, 16);
     if (Cin == 16) {
         if (!pscale || !pshift) return CRF_ERR_INVALID_ARG;
-        lin16_fwd_kernel<16, true><<<grid_for(tiles, kWarps * 4, 2), kThreads, 0, st>>>(a);
+        CRF_CUDA(launch_k(lin16_fwd_kernel<16, true>, dim3(grid_for(tiles, kWarps * 4, 2)), dim3(kThreads), 0, st, a));
     } else if (Cin == 64 && !pscale) {
-        lin16_fwd_kernel<64, false><<<grid_for(tiles, kWarps * 2, 2), kThreads, 0, st>>>(a);
+        CRF_CUDA(launch_k(lin16_fwd_kernel<64, false>, dim3(grid_for(tiles, kWarps * 2, 2)), dim3(kThreads), 0, st, a));
     } else if (Cin == 128 && !pscale) {
-        lin16_fwd_kernel<128, false><<<grid_for(tiles, kWarps * 2, 1), kThreads, 0, st>>>(a);
+        CRF_CUDA(launch_k(lin16_fwd_kernel<128, false>, dim3(grid_for(tiles, kWarps * 2, 1)), dim3(kThreads), 0, st, a));
     } else {
         return CRF_ERR_UNSUPPORTED;
     }
@@ -1106,7 +1123,7 @@ int crfconv_up16_fwd(const float* X, const float* W, int Cout, float* Y, int64_t
     Up16FwdArgs a{};
     a.X = X; a.W = W; a.Y = Y; a.M = M;
     a.fin = FwdFin{stats, counter, gamma, beta, running_mean, running_var, eps, momentum, (double)M, scale, shift, mean, invstd};
-    up16_fwd_kernel<64><<<grid_for(ceil_div(M, 16), kWarps * 2, 2), kThreads, 0, (cudaStream_t)stream>>>(a);
+    CRF_CUDA(launch_k(up16_fwd_kernel<64>, dim3(grid_for(ceil_div(M, 16), kWarps * 2, 2)), dim3(kThreads), 0, (cudaStream_t)stream, a));
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }
@@ -1123,7 +1140,7 @@ int crfconv_mid16_bwd(const float* dY, const float* H2, const float* sc2, const 
     a.H1 = H1; a.sc1 = sc1; a.sh1 = sh1; a.mu1 = mu1; a.is1 = is1; a.slope1 = slope1;
     a.W2 = W2; a.dV1 = dV1; a.dW2 = dW2; a.slot_stride = slot_stride; a.M = M;
     a.fin = BwdFin{part, counter, (double)M, k1_1, k2_1, dgamma1, dbeta1};
-    mid16_bwd_kernel<<<grid_for(ceil_div(M, 16), kWarps * 4, 2), kThreads, 0, (cudaStream_t)stream>>>(a);
+    CRF_CUDA(launch_k(mid16_bwd_kernel, dim3(grid_for(ceil_div(M, 16), kWarps * 4, 2)), dim3(kThreads), 0, (cudaStream_t)stream, a));
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }
@@ -1136,11 +1153,11 @@ int crfconv_in16_dgrad(const float* dV1, const float* H1, const float* sc1, cons
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t tiles = ceil_div(M, 16);
     if (Cin == 64) {
-        if (accumulate) in16_dgrad_kernel<64, true><<<grid_for(tiles, kWarps * 2, 2), kThreads, 0, st>>>(a);
-        else in16_dgrad_kernel<64, false><<<grid_for(tiles, kWarps * 2, 2), kThreads, 0, st>>>(a);
+        if (accumulate) CRF_CUDA(launch_k(in16_dgrad_kernel<64, true>, dim3(grid_for(tiles, kWarps * 2, 2)), dim3(kThreads), 0, st, a));
+        else CRF_CUDA(launch_k(in16_dgrad_kernel<64, false>, dim3(grid_for(tiles, kWarps * 2, 2)), dim3(kThreads), 0, st, a));
     } else if (Cin == 128) {
-        if (accumulate) in16_dgrad_kernel<128, true><<<grid_for(tiles, kWarps * 2, 1), kThreads, 0, st>>>(a);
-        else in16_dgrad_kernel<128, false><<<grid_for(tiles, kWarps * 2, 1), kThreads, 0, st>>>(a);
+        if (accumulate) CRF_CUDA(launch_k(in16_dgrad_kernel<128, true>, dim3(grid_for(tiles, kWarps * 2, 1)), dim3(kThreads), 0, st, a));
+        else CRF_CUDA(launch_k(in16_dgrad_kernel<128, false>, dim3(grid_for(tiles, kWarps * 2, 1)), dim3(kThreads), 0, st, a));
     } else {
         return CRF_ERR_UNSUPPORTED;
     }
@@ -1155,8 +1172,8 @@ int crfconv_in16_wgrad(const float* dV1, const float* H1, const float* sc1, cons
     In16WgradArgs a{dV1, H1, BnB{sc1, mu1, is1, k1, k2}, X, dW, slot_stride, M};
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t steps = ceil_div(M, 16);
-    if (Cin == 64) in16_wgrad_kernel<64><<<grid_for(steps, kWarps * 2, 2), kThreads, 0, st>>>(a);
-    else if (Cin == 128) in16_wgrad_kernel<128><<<grid_for(steps, kWarps * 2, 1), kThreads, 0, st>>>(a);
+    if (Cin == 64) CRF_CUDA(launch_k(in16_wgrad_kernel<64>, dim3(grid_for(steps, kWarps * 2, 2)), dim3(kThreads), 0, st, a));
+    else if (Cin == 128) CRF_CUDA(launch_k(in16_wgrad_kernel<128>, dim3(grid_for(steps, kWarps * 2, 1)), dim3(kThreads), 0, st, a));
     else return CRF_ERR_UNSUPPORTED;
     CRF_LAUNCH_CHECK();
     return CRF_OK;
@@ -1178,7 +1195,7 @@ int crfconv_out16_bwd(const float* dO, const float* H3, const float* sc3, const 
         CRF_CUDA(cudaFuncSetAttribute(out_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOutSmem));
         attr_set = true;
     }
-    out_bwd_kernel<<<grid_for(ceil_div(M, 16), kWarps * 2, 1), kThreads, kOutSmem, (cudaStream_t)stream>>>(a);
+    CRF_CUDA(launch_k(out_bwd_kernel, dim3(grid_for(ceil_div(M, 16), kWarps * 2, 1)), dim3(kThreads), kOutSmem, (cudaStream_t)stream, a));
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }
@@ -1200,8 +1217,8 @@ int crfconv_crf_step_bwd_fused(const float* Hy, const float* sc_y, const float* 
     a.xT = xT; a.Q = Q; a.a0 = a0; a.Gz = Gz; a.gz_acc = gz_acc; a.gprev = gprev; a.Gy = Gy; a.GC = GC; a.GM = GM;
     a.slot_stride = slot_stride; a.ysum = ysum; a.total = B * N; a.N = N;
     a.finalize = finalize; a.counter = counter; a.count = (double)(B * N); a.gamma_y = gamma_y; a.k1 = k1; a.k2 = k2; a.dgamma = dgamma; a.dbeta = dbeta;
-    if (g_tune[0] == 3) step_bwd_kernel<3><<<grid_for(ceil_div(a.total, 8), 4 * 4, 3), 128, 0, (cudaStream_t)stream>>>(a);
-    else step_bwd_kernel<2><<<grid_for(ceil_div(a.total, 8), 4 * 4, 2), 128, 0, (cudaStream_t)stream>>>(a);
+    if (g_tune[0] == 3) CRF_CUDA(launch_k(step_bwd_kernel<3>, dim3(grid_for(ceil_div(a.total, 8), 4 * 4, 3)), dim3(128), 0, (cudaStream_t)stream, a));
+    else CRF_CUDA(launch_k(step_bwd_kernel<2>, dim3(grid_for(ceil_div(a.total, 8), 4 * 4, 2)), dim3(128), 0, (cudaStream_t)stream, a));
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }
@@ -1214,7 +1231,7 @@ int crfconv_crf_upsample_bwd_fused(const float* Gz, const float* G0, const int64
     UpBwdArgs a{};
     a.Gz = Gz; a.G0 = G0; a.up = up_idx; a.Hu = Hu; a.mu = mu; a.is = is; a.Gu = Gu; a.total = B * N; a.N = N; a.Nc = Nc;
     a.fin = BwdFin{part, counter, (double)(B * Nc), k1, k2, dgamma, dbeta};
-    upsample_bwd_kernel<<<grid_for(a.total * 4, kThreads * 4, 3), kThreads, 0, (cudaStream_t)stream>>>(a);
+    CRF_CUDA(launch_k(upsample_bwd_kernel, dim3(grid_for(a.total * 4, kThreads * 4, 3)), dim3(kThreads), 0, (cudaStream_t)stream, a));
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }

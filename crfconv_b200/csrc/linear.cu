@@ -235,6 +235,8 @@ __global__ void __launch_bounds__(128) bn_finalize_fwd_kernel(const float* __res
 __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict__ H, const float* __restrict__ scale,
                                                          const float* __restrict__ shift, const float* __restrict__ R,
                                                          float slope, float* __restrict__ Y, int64_t total4, int C4) {
+    pdl_trigger();
+    pdl_wait();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % C4) * 4;
         const float4 h = __ldg(reinterpret_cast<const float4*>(H) + i);
@@ -261,6 +263,8 @@ __device__ __forceinline__ float bn_dv(float dy, float h, float ref, bool has_re
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ dY, const float* __restrict__ H, BnBwd bn,
                                                             float* __restrict__ sums, int64_t M, int C, const cl::BwdFin fin) {
     __shared__ float red[256 * 8];
+    pdl_trigger();
+    pdl_wait();
     const int C4 = C >> 2;
     const int tpr = C4;                           // threads per row
     const int rows_per_it = 256 / tpr;            // C4 divides 256 for C in {8,...,1024}
@@ -340,6 +344,8 @@ __global__ void __launch_bounds__(128) bn_finalize_bwd_kernel(const float* __res
 
 // dW[i] += Σ_slots scratch[slot][i]   (fixed order ⇒ deterministic for a given launch configuration)
 __global__ void __launch_bounds__(256) grad_slots_reduce_kernel(const float* __restrict__ scratch, float* dW, int n, int64_t stride) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float s = 0.f;
@@ -750,7 +756,7 @@ int crfconv_bn_act_fwd(const float* H, const float* scale, const float* shift, c
     if (M == 0) return CRF_OK;
     const int64_t total4 = M * (C / 4);
     const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(total4, 256), (int64_t)kNumSMs * 16);
-    lin::bn_act_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(H, scale, shift, R, slope, Y, total4, C / 4);
+    CRF_CUDA(launch_k(lin::bn_act_fwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, H, scale, shift, R, slope, Y, total4, C / 4));
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }
@@ -780,7 +786,7 @@ int crfconv_bn_finalize_bwd(const float* sums, int64_t count, float* k1, float* 
 int crfconv_grad_slots_reduce(const float* scratch, float* dW, int64_t n, int64_t stride, void* stream) {
     if (n < 0 || !scratch || !dW || stride < n) return CRF_ERR_INVALID_ARG;
     if (n == 0) return CRF_OK;
-    lin::grad_slots_reduce_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(scratch, dW, (int)n, stride);
+    CRF_CUDA(launch_k(lin::grad_slots_reduce_kernel, dim3((unsigned)ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream, scratch, dW, (int)n, stride));
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }
@@ -890,7 +896,8 @@ int crfconv_bn_bwd_reduce_fin(const float* dY, const float* H, const float* act_
     const int rows_per_it = 256 / (C / 4);
     // 84 registers x 256 threads: 3 CTAs are resident per SM — exactly one wave (a 4th CTA per SM would run alone in a second wave)
     const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(M, rows_per_it * 8), (int64_t)kNumSMs * 3);   // <= cl::kMaxTicketGrid
-    lin::bn_bwd_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dY, H, bn, sums, M, C, cl::BwdFin{sums, counter, (double)M, k1, k2, dgamma, dbeta});
+    CRF_CUDA(launch_k(lin::bn_bwd_reduce_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, dY, H, bn, sums, M, C,
+                      cl::BwdFin{sums, counter, (double)M, k1, k2, dgamma, dbeta}));
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }

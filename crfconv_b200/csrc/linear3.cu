@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd3_kernel(const FwdArgs a, cons
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pdl_trigger();                                                 // (common.cuh) the weight staging below overlaps the previous kernel's tail
     if (warp == 0) tmem_alloc(tmem_slot, L::kTmemCols);
     if (tid == kEpiWarps * 32) {
         for (int i = 0; i < RING; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd3_kernel(const FwdArgs a, cons
             }
         }
     }
+    pdl_wait();                                                    // weights are parameters; scale1 / shift1 and the activations are upstream results
     for (int k = tid; k < Kpad; k += kThreads) {
         float sc = 1.f, sh = 0.f;
         if (a.scale1 && k < nch1 * BK && k < a.C1) { sc = __ldg(a.scale1 + k); sh = __ldg(a.shift1 + k); }
@@ -407,8 +409,7 @@ bool try_fwd3(const FwdArgs& a, int precision, cudaStream_t st, int* rc) {
         const size_t smem = Layout<BN>::bytes(nch);
         cudaError_t e = cudaFuncSetAttribute(fwd3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) {
-            fwd3_kernel<BN><<<std::min(ntiles, kNumSMs), kThreads, smem, st>>>(a, ntiles);
-            e = cudaPeekAtLastError();
+            e = launch_k(fwd3_kernel<BN>, dim3(std::min(ntiles, kNumSMs)), dim3(kThreads), smem, st, a, ntiles);
         }
         if (e != cudaSuccess) *rc = (int)e;
         return true;

@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad3_kernel(const DgradArgs a, 
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool plain = a.bn.scale == nullptr;
+    pdl_trigger();
     if (warp == 0) tmem_alloc(tmem_slot, L::kTmemCols);
     if (tid == kEpiWarps * 32) {
         for (int i = 0; i < RING; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad3_kernel(const DgradArgs a, 
             }
         }
     }
+    pdl_wait();                                                    // W is a parameter; the BatchNorm constants, dY and H are upstream results
     for (int k = tid; k < Kpad; k += kThreads) {
         float sc = 1.f, sh = 0.f, pz = 0.f, pw = 0.f;
         if (!plain && k < C) {
@@ -279,8 +281,7 @@ bool try_dgrad3(const DgradArgs& a, int precision, cudaStream_t st, int* rc) {
         const size_t smem = Layout<BN>::bytes(nch);
         cudaError_t e = cudaFuncSetAttribute(dgrad3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) {
-            dgrad3_kernel<BN><<<std::min(ntiles, kNumSMs), kThreads, smem, st>>>(a, ntiles);
-            e = cudaPeekAtLastError();
+            e = launch_k(dgrad3_kernel<BN>, dim3(std::min(ntiles, kNumSMs)), dim3(kThreads), smem, st, a, ntiles);
         }
         if (e != cudaSuccess) *rc = (int)e;
         return true;

@@ -74,12 +74,14 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3_kernel(const WgradArgs a, 
     const int T = 2 * (nchX + NB);                                            // tasks per stage
     const bool plain = a.bn.scale == nullptr;
 
+    pdl_trigger();
     if (warp == 0) tmem_alloc(tmem_slot, L::kTmemCols);
     if (tid == kEpiWarps * 32) {
         for (int i = 0; i < 2; ++i) { mbar_init(full + i, (uint32_t)T); mbar_init(empty + i, 1); }
         mbar_init(done, 1);
         mbar_init_fence();
     }
+    pdl_wait();
     for (int k = tid; k < BN; k += kThreads) {
         float sc = 1.f, sh = 0.f, pz = 0.f, pw = 0.f;
         if (!plain && k < C) {
@@ -287,8 +289,7 @@ bool try_wgrad3(const WgradArgs& a, int precision, cudaStream_t st, int* rc) {
         const size_t smem = Layout<BN>::bytes();
         cudaError_t e = cudaFuncSetAttribute(wgrad3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) {
-            wgrad3_kernel<BN><<<std::min(ntiles, kNumSMs), kThreads, smem, st>>>(a, ntiles);
-            e = cudaPeekAtLastError();
+            e = launch_k(wgrad3_kernel<BN>, dim3(std::min(ntiles, kNumSMs)), dim3(kThreads), smem, st, a, ntiles);
         }
         if (e != cudaSuccess) *rc = (int)e;
         return true;

@@ -79,6 +79,14 @@ def test_direct_gradient_accumulation_equals_autograd_accumulation():
     torch.manual_seed(0)
     net = PointConvResNet(6, 13).to(dev).train()
     net.classifier[1].p = 0.0
+    # kink-free (all LeakyReLU slopes 1): two runs of the same network differ in the last bit of their BatchNorm statistics (atomics),
+    # and a LeakyReLU kink flip between the runs would swamp the comparison
+    from crfconv_b200 import point_conv_big as pcb
+    for m in net.modules():
+        if isinstance(m, torch.nn.LeakyReLU):
+            m.negative_slope = 1.0
+        if isinstance(m, pcb.ResNetBBlock):
+            m.negative_slope = 1.0
     pos, feat, lab, gen = train_dp.synthetic_shard(2, 2048, 13, dev, seed=5)
     data = train_dp.make_batch(pos, feat, lab, generator=gen)
     sd = {k: v.clone() for k, v in net.state_dict().items()}
