@@ -88,8 +88,6 @@ def lib():
             fn = getattr(handle, name)      # AttributeError here = header / library mismatch: fail loudly
             fn.restype, fn.argtypes = res, args
         _lib = handle
-        if os.environ.get("CRFCONV_PDL", "0") == "1":        # programmatic dependent launch for the kernels of the CRF layer (csrc/common.cuh)
-            handle.crfconv_fused_tune(1, 1)
     return _lib
 
 

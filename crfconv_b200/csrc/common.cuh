@@ -61,7 +61,10 @@ struct Carver {
 //     it returns once the preceding kernel has completed and its writes are visible.  Everything before the wait may only read
 //     parameters (weights) and write shared memory.
 // Every kernel launched through launch_k() executes pdl_wait(), which makes completion transitive along the chain.  Both
-// instructions are no-ops when the kernel was launched without the attribute.  Disabled by default; crfconv_fused_tune(1, 1) enables.
+// instructions are no-ops when the kernel was launched without the attribute.
+// MEASURED AND REJECTED (round 2, profiles/README_r02.md): with the attribute on, the S1 step went from 0.775 to 0.812 ms — the CTAs
+// of the next kernel sit on the SMs spinning in griddepcontrol.wait and crowd out the kernels of the parallel graph branches (unary
+// chain, compatibility algebra).  Kept as an experiment knob only: crfconv_fused_tune(1, 1); off by default.
 inline int& pdl_flag() { static int v = 0; return v; }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
