@@ -1,0 +1,77 @@
+"""Worker of tests/test_multi_gpu.py (launched with torch.distributed.run, one rank per GPU): SURVEY.md §8(e) option (i).
+
+Every rank runs the CRF layer on ITS shard of the clouds (different seeds), all-reduces the flat gradient with the product's
+FlatGradients (ONE NCCL collective, ReduceOp.AVG) and also runs the CPU oracle on its shard.  Checked on every rank:
+  * all-reduced gradient == mean over ranks of the per-shard PRODUCT gradients (gathered before the reduce)     — exact to 1e-6
+  * all-reduced gradient == mean over ranks of the per-shard ORACLE gradients                                  — 1e-3 (north_star)
+  * replicas stay bit-identical after the reduce."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from crfconv_b200.continuous_crf_conv_big import ContinuousGaussianCRFConv
+from crfconv_b200.distributed import FlatGradients, init_from_env
+from crfconv_b200 import nearest_neighbors
+from oracle import layers as ol
+from oracle import synthetic
+
+
+def main():
+    rank, local_rank, world = init_from_env("nccl")
+    dev = torch.device("cuda", local_rank)
+    torch.manual_seed(0)                                     # identical parameters on every rank
+    ref = ol.ContinuousGaussianCRFConv(128, 64, 64, steps=1).train()
+    with torch.no_grad():
+        ref.c.add_(0.1 * torch.randn(16, 16))
+    mine = ContinuousGaussianCRFConv(128, 64, 64, steps=1)
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.to(dev).train()
+    B, N = 2, 8192                                           # this rank's shard: 2 clouds of its own
+    inp = synthetic.crf_layer_inputs(B, N, 16, 128, 64, 4, seed=100 + rank, knn_batch_fn=nearest_neighbors.knn_batch)
+    cot = torch.randn(B, N, 64, generator=torch.Generator().manual_seed(7 + rank))
+    # oracle on this shard (CPU)
+    out0 = ref(inp.unary, inp.pairwise, inp.up_idx, inp.neighbor_idx)
+    (out0 * cot).sum().backward()
+    og = torch.cat([p.grad.reshape(-1) for p in ref.parameters()]).to(dev)
+    # product on this shard
+    fg = FlatGradients(mine, bind=False)
+    fg.zero()
+    out1 = mine(inp.unary.to(dev), inp.pairwise.to(dev), inp.up_idx.to(dev), inp.neighbor_idx.to(dev))
+    (out1 * cot.to(dev)).sum().backward()
+    local = torch.cat([p.grad.reshape(-1) for p in mine.parameters()]).clone()
+    gathered = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    ogs = [torch.empty_like(og) for _ in range(world)]
+    dist.all_gather(ogs, og)
+    fg.all_reduce()                                          # the product's collective (averages)
+    reduced = torch.cat([p.grad.reshape(-1) for p in mine.parameters()])
+    mean_prod = torch.stack(gathered).double().mean(0)
+    mean_orac = torch.stack(ogs).double().mean(0)
+    scale = float(mean_orac.abs().max())
+    e_exact = float((reduced.double() - mean_prod).abs().max()) / scale
+    # per-parameter comparison with the oracle mean (relative to the largest parameter gradient, like the single-GPU tests)
+    errs, off = {}, 0
+    for n, p in mine.named_parameters():
+        k = p.numel()
+        a, b = reduced[off:off + k].double(), mean_orac[off:off + k]
+        errs[n] = float((a - b).norm() / max(float(b.norm()), 1e-3 * scale * k ** 0.5))
+        off += k
+    same = reduced.clone()
+    dist.broadcast(same, 0)
+    ok = e_exact < 1e-6 and max(errs.values()) < 1e-3 and torch.equal(same, reduced)
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"MULTI_GPU_PARITY world={world} exact={e_exact:.2e} oracle_max_rel_l2={max(errs.values()):.2e} "
+              f"worst={max(errs, key=errs.get)} ok={bool(flag.item())}", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()
