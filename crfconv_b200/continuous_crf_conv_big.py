@@ -238,6 +238,18 @@ class _CRFConvFunction(torch.autograd.Function):
                 None, None, *_param_grads(ctx.gbuf, [Gc, *grads]))
 
 
+import os as _os
+WGRAD_BRANCH = _os.environ.get("CRFCONV_WGRAD_BRANCH", "1") != "0"   # fusion_nn's weight gradient on its own stream / graph branch (fused path)
+_WGRAD = {}
+
+
+def _wgrad_stream(dev):
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _WGRAD:
+        _WGRAD[key] = torch.cuda.Stream(device=dev)
+    return _WGRAD[key]
+
+
 _THIRD = {}
 
 
@@ -386,7 +398,20 @@ class _CRFConvFusedFunction(torch.autograd.Function):
         ops.bn_backward_prepare_fin(g2, Hf, sf, sl[5], dg["f"], db["f"], sums_f, cnt[0])
         dO = torch.empty((M, Co), dtype=torch.float32, device=dev)
         dP = torch.empty((M, Cp), dtype=torch.float32, device=dev)
-        ops.linear_bwd(g2, Hf, sf, sl[5], H3, Wf, scale1=so.scale, shift1=so.shift, slope1=sl[4], X2=P, dX1=dO, dX2=dP, dW=dW["f"], scratch=scr(dW["f"]), scratch_stride=n_small)
+        main = torch.cuda.current_stream(dev)
+        if WGRAD_BRANCH:
+            # fusion_nn's weight gradient (82 us) feeds nothing but the final fold: it runs on its own graph branch, off the critical path
+            # dOut → dO → out_nn → mean field → pairwise chain
+            wstream = _wgrad_stream(dev)
+            fork_w, join_w = torch.cuda.Event(), torch.cuda.Event()
+            fork_w.record(main)
+            wstream.wait_event(fork_w)
+            with torch.cuda.stream(wstream):
+                ops.linear_bwd(g2, Hf, sf, sl[5], H3, Wf, scale1=so.scale, shift1=so.shift, slope1=sl[4], X2=P, dW=dW["f"], scratch=scr(dW["f"]), scratch_stride=n_small)
+                join_w.record(wstream)
+            ops.linear_bwd(g2, Hf, sf, sl[5], H3, Wf, scale1=so.scale, shift1=so.shift, slope1=sl[4], X2=P, dX1=dO, dX2=dP)
+        else:
+            ops.linear_bwd(g2, Hf, sf, sl[5], H3, Wf, scale1=so.scale, shift1=so.shift, slope1=sl[4], X2=P, dX1=dO, dX2=dP, dW=dW["f"], scratch=scr(dW["f"]), scratch_stride=n_small)
         # out_nn (:74) in one pass over dO
         Q, a0 = torch.empty((F, F), dtype=torch.float32, device=dev), torch.empty(F, dtype=torch.float32, device=dev)
         T = ops.out16_bwd(dO, H3, so, sl[4], xs[-1], Wo, out_part, cnt[1], dg["o"], db["o"], dW["o"], Q, a0)
@@ -405,7 +430,6 @@ class _CRFConvFusedFunction(torch.autograd.Function):
         aux = _aux_stream(dev)
         fork_aux, join_aux = torch.cuda.Event(), torch.cuda.Event()
         bscr = torch.empty(3 * F * F, dtype=torch.float64, device=dev)
-        main = torch.cuda.current_stream(dev)
         fork_aux.record(main)
         aux.wait_event(fork_aux)
         with torch.cuda.stream(aux):                             # off the critical path: Gc is only needed when backward returns
@@ -440,6 +464,8 @@ class _CRFConvFusedFunction(torch.autograd.Function):
         main.wait_event(join)
         main.wait_event(join3)
         main.wait_event(join_aux)
+        if WGRAD_BRANCH:
+            main.wait_event(join_w)
         ops.grad_slots_reduce(wscr[2 * F * F:], small[2 * F * F:], n_small - 2 * F * F, n_small)   # all weight gradients, one launch
         grads = []
         for k in ("1u", "2u", "1p", "2p", "o", "f"):

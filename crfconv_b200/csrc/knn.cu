@@ -227,6 +227,7 @@ struct TopK {   // one slot per lane, ascending (d, i) by lane; slot K-1 is the 
 
 // (ld, li): lower threshold of a multi-pass search — only candidates strictly greater than it in (d, index) order may enter
 // (first pass: ld = -1, nothing is excluded since distances are >= 0).
+template <bool GENERAL>
 __device__ __forceinline__ void scan_range(int s, int e, float qx, float qy, float qz,
                                            const float4* __restrict__ sorted, TopK& t, int K, int lane, float ld = -1.0f, int li = -1,
                                            float r2 = -1.0f) {
@@ -240,9 +241,10 @@ __device__ __forceinline__ void scan_range(int s, int e, float qx, float qy, flo
             idx = __float_as_int(v.w);
             // radius mode (r2 >= 0): every support point within the radius gets the same key 0, so the (d, index) order below keeps
             // the K SMALLEST INDICES among them — torch_cluster's "first max_num_neighbors in index order"
-            if (r2 >= 0.0f) { if (d <= r2) d = 0.0f; else { d = INFINITY; idx = 0x7fffffff; } }
+            if (GENERAL && r2 >= 0.0f) { if (d <= r2) d = 0.0f; else { d = INFINITY; idx = 0x7fffffff; } }
         }
-        const bool pass = ((d < t.kth_d) || (d == t.kth_d && idx < t.kth_i)) && ((d > ld) || (d == ld && idx > li));
+        bool pass = (d < t.kth_d) || (d == t.kth_d && idx < t.kth_i);
+        if (GENERAL) pass = pass && ((d > ld) || (d == ld && idx > li));
         unsigned m = __ballot_sync(0xffffffffu, pass);
         while (m) {
             const int src = __ffs(m) - 1;
@@ -264,7 +266,9 @@ __device__ __forceinline__ void scan_range(int s, int e, float qx, float qy, flo
 
 // SELF = queries are the support points themselves (same buffer): queries are then taken in CELL order from the sorted records,
 // so the warps of a CTA search neighbouring cells and share their point ranges through L1; results go to the original row.
-template <bool SELF>
+// GENERAL = false: the plain K <= 32 search (one pass, no radius) — the hot path of the multiscale builder, kept free of the
+// threshold / radius logic; GENERAL = true: passes of 32 for K > 32 and the radius mode.
+template <bool SELF, bool GENERAL>
 __global__ void __launch_bounds__(256, 4) query_kernel(const float4* __restrict__ sorted_all,
                                                     const int* __restrict__ cell_start_all,
                                                     const Grid* __restrict__ grids, const float* __restrict__ edges,
@@ -299,8 +303,8 @@ __global__ void __launch_bounds__(256, 4) query_kernel(const float4* __restrict_
     // (each pass restarts from the query's own cell; the stopping rule below holds for the filtered candidate set as well)
     float ld = -1.0f;
     int li = -1;
-    for (int k0 = 0; k0 < K; k0 += 32) {
-    const int Kp = min(32, K - k0);
+    for (int k0 = 0; k0 < (GENERAL ? K : 1); k0 += 32) {
+    const int Kp = GENERAL ? min(32, K - k0) : K;
     TopK t;
     t.d = INFINITY; t.i = 0x7fffffff; t.kth_d = INFINITY; t.kth_i = 0x7fffffff;
 
@@ -330,8 +334,8 @@ __global__ void __launch_bounds__(256, 4) query_kernel(const float4* __restrict_
             for (int l = 0; l < nb; ++l) {
                 const int a0 = __shfl_sync(0xffffffffu, sA, l), a1 = __shfl_sync(0xffffffffu, eA, l);
                 const int b0 = __shfl_sync(0xffffffffu, sB, l), b1 = __shfl_sync(0xffffffffu, eB, l);
-                if (a1 > a0) scan_range(a0, a1, qx, qy, qz, sorted, t, Kp, lane, ld, li, r2);
-                if (b1 > b0) scan_range(b0, b1, qx, qy, qz, sorted, t, Kp, lane, ld, li, r2);
+                if (a1 > a0) scan_range<GENERAL>(a0, a1, qx, qy, qz, sorted, t, Kp, lane, ld, li, r2);
+                if (b1 > b0) scan_range<GENERAL>(b0, b1, qx, qy, qz, sorted, t, Kp, lane, ld, li, r2);
             }
         }
         // lower bound on the computed distance of every point outside the visited box
@@ -343,7 +347,7 @@ __global__ void __launch_bounds__(256, 4) query_kernel(const float4* __restrict_
         if (cz + r + 1 <= nz - 1) bound = fminf(bound, fmaxf(0.0f, __fsub_rn(__ldg(lo_edge + 2 * kMaxDim + cz + r + 1), qz)));
         if (cz - r - 1 >= 0)      bound = fminf(bound, fmaxf(0.0f, __fsub_rn(qz, __ldg(hi_edge + 2 * kMaxDim + cz - r - 1))));
         if (bound == INFINITY) break;                       // the whole grid has been visited
-        if (r2 >= 0.0f) {                                   // radius mode: stop once every unvisited point is farther than the radius
+        if (GENERAL && r2 >= 0.0f) {                        // radius mode: stop once every unvisited point is farther than the radius
             if (__fmul_rn(bound, bound) > r2) break;
             continue;
         }
@@ -351,8 +355,9 @@ __global__ void __launch_bounds__(256, 4) query_kernel(const float4* __restrict_
     }
     if (lane < Kp) {
         // K > N: unfilled slots keep 0, the observable behaviour of the reference's cpp_knn_omp (knn_.cxx:59,65-67)
-        out[((size_t)b * Q + out_row) * K + k0 + lane] = (t.i == 0x7fffffff) ? (r2 >= 0.0f ? -1 : 0) : (int64_t)t.i;   // radius mode pads with -1
+        out[((size_t)b * Q + out_row) * K + k0 + lane] = (t.i == 0x7fffffff) ? ((GENERAL && r2 >= 0.0f) ? -1 : 0) : (int64_t)t.i;   // radius mode pads with -1
     }
+    if (!GENERAL) break;
     ld = __shfl_sync(0xffffffffu, t.d, Kp - 1);
     li = __shfl_sync(0xffffffffu, t.i, Kp - 1);
     if (li == 0x7fffffff) {                                  // the cloud is exhausted: remaining slots are 0
@@ -616,12 +621,14 @@ static int knn_search(const float* pts, int64_t B, int64_t N, const float* queri
     knn::count_kernel<<<dim3((unsigned)ceil_div(N, 256), (unsigned)B), 256, 0, st>>>(pts, grids, cell_of, cell_start, (int)N, cap);
     knn::scan_kernel<<<(unsigned)B, 1024, 0, st>>>(cell_start, grids, cap);
     knn::scatter_kernel<<<dim3((unsigned)ceil_div(N, 256), (unsigned)B), 256, 0, st>>>(pts, cell_of, cell_start, cursor, sorted, (int)N, cap);
-    if (queries == pts && Q == N)
-        knn::query_kernel<true><<<dim3((unsigned)ceil_div(Q, 8), (unsigned)B), 256, 0, st>>>(sorted, cell_start, grids, edges, queries, out_idx,
-                                                                                         (int)N, (int)Q, (int)K, cap, r2);
-    else
-        knn::query_kernel<false><<<dim3((unsigned)ceil_div(Q, 8), (unsigned)B), 256, 0, st>>>(sorted, cell_start, grids, edges, queries, out_idx,
-                                                                                          (int)N, (int)Q, (int)K, cap, r2);
+    const bool self = queries == pts && Q == N, general = K > 32 || r2 >= 0.0f;
+    const dim3 qgrid((unsigned)ceil_div(Q, 8), (unsigned)B);
+#define CRF_KNN_LAUNCH(S, G) knn::query_kernel<S, G><<<qgrid, 256, 0, st>>>(sorted, cell_start, grids, edges, queries, out_idx, (int)N, (int)Q, (int)K, cap, r2)
+    if (self && !general) CRF_KNN_LAUNCH(true, false);
+    else if (self) CRF_KNN_LAUNCH(true, true);
+    else if (!general) CRF_KNN_LAUNCH(false, false);
+    else CRF_KNN_LAUNCH(false, true);
+#undef CRF_KNN_LAUNCH
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }

@@ -57,4 +57,9 @@ else:
         p, f, c = sub_inputs(n)
         us = t(lambda: gs.compute(p, features=f, classes=c, sampleDl=dl, order="key"), reps=5)
         m = gs.compute(p, features=f, classes=c, sampleDl=dl, order="key")[0].shape[0]
-        print(f"grid_subsample N={n} dl={dl}: {us:.0f} us  {n / us:.1f} M points/s  ({m} voxels)")
+        print(f"grid_subsample N={n} dl={dl}: {us:.0f} us  {n / us:.1f} M points/s  ({m} voxels; 13 RANDOM labels: most multi-point voxels tie)")
+        c2 = ((p[:, 0] * 2).floor().to(torch.int32) + (p[:, 1] * 2).floor().to(torch.int32) * 3) % 13      # spatially coherent labels (0.5 m blocks)
+        us = t(lambda: gs.compute(p, features=f, classes=c2, sampleDl=dl, order="key"), reps=5)
+        print(f"grid_subsample N={n} dl={dl}: {us:.0f} us  {n / us:.1f} M points/s  (spatially coherent labels: ties are rare)")
+        us = t(lambda: gs.compute(p, features=f, sampleDl=dl, order="key"), reps=5)
+        print(f"grid_subsample N={n} dl={dl}: {us:.0f} us  {n / us:.1f} M points/s  (no labels)")
