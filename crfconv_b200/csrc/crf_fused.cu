@@ -842,7 +842,7 @@ template <int MINB>
 __global__ void __launch_bounds__(128, MINB) step_bwd_kernel(const StepBwdArgs a) {
     __shared__ __align__(16) float CsT[256], MsT[256], Cs[256], Qs[256];
     __shared__ __align__(16) float stage[4][4][8][24];           // per warp: m, h, v, g rows of its 8 points (MMA operand staging)
-    __shared__ float s_gc[4][512];                               // per warp: running GC | GM (owned by the warp, no atomics)
+    __shared__ __align__(16) float s_gc[4][32][20];              // per warp and lane: its 16 running GC | GM fragment values (pitch 20: conflict-free 128-bit RMW)
     __shared__ float s_y[16];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_trigger();
@@ -854,14 +854,14 @@ __global__ void __launch_bounds__(128, MINB) step_bwd_kernel(const StepBwdArgs a
         MsT[c * 16 + r] = a.Minv[i];
         Qs[i] = a.Q ? a.Q[i] : 0.f;
     }
-    for (int i = tid; i < 4 * 512; i += 128) (&s_gc[0][0])[i] = 0.f;
+    for (int i = tid; i < 4 * 32 * 20; i += 128) (&s_gc[0][0][0])[i] = 0.f;
     if (tid < 16) s_y[tid] = 0.f;
     __syncthreads();
     const int sub = lane & 3, c0 = 4 * sub, pt = lane >> 2, gfr = lane >> 2, tfr = lane & 3;
     const float4 sc = ldg4(a.sc_y + c0);
     float4 ey = zero4();                                       // Σ_edges 2Ga·df·dfH for channels c0..c0+3
     float (*st)[8][24] = stage[warp];
-    float* wacc = s_gc[warp];
+    float4* wacc = reinterpret_cast<float4*>(&s_gc[warp][lane][0]);   // [accC nb0 | accC nb1 | accM nb0 | accM nb1]
     const int64_t ngroups = (a.total + 7) >> 3;
     for (int64_t grp = (int64_t)blockIdx.x * 4 + warp; grp < ngroups; grp += (int64_t)gridDim.x * 4) {
         int64_t p = grp * 8 + pt;
@@ -969,12 +969,12 @@ __global__ void __launch_bounds__(128, MINB) step_bwd_kernel(const StepBwdArgs a
                 FragB bh_, bg_;
                 make_b(bh_, st[1][tfr][nb * 8 + gfr], st[1][tfr + 4][nb * 8 + gfr]);
                 make_b(bg_, st[3][tfr][nb * 8 + gfr], st[3][tfr + 4][nb * 8 + gfr]);
-                float* wc = wacc + gfr * 16 + nb * 8 + 2 * tfr;
-                float cC[4] = {wc[0], wc[1], wc[128], wc[129]}, cM[4] = {wc[256], wc[257], wc[384], wc[385]};
+                const float4 c4 = wacc[nb], m4 = wacc[2 + nb];
+                float cC[4] = {c4.x, c4.y, c4.z, c4.w}, cM[4] = {m4.x, m4.y, m4.z, m4.w};
                 mma3(cC, fm, bh_);
                 mma3(cM, fv, bg_);
-                wc[0] = cC[0]; wc[1] = cC[1]; wc[128] = cC[2]; wc[129] = cC[3];
-                wc[256] = cM[0]; wc[257] = cM[1]; wc[384] = cM[2]; wc[385] = cM[3];
+                wacc[nb] = make_float4(cC[0], cC[1], cC[2], cC[3]);
+                wacc[2 + nb] = make_float4(cM[0], cM[1], cM[2], cM[3]);
             }
         }
         __syncwarp();
@@ -991,9 +991,12 @@ __global__ void __launch_bounds__(128, MINB) step_bwd_kernel(const StepBwdArgs a
     __syncthreads();
     {
         const int64_t slot = blockIdx.x % kGradSlotsF;
-        for (int i = tid; i < 256; i += 128) {
-            atomicAdd(a.GC + a.slot_stride * slot + i, s_gc[0][i] + s_gc[1][i] + s_gc[2][i] + s_gc[3][i]);
-            atomicAdd(a.GM + a.slot_stride * slot + i, s_gc[0][256 + i] + s_gc[1][256 + i] + s_gc[2][256 + i] + s_gc[3][256 + i]);
+        // fragment value k of lane l: matrix k >> 3 (GC / GM), block nb = (k >> 2) & 1, element e = k & 3 ↔ (row g (+8 if e >= 2), col 8nb + 2t + (e & 1))
+        for (int i = tid; i < 512; i += 128) {
+            const int l = i >> 4, k = i & 15, gg = l >> 2, tt = l & 3, e = k & 3;
+            const int row = gg + ((e & 2) ? 8 : 0), col = ((k >> 2) & 1) * 8 + 2 * tt + (e & 1);
+            const float v = s_gc[0][l][k] + s_gc[1][l][k] + s_gc[2][l][k] + s_gc[3][l][k];
+            atomicAdd(((k >> 3) ? a.GM : a.GC) + a.slot_stride * slot + row * 16 + col, v);
         }
         if (tid < 16) atomicAdd(a.ysum + (blockIdx.x % kStepSlots) * 16 + tid, s_y[tid]);
     }
