@@ -834,6 +834,7 @@ struct StepBwdArgs {
     int64_t total, N;
     // last launch of the backward loop: fold ysum into the BatchNorm-backward constants of the y layer (pairwise_nn[1]; gamma_y = its weight)
     int finalize; unsigned int* counter; double count; const float* gamma_y;
+    int debug_skip;                                           // timing experiments only (crfconv_fused_tune(2, mask)): 1 = no Gy reds, 2 = no gprev reds, 4 = no GC/GM
     float* k1; float* k2; float* dgamma; float* dbeta;
 };
 
@@ -844,6 +845,7 @@ __global__ void __launch_bounds__(128, MINB) step_bwd_kernel(const StepBwdArgs a
     __shared__ __align__(16) float stage[4][4][8][24];           // per warp: m, h, v, g rows of its 8 points (MMA operand staging)
     __shared__ __align__(16) float s_gc[4][32][20];              // per warp and lane: its 16 running GC | GM fragment values (pitch 20: conflict-free 128-bit RMW)
     __shared__ float s_y[16];
+    __shared__ __align__(16) long long s_idx[4][2][8][16];          // per warp: double-buffered neighbour-index rows of its next group (cp.async)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_trigger();
     pdl_wait();
@@ -863,17 +865,59 @@ __global__ void __launch_bounds__(128, MINB) step_bwd_kernel(const StepBwdArgs a
     float (*st)[8][24] = stage[warp];
     float4* wacc = reinterpret_cast<float4*>(&s_gc[warp][lane][0]);   // [accC nb0 | accC nb1 | accM nb0 | accM nb1]
     const int64_t ngroups = (a.total + 7) >> 3;
-    for (int64_t grp = (int64_t)blockIdx.x * 4 + warp; grp < ngroups; grp += (int64_t)gridDim.x * 4) {
+    const int64_t gstride = (int64_t)gridDim.x * 4;
+    // The gathers of a group cannot be issued before its neighbour indices have arrived: that dependent round trip (≈1 us, with only
+    // 8 warps per SM to hide it) is taken off the critical path by prefetching the NEXT group's 8 index rows (1 KB) into shared memory.
+    auto prefetch_idx = [&](int64_t g_, int buf) {
+        if (g_ < ngroups) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int c = lane + 32 * i, row = c >> 3, ch = c & 7;       // 8 rows x 8 chunks of 16 B
+                const int64_t pp = min(g_ * 8 + row, a.total - 1);
+                cp_async16(&s_idx[warp][buf][row][2 * ch], a.nbr + pp * 16 + 2 * ch, true);
+            }
+        }
+        cp_async_commit();
+    };
+    int ibuf = 0;
+    prefetch_idx((int64_t)blockIdx.x * 4 + warp, 0);
+    for (int64_t grp = (int64_t)blockIdx.x * 4 + warp; grp < ngroups; grp += gstride, ibuf ^= 1) {
+        prefetch_idx(grp + gstride, ibuf ^ 1);
         int64_t p = grp * 8 + pt;
         const bool valid = p < a.total;
         if (!valid) p = a.total - 1;
         const int64_t base = (p / a.N) * a.N;
+        int rj[KN];
+        {   // the 16 int64 neighbour indices of a point are one 128-byte row: two 128-bit loads per lane, shared by shuffle
+            cp_async_wait<1>();                                // this group's rows have landed (the next group's may be in flight)
+            __syncwarp();
+            const longlong2 ia = *reinterpret_cast<const longlong2*>(&s_idx[warp][ibuf][pt][2 * sub]);
+            const longlong2 ib = *reinterpret_cast<const longlong2*>(&s_idx[warp][ibuf][pt][8 + 2 * sub]);
+            const int r0 = (int)ia.x, r1 = (int)ia.y, r2 = (int)ib.x, r3 = (int)ib.y;   // indices 2s, 2s+1, 8+2s, 8+2s+1
+            const int gb = lane & ~3;
+#pragma unroll
+            for (int k = 1; k < 16; ++k) {                    // index k lives in lane (k & 7) >> 1 of the group, register (k>>3)*2 + (k&1)
+                const int v = (k & 8) ? ((k & 1) ? r3 : r2) : ((k & 1) ? r1 : r0);
+                rj[k - 1] = __shfl_sync(0xffffffffu, v, gb + ((k & 7) >> 1));
+            }
+        }
+        const float4 hyi = ldg4(a.Hy + p * 16 + c0);
+        const float4 gi_raw = ldg4(a.g + p * 16 + c0);
+        const float4 xt_raw = a.Q ? ldg4(a.xT + p * 16 + c0) : zero4();
+        float4 dfj[KN], xj[KN];
+#pragma unroll
+        for (int k = 0; k < KN; ++k) {                         // all gathers issued back to back
+            const int64_t row = base + rj[k];
+            dfj[k] = ldg4(a.Hy + row * 16 + c0);
+            xj[k] = ldg4(a.xprev + row * 16 + c0);
+        }
+        // the point-local algebra (h = g·Minvᵀ, q = h·Cᵀ) runs while the 30 gathers above are in flight
         float4 q;
         {
             float full[16];
-            float4 gi = ldg4(a.g + p * 16 + c0);
+            float4 gi = gi_raw;
             if (a.Q) {
-                gather16(ldg4(a.xT + p * 16 + c0), full, lane);
+                gather16(xt_raw, full, lane);
                 const float4 qx = rowvec_mat16(full, Qs, c0);  // Q is symmetric
                 const float4 a0v = ldg4(a.a0 + c0);
                 gi = make_float4(gi.x - a0v.x - qx.x, gi.y - a0v.y - qx.y, gi.z - a0v.z - qx.z, gi.w - a0v.w - qx.w);
@@ -890,26 +934,6 @@ __global__ void __launch_bounds__(128, MINB) step_bwd_kernel(const StepBwdArgs a
             }
             *reinterpret_cast<float4*>(&st[1][pt][c0]) = valid ? h : zero4();
             *reinterpret_cast<float4*>(&st[3][pt][c0]) = valid ? gi : zero4();
-        }
-        int rj[KN];
-        {   // the 16 int64 neighbour indices of a point are one 128-byte row: two 128-bit loads per lane, shared by shuffle
-            const longlong2 ia = __ldg(reinterpret_cast<const longlong2*>(a.nbr + p * 16) + sub);
-            const longlong2 ib = __ldg(reinterpret_cast<const longlong2*>(a.nbr + p * 16) + 4 + sub);
-            const int r0 = (int)ia.x, r1 = (int)ia.y, r2 = (int)ib.x, r3 = (int)ib.y;   // indices 2s, 2s+1, 8+2s, 8+2s+1
-            const int gb = lane & ~3;
-#pragma unroll
-            for (int k = 1; k < 16; ++k) {                    // index k lives in lane (k & 7) >> 1 of the group, register (k>>3)*2 + (k&1)
-                const int v = (k & 8) ? ((k & 1) ? r3 : r2) : ((k & 1) ? r1 : r0);
-                rj[k - 1] = __shfl_sync(0xffffffffu, v, gb + ((k & 7) >> 1));
-            }
-        }
-        const float4 hyi = ldg4(a.Hy + p * 16 + c0);
-        float4 dfj[KN], xj[KN];
-#pragma unroll
-        for (int k = 0; k < KN; ++k) {                         // all gathers issued back to back
-            const int64_t row = base + rj[k];
-            dfj[k] = ldg4(a.Hy + row * 16 + c0);
-            xj[k] = ldg4(a.xprev + row * 16 + c0);
         }
         float dj[KN], gsj[KN];
         float mx = -INFINITY;
@@ -953,14 +977,14 @@ __global__ void __launch_bounds__(128, MINB) step_bwd_kernel(const StepBwdArgs a
             ey = fma4(gd, df, ey);                             // Σ 2Ga·df² (divided by sc at the end: df·dfH = df²/sc)
             if (valid) {
                 const int64_t row = base + rj[k];
-                red_add_v4(a.Gy + row * 16 + c0, gd);
-                red_add_v4(a.gprev + row * 16 + c0, make_float4(s_ * q.x, s_ * q.y, s_ * q.z, s_ * q.w));
+                if (!(a.debug_skip & 1)) red_add_v4(a.Gy + row * 16 + c0, gd);
+                if (!(a.debug_skip & 2)) red_add_v4(a.gprev + row * 16 + c0, make_float4(s_ * q.x, s_ * q.y, s_ * q.z, s_ * q.w));
             }
         }
         if (valid) red_add_v4(a.Gy + p * 16 + c0, gyi);
         // ---- GC += mᵀ·h, GM += vᵀ·g over the warp's 8 points on the tensor cores (k = point)
         __syncwarp();
-        {
+        if (!(a.debug_skip & 4)) {
             FragA fm, fv;
             make_a(fm, st[0][tfr][gfr], st[0][tfr][gfr + 8], st[0][tfr + 4][gfr], st[0][tfr + 4][gfr + 8]);
             make_a(fv, st[2][tfr][gfr], st[2][tfr][gfr + 8], st[2][tfr + 4][gfr], st[2][tfr + 4][gfr + 8]);
@@ -1219,6 +1243,7 @@ int crfconv_crf_step_bwd_fused(const float* Hy, const float* sc_y, const float* 
     a.Hy = Hy; a.sc_y = sc_y; a.z = z; a.xprev = xprev; a.nbr = neighbor_idx; a.Cm = Cm; a.Minv = Minv; a.g = g;
     a.xT = xT; a.Q = Q; a.a0 = a0; a.Gz = Gz; a.gz_acc = gz_acc; a.gprev = gprev; a.Gy = Gy; a.GC = GC; a.GM = GM;
     a.slot_stride = slot_stride; a.ysum = ysum; a.total = B * N; a.N = N;
+    a.debug_skip = g_tune[2];
     a.finalize = finalize; a.counter = counter; a.count = (double)(B * N); a.gamma_y = gamma_y; a.k1 = k1; a.k2 = k2; a.dgamma = dgamma; a.dbeta = dbeta;
     if (g_tune[0] == 3) CRF_CUDA(launch_k(step_bwd_kernel<3>, dim3(grid_for(ceil_div(a.total, 8), 4 * 4, 3)), dim3(128), 0, (cudaStream_t)stream, a));
     else CRF_CUDA(launch_k(step_bwd_kernel<2>, dim3(grid_for(ceil_div(a.total, 8), 4 * 4, 2)), dim3(128), 0, (cudaStream_t)stream, a));

@@ -112,6 +112,11 @@ for variant in (2, 3):
     timeit(f"crf_step_bwd_fused (CTAs/SM = {variant})", lambda: ops.crf_step_bwd_fused(H2p, b2, z, z, nbr, Cm, Minv, T, x1, Q, a0, Gz, False, gp, Gy, scr, scr[256:], 20000,
                                                                                  ysum, B, N, K, True, cnt, gam, d16, e16), fb * M * F * 7 + 8 * M * K)
 ops._lib.lib().crfconv_fused_tune(0, 2)
+for mask, what in ((1, "no Gy reds"), (2, "no gprev reds"), (3, "no reds"), (4, "no GC/GM MMA"), (7, "gathers + math only")):
+    ops._lib.lib().crfconv_fused_tune(2, mask)
+    timeit(f"  [timing probe, wrong results] {what}", lambda: ops.crf_step_bwd_fused(H2p, b2, z, z, nbr, Cm, Minv, T, x1, Q, a0, Gz, False, gp, Gy, scr, scr[256:], 20000,
+                                                                                  ysum, B, N, K, True, cnt, gam, d16, e16), fb * M * F * 7 + 8 * M * K)
+ops._lib.lib().crfconv_fused_tune(2, 0)
 mo, vo, ho = (torch.empty(M, F, device=dev) for _ in range(3))
 cgrad, w2grad, w1grad = torch.zeros(F, F, device=dev), torch.zeros(F, F, device=dev), torch.zeros(16, Co, device=dev)
 timeit("  generic crf_step_bwd + GC/GM GEMMs", lambda: (ops.crf_step_bwd(H2p, b2.scale, z, z, nbr, Cm, Minv, T, Gz, gp, Gy, mo, vo, ho, False, B, N, K),
