@@ -368,24 +368,14 @@ class _CRFConvFusedFunction(torch.autograd.Function):
         n_big = (steps + 1) * M * F + Mc * F
         # ONE zero-filled allocation: [small grads | weight-grad partial slots | fusion BN Σ slots | out_nn partials | y sums | counters | scatter targets]
         CI = ops.counter_ints()
-        flat = ops.Flat(n_small * (1 + ops.GRAD_SLOTS) + ops.STAT_SLOTS * 2 * Co + n_out + 128 + 8 * CI, torch.float32, dev)
+        flat = ops.Flat(n_small * (1 + ops.GRAD_SLOTS) + ops.STAT_SLOTS * 2 * Co + n_out + 128 + 8 * CI + n_big, torch.float32, dev)
         small = flat.take(n_small)
         wscr = flat.take(ops.GRAD_SLOTS * n_small)
         sums_f = flat.take(ops.STAT_SLOTS * 2 * Co)
         out_part = flat.take(n_out)
         ysum = flat.take(128)
         cnt = flat.take(8 * CI).view(torch.int32).view(8, CI)
-        # the scatter targets (Gy, g^{t-1}, Gu: 47 MB at S1) are first touched by the mean-field backward, four kernels from here: their
-        # zero-fill runs on the auxiliary stream instead of in front of the BatchNorm reduction
-        main0, aux0 = torch.cuda.current_stream(dev), _aux_stream(dev)
-        big = ops.Flat.__new__(ops.Flat)
-        big.buf, big.off = torch.empty(n_big, dtype=torch.float32, device=dev), 0
-        ev_a, ev_big = torch.cuda.Event(), torch.cuda.Event()
-        ev_a.record(main0)
-        aux0.wait_event(ev_a)
-        with torch.cuda.stream(aux0):
-            big.buf.zero_()
-            ev_big.record(aux0)
+        big = ops.Flat.__new__(ops.Flat); big.buf, big.off = flat.take(n_big), 0
         parts = torch.empty((3, NP), dtype=torch.float32, device=dev)
         cursor = [0]
 
@@ -426,7 +416,6 @@ class _CRFConvFusedFunction(torch.autograd.Function):
         Q, a0 = torch.empty((F, F), dtype=torch.float32, device=dev), torch.empty(F, dtype=torch.float32, device=dev)
         T = ops.out16_bwd(dO, H3, so, sl[4], xs[-1], Wo, out_part, cnt[1], dg["o"], db["o"], dW["o"], Q, a0)
         # mean-field steps, last to first (:68-72)
-        main.wait_event(ev_big)
         Gy = big.take(M, F)
         Gz = torch.empty((M, F), dtype=torch.float32, device=dev)
         g = T
@@ -448,6 +437,7 @@ class _CRFConvFusedFunction(torch.autograd.Function):
             ops.crf_compat_bwd(cc, Minv, GC, GM, Gc, scratch=bscr)
             join_aux.record(aux)
         Gu = big.take(Mc, F)
+        ops.crf_upsample_bwd_fused(Gz, g, up, H2u, s2u, Gu, B, N, Nc, parts[0], cnt[3], dg["2u"], db["2u"])   # dL/dz = Σ_t h^t + g^0
         need_u, need_p = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         dV1u = torch.empty((Mc, F), dtype=torch.float32, device=dev)
         dV1p = torch.empty((M, F), dtype=torch.float32, device=dev)
@@ -456,8 +446,7 @@ class _CRFConvFusedFunction(torch.autograd.Function):
         fork, join, fork3, join3 = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         fork.record(main)
         side.wait_event(fork)
-        with torch.cuda.stream(side):                            # upsample (:60) and unary_nn: a branch of its own
-            ops.crf_upsample_bwd_fused(Gz, g, up, H2u, s2u, Gu, B, N, Nc, parts[0], cnt[3], dg["2u"], db["2u"])   # dL/dz = Σ_t h^t + g^0
+        with torch.cuda.stream(side):                            # unary_nn
             ops.mid16_bwd(Gu, H2u, s2u, H1u, s1u, sl[0], W2u, scr(dW["2u"]), n_small, parts[1], cnt[4], dg["1u"], db["1u"], out=dV1u)
             ops.in16_wgrad(dV1u, H1u, s1u, U, scr(dW["1u"]), n_small)
             if need_u:
