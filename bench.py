@@ -270,7 +270,7 @@ def _single_kernel_name(call):
     """C-ABI call label of ops.profile_calls → the CUDA kernel(s) it launches (for `roofline.dominant_kernel`)."""
     table = {"crf_step_bwd_fused": "cl::step_bwd_kernel", "crf_step_fwd[16]": "mf::step_fwd_kernel<16>", "out16_bwd": "cl::out_bwd_kernel",
              "linear_fwd_bn[128->64]": "lin3::fwd3_kernel<64>", "up16_fwd[64]": "cl::up16_fwd_kernel<64>",
-             "linear_bwd[64<-128]": "lin3d::dgrad3_kernel<128> + lin3w::wgrad3_kernel<64>", "bn_bwd_reduce_fin[64]": "lin::bn_bwd_reduce_kernel",
+             "linear_bwd[64<-128]:dgrad": "lin3d::dgrad3_kernel<128>", "linear_bwd[64<-128]:wgrad": "lin3w::wgrad3_kernel<64>", "bn_bwd_reduce_fin[64]": "lin::bn_bwd_reduce_kernel",
              "mid16_bwd": "cl::mid16_bwd_kernel", "lin16_fwd[64]": "cl::lin16_fwd_kernel<64>", "lin16_fwd[128]": "cl::lin16_fwd_kernel<128>",
              "lin16_fwd[16]": "cl::lin16_fwd_kernel<16>", "in16_dgrad[64]": "cl::in16_dgrad_kernel<64>", "in16_wgrad[64]": "cl::in16_wgrad_kernel<64>"}
     return table.get(call, call)

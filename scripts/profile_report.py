@@ -158,8 +158,18 @@ def metrics_csv(path, out_json=None, skip_prefixes=("at::", "knn::")):
     tot_mb = sum(t.get("rd_MB", 0) + t.get("wr_MB", 0) for t in keep)
     print(f"\nlayer kernels: {len(keep)}; summed time {tot_us:.1f} us; DRAM traffic {tot_mb:.1f} MB (read + write)")
     if out_json:
+        # bench.py's call labels → DRAM bytes (read + write) of the kernel(s) behind them, per launch
+        call_of = {"cl::step_bwd_kernel": "crf_step_bwd_fused", "mf::step_fwd_kernel<16>": "crf_step_fwd[16]", "cl::out_bwd_kernel": "out16_bwd",
+                   "lin3::fwd3_kernel<64>": "linear_fwd_bn[128->64]", "cl::up16_fwd_kernel<64>": "up16_fwd[64]",
+                   "lin::bn_bwd_reduce_kernel": "bn_bwd_reduce_fin[64]", "lin3d::dgrad3_kernel<128>": "linear_bwd[64<-128]:dgrad",
+                   "lin3w::wgrad3_kernel<64>": "linear_bwd[64<-128]:wgrad", "lin::bn_act_fwd_kernel": "bn_act_fwd[64]"}
+        calls = {}
+        for t in keep:
+            for kname, label in call_of.items():
+                if t["kernel"].startswith(kname) and label not in calls:
+                    calls[label] = round((t.get("rd_MB", 0) + t.get("wr_MB", 0)) * 1e6)
         json.dump({"source": f"ncu --set full --clock-control none --csv --page raw ({path})", "kernels": keep,
-                   "step_dram_bytes": round(tot_mb * 1e6), "step_sum_us": round(tot_us, 1)}, open(out_json, "w"), indent=1)
+                   "step_dram_bytes": round(tot_mb * 1e6), "step_sum_us": round(tot_us, 1), **calls}, open(out_json, "w"), indent=1)
 
 
 
