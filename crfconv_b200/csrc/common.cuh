@@ -83,6 +83,23 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// ---- 256-bit global loads (sm_100: LDG.E.256) ---------------------------------------------------------------------------
+// The L1 data pipe is charged per 128-byte line an instruction touches (≈2 cycles per line inside one instruction).  A gather of
+// 64-byte rows with 128-bit loads touches 8 lines per warp instruction and uses half of each; with the two 64-byte rows an edge
+// needs (y_j, x_j) interleaved into ONE 128-byte row ("packed" layout, crf.cu) and 256-bit loads, 4 lanes fetch a whole line
+// and the line count per edge halves.
+__device__ __forceinline__ void ldg8(const float* p, float4& a, float4& b) {
+    asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+        : "l"(p));
+}
+// 4 consecutive int64 (one quarter of a K = 16 neighbour row) as ints
+__device__ __forceinline__ void ldg_idx4(const long long* p, int (&r)[4]) {
+    long long a, b, c, d;
+    asm("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    r[0] = (int)a; r[1] = (int)b; r[2] = (int)c; r[3] = (int)d;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -13,6 +13,7 @@
 
 #include "../../include/crfconv_b200.h"
 #include "common.cuh"
+#include "fused_common.cuh"
 
 namespace crf {
 namespace mf {
@@ -138,11 +139,18 @@ struct StepArgs {
 template <int F>
 __global__ void __launch_bounds__(256) step_fwd_kernel(const StepArgs a) {
     constexpr int LP = F / 4, PPW = 32 / LP;
-    __shared__ __align__(16) float Cs[F * F];
-    __shared__ __align__(16) float Ms[F * F];
+    constexpr bool TC = F == 16;                           // hidden width of the hot path: the two F×F products on the tensor cores
+    __shared__ __align__(16) float Cs[TC ? 4 : F * F];
+    __shared__ __align__(16) float Ms[TC ? 4 : F * F];
+    __shared__ __align__(16) float4 fC[TC ? 128 : 1], fM[TC ? 128 : 1];
     pdl_trigger();
     pdl_wait();
-    for (int i = threadIdx.x; i < F * F; i += blockDim.x) { Cs[i] = a.Cm[i]; Ms[i] = a.Minv[i]; }
+    if constexpr (TC) {
+        cl::stage_mat16(fC, [&](int k, int n) { return a.Cm[k * 16 + n]; }, threadIdx.x, blockDim.x);
+        cl::stage_mat16(fM, [&](int k, int n) { return a.Minv[k * 16 + n]; }, threadIdx.x, blockDim.x);
+    } else {
+        for (int i = threadIdx.x; i < F * F; i += blockDim.x) { Cs[i] = a.Cm[i]; Ms[i] = a.Minv[i]; }
+    }
     __syncthreads();
     const int lane = lane_id();
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -187,13 +195,87 @@ __global__ void __launch_bounds__(256) step_fwd_kernel(const StepArgs a) {
         for (int k = 1; k < a.K; ++k) edge(base + __ldg(nb + k));
     const float inv_l = a.K > 1 ? 1.0f / l : 0.0f;
     const float4 msg = make_float4(acc.x * inv_l, acc.y * inv_l, acc.z * inv_l, acc.w * inv_l);
-    float full[F];
-    gather_full<F>(msg, full, lane);
-    float4 v = rowvec_mat<F>(full, Cs, c0);
     const float4 zi = ld4(a.z + p * F + c0);
+    float4 x;
+    if constexpr (TC) {                                    // x = (z + m·C)·Minv, chained through MMA fragments (fused_common.cuh)
+        float4 v = cl::rows8_mat16(msg, fC, lane);
+        v.x += zi.x; v.y += zi.y; v.z += zi.z; v.w += zi.w;
+        x = cl::rows8_mat16(v, fM, lane);
+    } else {
+        float full[F];
+        gather_full<F>(msg, full, lane);
+        float4 v = rowvec_mat<F>(full, Cs, c0);
+        v.x += zi.x; v.y += zi.y; v.z += zi.z; v.w += zi.w;
+        gather_full<F>(v, full, lane);
+        x = rowvec_mat<F>(full, Ms, c0);
+    }
+    if (valid) *reinterpret_cast<float4*>(a.xout + p * F + c0) = x;
+}
+
+// ---- packed layout (F = 16, K = 16, first mean-field step: x^0 = z) ---------------------------------------------------------
+// YX[m][32]: lane slice s (channels 4s..4s+3) of point m owns floats [8s, 8s+8) = { Hy[m][4s..4s+3], z[m][4s..4s+3] }: the two rows an
+// edge gathers are ONE 128-byte line fetched by the point's 4 lanes with one 256-bit load each (see ldg8, common.cuh).
+__global__ void __launch_bounds__(256) upsample_affine_packed_kernel(const float* __restrict__ Hu, const float* __restrict__ scale,
+                                                                     const float* __restrict__ shift, const int64_t* __restrict__ up,
+                                                                     float* __restrict__ YX, int64_t total, int64_t N, int64_t Nc) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total * 4) return;
+    const int64_t m = i >> 2;
+    const int s = (int)(i & 3), c = 4 * s;
+    const int64_t src = (m / N) * Nc + __ldg(up + m);
+    const float4 h = ld4(Hu + src * 16 + c), sc = ld4(scale + c), sh = ld4(shift + c);
+    *reinterpret_cast<float4*>(YX + m * 32 + 8 * s + 4) =
+        make_float4(fmaf(h.x, sc.x, sh.x), fmaf(h.y, sc.y, sh.y), fmaf(h.z, sc.z, sh.z), fmaf(h.w, sc.w, sh.w));
+}
+
+struct StepPackedArgs {
+    const float* YX; const float* scale_y; const int64_t* nbr; const float* Cm; const float* Minv;
+    float* xout; int64_t total, N;
+};
+
+__global__ void __launch_bounds__(256) step_fwd_packed_kernel(const StepPackedArgs a) {
+    constexpr int F = 16;
+    __shared__ __align__(16) float4 fC[128], fM[128];
+    pdl_trigger();
+    pdl_wait();
+    cl::stage_mat16(fC, [&](int k, int n) { return a.Cm[k * 16 + n]; }, threadIdx.x, blockDim.x);
+    cl::stage_mat16(fM, [&](int k, int n) { return a.Minv[k * 16 + n]; }, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const int lane = lane_id(), sub = lane & 3, c0 = 4 * sub, gb = lane & ~3;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t p = warp * 8 + (lane >> 2);
+    const bool valid = p < a.total;
+    if (!valid) p = a.total - 1;
+    const int64_t base = (p / a.N) * a.N;
+    int r[4];                                              // lane s of the point holds indices 4s..4s+3
+    ldg_idx4(reinterpret_cast<const long long*>(a.nbr + p * 16) + 4 * sub, r);
+    const float4 sc = ld4(a.scale_y + c0);
+    float4 hyi, zi;
+    ldg8(a.YX + p * 32 + 8 * sub, hyi, zi);
+    const float4 yi = mul4(hyi, sc);
+    float mx = -INFINITY, l = 0.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 1; k < 16; ++k) {                         // online softmax: the compiler keeps a handful of gathers in flight (56 registers)
+        const int64_t row = base + __shfl_sync(0xffffffffu, r[k & 3], gb + (k >> 2));
+        float4 hj, xj;
+        ldg8(a.YX + row * 32 + 8 * sub, hj, xj);
+        const float4 df = sub4(yi, mul4(hj, sc));
+        const float al = -group_sum<4>(dot4(df, df));
+        const float nm = fmaxf(mx, al);
+        const float corr = __expf(mx - nm), pj = __expf(al - nm);
+        l = l * corr + pj;
+        acc.x = acc.x * corr + pj * xj.x; acc.y = acc.y * corr + pj * xj.y;
+        acc.z = acc.z * corr + pj * xj.z; acc.w = acc.w * corr + pj * xj.w;
+        mx = nm;
+    }
+    const float inv_l = 1.0f / l;
+    const float4 msg = make_float4(acc.x * inv_l, acc.y * inv_l, acc.z * inv_l, acc.w * inv_l);
+    float4 v = cl::rows8_mat16(msg, fC, lane);
     v.x += zi.x; v.y += zi.y; v.z += zi.z; v.w += zi.w;
-    gather_full<F>(v, full, lane);
-    const float4 x = rowvec_mat<F>(full, Ms, c0);
+    const float4 x = cl::rows8_mat16(v, fM, lane);
     if (valid) *reinterpret_cast<float4*>(a.xout + p * F + c0) = x;
 }
 
@@ -526,6 +608,27 @@ int crfconv_crf_step_fwd(const float* Hy, const float* scale_y, const float* z, 
         CRF_LAUNCH_CHECK();
         return CRF_OK;
     });
+}
+
+// Packed variants (F = 16, K = 16, step 1 only): YX[B*N, 32] holds Hy (written by crfconv_lin16_fwd's Ypk output) and z interleaved.
+int crfconv_crf_upsample_fwd_packed(const float* Hu, const float* scale, const float* shift, const int64_t* up_idx, float* YX, int64_t B,
+                                    int64_t N, int64_t Nc, void* stream) {
+    if (B <= 0 || N <= 0 || Nc <= 0 || !Hu || !scale || !shift || !up_idx || !YX) return CRF_ERR_INVALID_ARG;
+    const int64_t total = B * N;
+    CRF_CUDA(launch_k(mf::upsample_affine_packed_kernel, dim3((unsigned)ceil_div(total * 4, 256)), dim3(256), 0, (cudaStream_t)stream, Hu, scale,
+                      shift, up_idx, YX, total, N, Nc));
+    CRF_LAUNCH_CHECK();
+    return CRF_OK;
+}
+
+int crfconv_crf_step_fwd_packed(const float* YX, const float* scale_y, const int64_t* neighbor_idx, const float* Cm, const float* Minv,
+                                float* xout, int64_t B, int64_t N, void* stream) {
+    if (B <= 0 || N <= 0 || !YX || !scale_y || !neighbor_idx || !Cm || !Minv || !xout) return CRF_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(YX) & 31) || (reinterpret_cast<uintptr_t>(neighbor_idx) & 31)) return CRF_ERR_INVALID_ARG;
+    mf::StepPackedArgs a{YX, scale_y, neighbor_idx, Cm, Minv, xout, B * N, N};
+    CRF_CUDA(launch_k(mf::step_fwd_packed_kernel, dim3((unsigned)ceil_div(ceil_div(a.total, 8), 8)), dim3(256), 0, (cudaStream_t)stream, a));
+    CRF_LAUNCH_CHECK();
+    return CRF_OK;
 }
 
 // Backward of one step.  g = dL/dx^t.  Gz = h, or += h when gz_acc (owner rows), gprev += Σ s_ij q_i (must be zero-initialised),

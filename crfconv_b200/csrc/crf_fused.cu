@@ -66,6 +66,7 @@ struct LinFwdArgs {
     const float* W;                                           // [16, CIN]
     const float* pscale; const float* pshift; float pslope;   // PRO: X ← lrelu(X·pscale + pshift)
     float* Y;                                                 // [M, 16]
+    float* Ypk;                                               // optional second copy into the packed [M,32] layout of the mean field (crf.cu)
     int64_t M;
     FwdFin fin;
 };
@@ -136,6 +137,11 @@ __global__ void __launch_bounds__(kThreads, CIN > 64 ? 1 : 2) lin16_fwd_kernel(c
         for (int nb = 0; nb < 2; ++nb) {
             if (ok0) *reinterpret_cast<float2*>(a.Y + r0 * 16 + nb * 8 + 2 * t) = make_float2(acc[nb][0], acc[nb][1]);
             if (ok1) *reinterpret_cast<float2*>(a.Y + r1 * 16 + nb * 8 + 2 * t) = make_float2(acc[nb][2], acc[nb][3]);
+            if (a.Ypk) {                                       // channel c ↦ float 8·(c >> 2) + (c & 3) of the packed row
+                const int off = (nb * 2 + (t >> 1)) * 8 + 2 * (t & 1);
+                if (ok0) *reinterpret_cast<float2*>(a.Ypk + r0 * 32 + off) = make_float2(acc[nb][0], acc[nb][1]);
+                if (ok1) *reinterpret_cast<float2*>(a.Ypk + r1 * 32 + off) = make_float2(acc[nb][2], acc[nb][3]);
+            }
             ssum[nb][0] += acc[nb][0] + acc[nb][2];            // rows beyond M are exact zeros
             ssum[nb][1] += acc[nb][1] + acc[nb][3];
             ssq[nb][0] = fmaf(acc[nb][0], acc[nb][0], fmaf(acc[nb][2], acc[nb][2], ssq[nb][0]));
@@ -824,6 +830,7 @@ constexpr int kStepSlots = 8;
 struct StepBwdArgs {
     const float* Hy; const float* sc_y;                       // pre-BN pairwise embedding [M,16], γ·istd of its BatchNorm
     const float* z; const float* xprev; const int64_t* nbr;   // [M,16], [M,16], [M,16] (column 0 = self, skipped)
+    const float* YX;                                          // PK: packed [M,32] rows {Hy | z} (x^{t-1} = z: first step), replaces Hy / z / xprev
     const float* Cm; const float* Minv;                       // [16,16]
     const float* g;                                           // [M,16]  dL/dx^t  (t_i of out_bwd when Q != null)
     const float* xT; const float* Q; const float* a0;         // out_nn BatchNorm-backward correction: g_i ← g_i − a0 − Q·xT_i
@@ -839,9 +846,9 @@ struct StepBwdArgs {
 };
 
 constexpr int KN = 15;
-template <int MINB>
+template <int MINB, bool PK>
 __global__ void __launch_bounds__(128, MINB) step_bwd_kernel(const StepBwdArgs a) {
-    __shared__ __align__(16) float CsT[256], MsT[256], Cs[256], Qs[256];
+    __shared__ __align__(16) float4 fCT[128], fMT[128], fC[128], fQ[128];   // pre-split MMA fragments of Cᵀ, Minvᵀ, C, Q (rows8_mat16)
     __shared__ __align__(16) float stage[4][4][8][24];           // per warp: m, h, v, g rows of its 8 points (MMA operand staging)
     __shared__ __align__(16) float s_gc[4][32][20];              // per warp and lane: its 16 running GC | GM fragment values (pitch 20: conflict-free 128-bit RMW)
     __shared__ float s_y[16];
@@ -849,13 +856,10 @@ __global__ void __launch_bounds__(128, MINB) step_bwd_kernel(const StepBwdArgs a
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_trigger();
     pdl_wait();
-    for (int i = tid; i < 256; i += 128) {
-        const int r = i >> 4, c = i & 15;
-        Cs[i] = a.Cm[i];
-        CsT[c * 16 + r] = a.Cm[i];
-        MsT[c * 16 + r] = a.Minv[i];
-        Qs[i] = a.Q ? a.Q[i] : 0.f;
-    }
+    stage_mat16(fC, [&](int k, int n) { return a.Cm[k * 16 + n]; }, tid, 128);
+    stage_mat16(fCT, [&](int k, int n) { return a.Cm[n * 16 + k]; }, tid, 128);
+    stage_mat16(fMT, [&](int k, int n) { return a.Minv[n * 16 + k]; }, tid, 128);
+    stage_mat16(fQ, [&](int k, int n) { return a.Q ? a.Q[k * 16 + n] : 0.f; }, tid, 128);
     for (int i = tid; i < 4 * 32 * 20; i += 128) (&s_gc[0][0][0])[i] = 0.f;
     if (tid < 16) s_y[tid] = 0.f;
     __syncthreads();
@@ -901,31 +905,35 @@ __global__ void __launch_bounds__(128, MINB) step_bwd_kernel(const StepBwdArgs a
                 rj[k - 1] = __shfl_sync(0xffffffffu, v, gb + ((k & 7) >> 1));
             }
         }
-        const float4 hyi = ldg4(a.Hy + p * 16 + c0);
+        float4 hyi, zi;
+        if (PK) ldg8(a.YX + p * 32 + 2 * c0, hyi, zi);
+        else hyi = ldg4(a.Hy + p * 16 + c0);
         const float4 gi_raw = ldg4(a.g + p * 16 + c0);
         const float4 xt_raw = a.Q ? ldg4(a.xT + p * 16 + c0) : zero4();
-        float4 dfj[KN], xj[KN];
+        constexpr bool ONLINE = MINB >= 3;                     // 3 CTAs per SM: x_j rows are consumed as they arrive (online softmax), 60 fewer live registers
+        float4 dfj[KN], xj[ONLINE ? 1 : KN];
+        if constexpr (!ONLINE) {
 #pragma unroll
-        for (int k = 0; k < KN; ++k) {                         // all gathers issued back to back
-            const int64_t row = base + rj[k];
-            dfj[k] = ldg4(a.Hy + row * 16 + c0);
-            xj[k] = ldg4(a.xprev + row * 16 + c0);
+            for (int k = 0; k < KN; ++k) {                     // all gathers issued back to back
+                const int64_t row = base + rj[k];
+                if (PK) ldg8(a.YX + row * 32 + 2 * c0, dfj[k], xj[k]);
+                else {
+                    dfj[k] = ldg4(a.Hy + row * 16 + c0);
+                    xj[k] = ldg4(a.xprev + row * 16 + c0);
+                }
+            }
         }
-        // the point-local algebra (h = g·Minvᵀ, q = h·Cᵀ) runs while the 30 gathers above are in flight
+        // the point-local algebra (h = g·Minvᵀ, q = h·Cᵀ; tensor cores, chained through registers) runs while the 30 gathers above are in flight
         float4 q;
         {
-            float full[16];
             float4 gi = gi_raw;
             if (a.Q) {
-                gather16(xt_raw, full, lane);
-                const float4 qx = rowvec_mat16(full, Qs, c0);  // Q is symmetric
+                const float4 qx = rows8_mat16(xt_raw, fQ, lane);
                 const float4 a0v = ldg4(a.a0 + c0);
                 gi = make_float4(gi.x - a0v.x - qx.x, gi.y - a0v.y - qx.y, gi.z - a0v.z - qx.z, gi.w - a0v.w - qx.w);
             }
-            gather16(gi, full, lane);
-            const float4 h = rowvec_mat16(full, MsT, c0);      // h = g·Minvᵀ
-            gather16(h, full, lane);
-            q = rowvec_mat16(full, CsT, c0);                   // q = h·Cᵀ
+            const float4 h = rows8_mat16(gi, fMT, lane);       // h = g·Minvᵀ
+            q = rows8_mat16(h, fCT, lane);                     // q = h·Cᵀ
             if (valid) {
                 float* gz = a.Gz + p * 16 + c0;
                 float4 o = h;
@@ -937,32 +945,54 @@ __global__ void __launch_bounds__(128, MINB) step_bwd_kernel(const StepBwdArgs a
         }
         float dj[KN], gsj[KN];
         float mx = -INFINITY;
-#pragma unroll
-        for (int k = 0; k < KN; ++k) {
-            dfj[k] = mul4(sub4(hyi, dfj[k]), sc);              // df = sc ⊙ (Hy_i − Hy_j) = y_i − y_j
-            dj[k] = quad_sum(dot4(dfj[k], dfj[k]));
-            gsj[k] = quad_sum(dot4(q, xj[k]));
-            mx = fmaxf(mx, -dj[k]);
-        }
         float l = 0.f, tacc = 0.f;
         float4 acc = zero4();
+        if constexpr (ONLINE) {
 #pragma unroll
-        for (int k = 0; k < KN; ++k) {
-            const float pj = __expf(-dj[k] - mx);
-            dj[k] = pj;
-            l += pj;
-            tacc = fmaf(pj, gsj[k], tacc);
-            acc.x = fmaf(pj, xj[k].x, acc.x); acc.y = fmaf(pj, xj[k].y, acc.y);
-            acc.z = fmaf(pj, xj[k].z, acc.z); acc.w = fmaf(pj, xj[k].w, acc.w);
+            for (int k = 0; k < KN; ++k) {
+                const int64_t row = base + rj[k];
+                float4 hj, x;
+                if (PK) ldg8(a.YX + row * 32 + 2 * c0, hj, x);
+                else { hj = ldg4(a.Hy + row * 16 + c0); x = ldg4(a.xprev + row * 16 + c0); }
+                dfj[k] = mul4(sub4(hyi, hj), sc);
+                const float al = -quad_sum(dot4(dfj[k], dfj[k]));
+                gsj[k] = quad_sum(dot4(q, x));
+                const float nm = fmaxf(mx, al);
+                const float corr = __expf(mx - nm), pj = __expf(al - nm);
+                l = fmaf(l, corr, pj);
+                tacc = fmaf(tacc, corr, pj * gsj[k]);
+                acc.x = fmaf(acc.x, corr, pj * x.x); acc.y = fmaf(acc.y, corr, pj * x.y);
+                acc.z = fmaf(acc.z, corr, pj * x.z); acc.w = fmaf(acc.w, corr, pj * x.w);
+                dj[k] = al;
+                mx = nm;
+            }
+#pragma unroll
+            for (int k = 0; k < KN; ++k) dj[k] = __expf(dj[k] - mx);
+        } else {
+#pragma unroll
+            for (int k = 0; k < KN; ++k) {
+                dfj[k] = mul4(sub4(hyi, dfj[k]), sc);          // df = sc ⊙ (Hy_i − Hy_j) = y_i − y_j
+                dj[k] = quad_sum(dot4(dfj[k], dfj[k]));
+                gsj[k] = quad_sum(dot4(q, xj[0 + (ONLINE ? 0 : k)]));
+                mx = fmaxf(mx, -dj[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < KN; ++k) {
+                const float pj = __expf(-dj[k] - mx);
+                dj[k] = pj;
+                l += pj;
+                tacc = fmaf(pj, gsj[k], tacc);
+                const float4 x = xj[ONLINE ? 0 : k];
+                acc.x = fmaf(pj, x.x, acc.x); acc.y = fmaf(pj, x.y, acc.y);
+                acc.z = fmaf(pj, x.z, acc.z); acc.w = fmaf(pj, x.w, acc.w);
+            }
         }
         const float inv_l = 1.0f / l;
         const float sdot = tacc * inv_l;
         {
             const float4 msg = make_float4(acc.x * inv_l, acc.y * inv_l, acc.z * inv_l, acc.w * inv_l);
-            float full[16];
-            gather16(msg, full, lane);
-            float4 v = rowvec_mat16(full, Cs, c0);             // v = z + m·C
-            v = add4(v, ldg4(a.z + p * 16 + c0));
+            float4 v = rows8_mat16(msg, fC, lane);             // v = z + m·C
+            v = add4(v, PK ? zi : ldg4(a.z + p * 16 + c0));
             *reinterpret_cast<float4*>(&st[0][pt][c0]) = valid ? msg : zero4();
             *reinterpret_cast<float4*>(&st[2][pt][c0]) = valid ? v : zero4();
         }
@@ -976,7 +1006,8 @@ __global__ void __launch_bounds__(128, MINB) step_bwd_kernel(const StepBwdArgs a
             gyi = sub4(gyi, gd);
             ey = fma4(gd, df, ey);                             // Σ 2Ga·df² (divided by sc at the end: df·dfH = df²/sc)
             if (valid) {
-                const int64_t row = base + rj[k];
+                // ONLINE: the index is re-read from the (still intact) shared-memory row instead of staying live in a register
+                const int64_t row = base + (ONLINE ? (int)s_idx[warp][ibuf][pt][k + 1] : rj[k]);
                 if (!(a.debug_skip & 1)) red_add_v4(a.Gy + row * 16 + c0, gd);
                 if (!(a.debug_skip & 2)) red_add_v4(a.gprev + row * 16 + c0, make_float4(s_ * q.x, s_ * q.y, s_ * q.z, s_ * q.w));
             }
@@ -1087,7 +1118,7 @@ __global__ void __launch_bounds__(kThreads, 4) upsample_bwd_kernel(const UpBwdAr
         bn_bwd_finalize(a.fin, s_red[tid], s_red[16 + tid], tid);
 }
 
-static int g_tune[8] = {2, 0, 0, 0, 0, 0, 0, 0};   // [0] CTAs/SM of step_bwd, [1] programmatic dependent launch on/off
+static int g_tune[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // [0] CTAs/SM of step_bwd (0 = automatic), [1] programmatic dependent launch on/off
 
 inline int grid_for(int64_t units, int per_cta, int ctas_per_sm) {
     const int64_t want = ceil_div(units, per_cta);
@@ -1118,12 +1149,12 @@ int crfconv_fused_tune(int key, int value) {
 // H[M,16] = act(X[M,Cin])·Wᵀ with the BatchNorm statistics of H finalized in the same launch.  Cin ∈ {16, 64, 128}; pscale/pshift
 // (BN affine of the previous layer, applied with LeakyReLU(pslope) while loading X) are required for Cin = 16 and must be NULL otherwise.
 // part: scratch of crfconv_fused_max_parts()·32 floats; counter: one zeroed uint32 (left zero).  Outputs scale/shift/mean/invstd [16].
-int crfconv_lin16_fwd(const float* X, int Cin, const float* W, const float* pscale, const float* pshift, float pslope, float* Y, int64_t M,
-                      float* part, unsigned int* counter, const float* gamma, const float* beta, float* running_mean,
+int crfconv_lin16_fwd(const float* X, int Cin, const float* W, const float* pscale, const float* pshift, float pslope, float* Y, float* Ypk,
+                      int64_t M, float* part, unsigned int* counter, const float* gamma, const float* beta, float* running_mean,
                       float* running_var, float eps, float momentum, float* scale, float* shift, float* mean, float* invstd, void* stream) {
     if (!X || !W || !Y || !part || !counter || !scale || !shift || M <= 0 || !al16(X) || !al16(Y)) return CRF_ERR_INVALID_ARG;
     LinFwdArgs a{};
-    a.X = X; a.W = W; a.pscale = pscale; a.pshift = pshift; a.pslope = pslope; a.Y = Y; a.M = M;
+    a.X = X; a.W = W; a.pscale = pscale; a.pshift = pshift; a.pslope = pslope; a.Y = Y; a.Ypk = Ypk; a.M = M;
     a.fin = FwdFin{part, counter, gamma, beta, running_mean, running_var, eps, momentum, (double)M, scale, shift, mean, invstd};
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t tiles = ceil_div(M, 16);
@@ -1232,10 +1263,11 @@ int crfconv_out16_bwd(const float* dO, const float* H3, const float* sc3, const 
 int crfconv_crf_step_bwd_fused(const float* Hy, const float* sc_y, const float* z, const float* xprev, const int64_t* neighbor_idx,
                                const float* Cm, const float* Minv, const float* g, const float* xT, const float* Q, const float* a0,
                                float* Gz, int gz_acc, float* gprev, float* Gy, float* GC, float* GM, int64_t slot_stride,
-                               float* ysum, int64_t B, int64_t N, int K, int F, int finalize, unsigned int* counter,
+                               float* ysum, int64_t B, int64_t N, int K, int F, int packed, int finalize, unsigned int* counter,
                                const float* gamma_y, float* k1, float* k2, float* dgamma, float* dbeta, void* stream) {
     if (F != 16 || K != 16) return CRF_ERR_UNSUPPORTED;
-    if (!Hy || !sc_y || !z || !xprev || !neighbor_idx || !Cm || !Minv || !g || !Gz || !gprev || !Gy || !GC || !GM || !ysum || B <= 0 || N <= 0)
+    if (packed && (reinterpret_cast<uintptr_t>(Hy) & 31)) return CRF_ERR_INVALID_ARG;
+    if (!Hy || !sc_y || (!packed && (!z || !xprev)) || !neighbor_idx || !Cm || !Minv || !g || !Gz || !gprev || !Gy || !GC || !GM || !ysum || B <= 0 || N <= 0)
         return CRF_ERR_INVALID_ARG;
     if (Q && (!xT || !a0)) return CRF_ERR_INVALID_ARG;
     if (finalize && (!counter || !gamma_y || !k1 || !k2)) return CRF_ERR_INVALID_ARG;
@@ -1245,8 +1277,14 @@ int crfconv_crf_step_bwd_fused(const float* Hy, const float* sc_y, const float* 
     a.slot_stride = slot_stride; a.ysum = ysum; a.total = B * N; a.N = N;
     a.debug_skip = g_tune[2];
     a.finalize = finalize; a.counter = counter; a.count = (double)(B * N); a.gamma_y = gamma_y; a.k1 = k1; a.k2 = k2; a.dgamma = dgamma; a.dbeta = dbeta;
-    if (g_tune[0] == 3) CRF_CUDA(launch_k(step_bwd_kernel<3>, dim3(grid_for(ceil_div(a.total, 8), 4 * 4, 3)), dim3(128), 0, (cudaStream_t)stream, a));
-    else CRF_CUDA(launch_k(step_bwd_kernel<2>, dim3(grid_for(ceil_div(a.total, 8), 4 * 4, 2)), dim3(128), 0, (cudaStream_t)stream, a));
+    a.YX = packed ? Hy : nullptr;
+    const dim3 grid2(grid_for(ceil_div(a.total, 8), 4 * 4, 2));
+    // CTAs per SM: 0 = automatic (packed: 2 — the 256-bit gathers need fewer instructions; two tables: 3 with the online-softmax register diet)
+    const int per_sm = g_tune[0] ? g_tune[0] : (packed ? 2 : 3);
+    if (packed && per_sm == 3) CRF_CUDA(launch_k(step_bwd_kernel<3, true>, dim3(grid_for(ceil_div(a.total, 8), 4 * 4, 3)), dim3(128), 0, (cudaStream_t)stream, a));
+    else if (packed) CRF_CUDA(launch_k(step_bwd_kernel<2, true>, grid2, dim3(128), 0, (cudaStream_t)stream, a));
+    else if (per_sm == 3) CRF_CUDA(launch_k(step_bwd_kernel<3, false>, dim3(grid_for(ceil_div(a.total, 8), 4 * 4, 3)), dim3(128), 0, (cudaStream_t)stream, a));
+    else CRF_CUDA(launch_k(step_bwd_kernel<2, false>, grid2, dim3(128), 0, (cudaStream_t)stream, a));
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }

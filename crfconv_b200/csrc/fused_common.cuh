@@ -270,6 +270,41 @@ __device__ __forceinline__ void store_split(float2* Bh, float2* Bl, int i, float
     Bl[i] = make_float2(__uint_as_float(l0), __uint_as_float(l1));
 }
 
+// ---- a 16×16 matrix applied to the 8 point rows a warp holds in the "4 lanes × float4" layout ----------------------------------
+// Lane (g, t) = (lane >> 2, lane & 3) holds channels 4t..4t+3 of point g.  That IS an m16n8k8 A fragment (rows 8..15 zero) once
+// the k index is permuted (k-step s: k = t ↔ channel 4t+2s, k = t+4 ↔ channel 4t+2s+1), and with the output columns permuted by
+// phys_col the two accumulator blocks come back as channels 4t..4t+3 of point g: row-vector × matrix products chain through
+// registers with 12 MMAs each, no shuffle and no operand broadcast from shared memory.  (The shuffle + LDS.128 form costs
+// 16 + 4·16 = 80 L1 data-pipe wavefronts per product and warp — the mean-field kernels are bound by that pipe — this one 16.)
+// Matrix fragments live pre-split in shared memory: frag[(s·2 + nb)·32 + lane] = { hi(b0), hi(b1), lo(b0), lo(b1) }.
+template <typename GetW>
+__device__ __forceinline__ void stage_mat16(float4* frag, GetW w, int tid, int nthreads) {   // w(k, n) = Mat[k][n] of  out = x·Mat
+    for (int i = tid; i < 128; i += nthreads) {
+        const int s = i >> 6, nb = (i >> 5) & 1, gg = (i & 31) >> 2, tt = i & 3;
+        const int kin = 4 * tt + 2 * s, nout = 4 * (gg >> 1) + 2 * nb + (gg & 1);
+        uint32_t h0, l0, h1, l1;
+        split(w(kin, nout), h0, l0);
+        split(w(kin + 1, nout), h1, l1);
+        frag[i] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
+    }
+}
+__device__ __forceinline__ float4 rows8_mat16(float4 x, const float4* frag, int lane) {
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    FragA f;
+    f.hi[1] = f.lo[1] = f.hi[3] = f.lo[3] = 0u;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        split(s ? x.z : x.x, f.hi[0], f.lo[0]);
+        split(s ? x.w : x.y, f.hi[2], f.lo[2]);
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+            const float4 b = frag[(s * 2 + nb) * 32 + lane];
+            mma3(acc[nb], f, make_float2(b.x, b.y), make_float2(b.z, b.w));
+        }
+    }
+    return make_float4(acc[0][0], acc[0][1], acc[1][0], acc[1][1]);
+}
+
 // Output-column permutation that turns the two 8-wide accumulator blocks 2q, 2q+1 of a thread into ONE float4 of 4 consecutive
 // physical columns 16q + 4t .. 16q + 4t + 3 (so stores / read-modify-writes are 128-bit and line up with row-major float4 loads):
 //   MMA column n of block nb  ↔  physical column 16·(nb>>1) + 4·(n>>1) + 2·(nb&1) + (n&1)

@@ -260,7 +260,10 @@ __device__ __forceinline__ float bn_dv(float dy, float h, float ref, bool has_re
 }
 
 // s1[c] = Σ_rows dV, s2[c] = Σ_rows dV·Ĥ (double atomics).  C % 4 == 0, C <= 1024.
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ dY, const float* __restrict__ H, BnBwd bn,
+// REF = false (activation selected by the recomputed pre-activation): 64 registers ⇒ 4 CTAs per SM; with 3 (84 registers) ncu showed
+// 15 resident warps on average and the two input streams at 3.3 TB/s — not enough loads in flight.
+template <bool REF>
+__global__ void __launch_bounds__(256, REF ? 3 : 4) bn_bwd_reduce_kernel(const float* __restrict__ dY, const float* __restrict__ H, BnBwd bn,
                                                             float* __restrict__ sums, int64_t M, int C, const cl::BwdFin fin) {
     __shared__ float red[256 * 8];
     pdl_trigger();
@@ -275,27 +278,29 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
         const int c = cslot * 4;
         const float4 sc = __ldg(reinterpret_cast<const float4*>(bn.scale + c)), sh = __ldg(reinterpret_cast<const float4*>(bn.shift + c));
         const float4 mu = __ldg(reinterpret_cast<const float4*>(bn.mean + c)), is = __ldg(reinterpret_cast<const float4*>(bn.invstd + c));
-        const bool has_ref = bn.act_ref != nullptr;
+        constexpr bool has_ref = REF;
         // 4 rows per thread per trip: 8-12 independent 128-bit loads in flight per thread (the kernel is pure streaming)
         constexpr int U = 4;
         const int64_t stride = (int64_t)gridDim.x * rows_per_it;
         for (int64_t m0 = (int64_t)blockIdx.x * rows_per_it + rslot; m0 < M; m0 += U * stride) {
-            float4 dy[U], h[U], rf[U];
+            float4 dy[U], h[U], rf[REF ? U : 1];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int64_t m = m0 + u * stride;
                 if (m < M) {
                     dy[u] = __ldg(reinterpret_cast<const float4*>(dY + m * C + c));
                     h[u] = __ldg(reinterpret_cast<const float4*>(H + m * C + c));
-                    rf[u] = has_ref ? __ldg(reinterpret_cast<const float4*>(bn.act_ref + m * C + c)) : make_float4(0, 0, 0, 0);
+                    if (REF) rf[u] = __ldg(reinterpret_cast<const float4*>(bn.act_ref + m * C + c));
                 } else {
-                    dy[u] = make_float4(0, 0, 0, 0); h[u] = mu; rf[u] = make_float4(0, 0, 0, 0);
+                    dy[u] = make_float4(0, 0, 0, 0); h[u] = mu;
+                    if (REF) rf[u] = make_float4(0, 0, 0, 0);
                 }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const float d0 = bn_dv(dy[u].x, h[u].x, rf[u].x, has_ref, sc.x, sh.x, bn.slope), d1 = bn_dv(dy[u].y, h[u].y, rf[u].y, has_ref, sc.y, sh.y, bn.slope);
-                const float d2 = bn_dv(dy[u].z, h[u].z, rf[u].z, has_ref, sc.z, sh.z, bn.slope), d3 = bn_dv(dy[u].w, h[u].w, rf[u].w, has_ref, sc.w, sh.w, bn.slope);
+                const float4 r = rf[REF ? u : 0];
+                const float d0 = bn_dv(dy[u].x, h[u].x, r.x, has_ref, sc.x, sh.x, bn.slope), d1 = bn_dv(dy[u].y, h[u].y, r.y, has_ref, sc.y, sh.y, bn.slope);
+                const float d2 = bn_dv(dy[u].z, h[u].z, r.z, has_ref, sc.z, sh.z, bn.slope), d3 = bn_dv(dy[u].w, h[u].w, r.w, has_ref, sc.w, sh.w, bn.slope);
                 s1[0] += d0; s1[1] += d1; s1[2] += d2; s1[3] += d3;
                 s2[0] += d0 * (h[u].x - mu.x) * is.x; s2[1] += d1 * (h[u].y - mu.y) * is.y;
                 s2[2] += d2 * (h[u].z - mu.z) * is.z; s2[3] += d3 * (h[u].w - mu.w) * is.w;
@@ -770,7 +775,8 @@ int crfconv_bn_bwd_reduce(const float* dY, const float* H, const float* act_ref,
     const int rows_per_it = 256 / (C / 4);
     static const int mult = [] { const char* e = getenv("CRFCONV_REDUCE_CTAS_PER_SM"); return e ? std::max(1, atoi(e)) : 8; }();
     const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(M, rows_per_it * 8), (int64_t)kNumSMs * mult);
-    lin::bn_bwd_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dY, H, bn, sums, M, C, cl::BwdFin{});
+    if (act_ref) lin::bn_bwd_reduce_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(dY, H, bn, sums, M, C, cl::BwdFin{});
+    else lin::bn_bwd_reduce_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(dY, H, bn, sums, M, C, cl::BwdFin{});
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }
@@ -894,10 +900,11 @@ int crfconv_bn_bwd_reduce_fin(const float* dY, const float* H, const float* act_
     }
     lin::BnBwd bn{scale, shift, mean, invstd, nullptr, nullptr, act_ref, slope};
     const int rows_per_it = 256 / (C / 4);
-    // 84 registers x 256 threads: 3 CTAs are resident per SM — exactly one wave (a 4th CTA per SM would run alone in a second wave)
-    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(M, rows_per_it * 8), (int64_t)kNumSMs * 3);   // <= cl::kMaxTicketGrid
-    CRF_CUDA(launch_k(lin::bn_bwd_reduce_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, dY, H, bn, sums, M, C,
-                      cl::BwdFin{sums, counter, (double)M, k1, k2, dgamma, dbeta}));
+    // exactly one resident wave: 3 (REF, 84 registers) or 4 (64 registers) CTAs per SM
+    const cl::BwdFin fin{sums, counter, (double)M, k1, k2, dgamma, dbeta};
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(M, rows_per_it * 8), (int64_t)kNumSMs * (act_ref ? 3 : 4));   // <= cl::kMaxTicketGrid
+    if (act_ref) CRF_CUDA(launch_k(lin::bn_bwd_reduce_kernel<true>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, dY, H, bn, sums, M, C, fin));
+    else CRF_CUDA(launch_k(lin::bn_bwd_reduce_kernel<false>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, dY, H, bn, sums, M, C, fin));
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }

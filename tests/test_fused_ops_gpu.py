@@ -260,7 +260,66 @@ def test_step_bwd_fused_matches_the_generic_kernels(B, N, corr):
                 "GM": _rel(S[F * F:].view(F, F), GM0), "k2_y": _rel(bny.k2, s2 / M, floor=float(s2.abs().max()) / M * 1e-2),
                 "dgamma_y": _rel(dg, s2, floor=float(s2.abs().max()) * 1e-2), "k1_y": float(bny.k1.abs().max())})
         assert int(cnt.abs().sum().item()) == 0
-    ops._lib.lib().crfconv_fused_tune(0, 2)
+    ops._lib.lib().crfconv_fused_tune(0, 0)
+
+
+def _pack_yx(Hy, z):
+    M = Hy.shape[0]
+    return torch.stack([Hy.view(M, 4, 4), z.view(M, 4, 4)], dim=2).reshape(M, 32).contiguous()
+
+
+@pytest.mark.parametrize("B,N", [(2, 1501), (3, 4096), (1, 40960)])
+def test_packed_mean_field_matches_the_two_table_kernels(B, N):
+    """The packed {Hy | z} layout (one 128-byte line per gathered neighbour, 256-bit loads) computes what the two-table kernels do:
+    producers (lin16_fwd's second output, upsample into the z half), forward step, fused backward step."""
+    from crfconv_b200 import ops
+    from crfconv_b200.nearest_neighbors import knn_batch
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(N + 1)
+    M, F, K, Nc = B * N, 16, 16, max(N // 4, 1)
+    Mc = B * Nc
+    pos = torch.rand(B, N, 3, generator=g).to(dev)
+    nbr = knn_batch(pos, pos, K)
+    up = torch.randint(0, Nc, (B, N), generator=g).to(dev)
+    H1 = torch.randn(M, F, generator=g).to(dev)
+    Hu = torch.randn(Mc, F, generator=g).to(dev)
+    W2 = (torch.randn(F, F, generator=g) / 4).to(dev)
+    bn1 = _bn_state(ops, F, H1.double(), torch.ones(F, device=dev), torch.zeros(F, device=dev))
+    bnu = _bn_state(ops, F, Hu.double(), (1 + 0.2 * torch.randn(F, generator=g)).to(dev), (0.1 * torch.randn(F, generator=g)).to(dev))
+    part, cnt = _scratch(ops, dev)
+    bnm = torch.nn.BatchNorm1d(F).to(dev)
+    gamma = (1 + 0.2 * torch.randn(F, generator=g)).to(dev)
+    with torch.no_grad():
+        bnm.weight.copy_(gamma)
+    bny = ops.BN(F, dev, alloc_stats=False)
+    YX = torch.full((M, 32), float("nan"), device=dev)
+    Hy = ops.lin16_fwd(H1, W2, bny, bnm, part, cnt, pre=bn1, pslope=0.1, packed_out=YX)
+    z = ops.crf_upsample_fwd(Hu, bnu, up, B, N, Nc)
+    ops.crf_upsample_fwd_packed(Hu, bnu, up, YX, B, N, Nc)
+    assert torch.equal(YX, _pack_yx(Hy, z))                    # producers: bit-identical values, no float left unwritten
+    c = (torch.eye(F) + 0.1 * torch.randn(F, F, generator=g)).to(dev)
+    Cm, Minv = ops.crf_compat_fwd(c)
+    x0 = ops.crf_step_fwd(Hy, bny.scale, z, z, nbr, Cm, Minv, B, N, K)
+    x1 = ops.crf_step_fwd_packed(YX, bny.scale, nbr, Cm, Minv, B, N)
+    _check({"x": _rel(x1, x0)}, tol=2e-6)
+    gin, xT = (torch.randn(M, F, generator=g).to(dev) for _ in range(2))
+    Qm = torch.randn(F, F, generator=g).to(dev) * 0.1
+    Qm = (Qm + Qm.T).contiguous()
+    a0 = torch.randn(F, generator=g).to(dev) * 0.1
+    n_small = 2 * F * F
+    res = []
+    for packed in (False, True):
+        slots = torch.zeros(ops.GRAD_SLOTS * n_small, device=dev)
+        Gz, gp, Gy = torch.empty(M, F, device=dev), torch.zeros(M, F, device=dev), torch.zeros(M, F, device=dev)
+        ysum = torch.zeros(128, device=dev)
+        dg, db = torch.zeros(F, device=dev), torch.zeros(F, device=dev)
+        bny.k1.zero_(); bny.k2.zero_()
+        ops.crf_step_bwd_fused(YX if packed else Hy, bny, None if packed else z, None if packed else z, nbr, Cm, Minv, gin, xT, Qm, a0,
+                               Gz, False, gp, Gy, slots, slots[F * F:], n_small, ysum, B, N, K, True, cnt, gamma, dg, db, packed=packed)
+        res.append((Gz, gp, Gy, slots.view(ops.GRAD_SLOTS, n_small).double().sum(0), bny.k2.clone(), dg))
+        assert int(cnt.abs().sum().item()) == 0
+    names = ("Gz", "gprev", "Gy", "GC|GM", "k2_y", "dgamma_y")
+    _check({n: _rel(a, b, floor=1e-6) for n, a, b in zip(names, res[1], res[0])}, tol=1e-5)   # same arithmetic; atomics reorder sums
 
 
 def test_upsample_bwd_fused():
