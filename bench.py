@@ -551,7 +551,7 @@ def run_gpu_network(args, rank, local_rank, world, dev, numa):
     import torch
     import torch.distributed as dist
     import torch.nn.functional as Fn
-    from crfconv_b200 import ops, train_dp
+    from crfconv_b200 import losses, ops, train_dp
     from crfconv_b200.distributed import FlatGradients
     from crfconv_b200.graphs import GraphedStep
     from crfconv_b200.point_conv_big import PointConvResNet
@@ -572,7 +572,7 @@ def run_gpu_network(args, rank, local_rank, world, dev, numa):
 
     def net_step():
         grads.zero()
-        loss = Fn.cross_entropy(net(data), target)
+        loss = losses.cross_entropy(net(data), target)        # the package's criterion kernels (csrc/loss.cu)
         loss.backward()
         return loss.detach()
 
@@ -616,7 +616,7 @@ def run_gpu_network(args, rank, local_rank, world, dev, numa):
         p, f, l = hp.to(dev, non_blocking=True), hf.to(dev, non_blocking=True), hl.to(dev, non_blocking=True)
         d = train_dp.make_batch(p, f, l, generator=gen)
         grads.zero()
-        loss = Fn.cross_entropy(net(d), l.reshape(-1) - 1)
+        loss = losses.cross_entropy(net(d), l.reshape(-1) - 1)
         loss.backward()
         if world > 1:
             grads.all_reduce()

@@ -70,6 +70,8 @@ SIGNATURES = {
     "crfconv_crf_compat_fwd": (_int, [_vp, _vp, _vp, _vp, _int, _vp]),
     "crfconv_crf_compat_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "crfconv_crf_upsample_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
+    "crfconv_cross_entropy_fwd": (_int, [_vp, _vp, _vp, _i64, _int, _i64, _vp, _vp]),
+    "crfconv_cross_entropy_bwd": (_int, [_vp, _vp, _vp, _i64, _int, _i64, _vp, _vp, _int, _vp, _vp]),
     "crfconv_crf_upsample_fwd_packed": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "crfconv_crf_step_fwd_packed": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     "crfconv_crf_upsample_bwd": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),

@@ -733,6 +733,10 @@ int crfconv_linear_fwd(const float* X1, int C1, const float* scale1, const float
         if (lin::try_narrow_fwd(a, st, &rc2)) return rc2;
         if (lin::try_fwd2(a, precision, st, &rc2)) return rc2;
     }
+    if (precision == 0) {
+        int rc2 = CRF_OK;
+        if (lin::try_fwd_small(a, st, &rc2)) return rc2;
+    }
     if (precision == 2) precision = 1;     // generic kernels: single-pass TF32 stands in for single-pass bf16
     return lin::dispatch_bn(Cout, [&](auto bn) {
         constexpr int BN = decltype(bn)::value;
@@ -833,7 +837,8 @@ int crfconv_linear_bwd(const float* dY, const float* H, const float* act_ref, co
         // with idx1, dX1 is the gradient wrt the GATHERED rows [M, C1]; scatter it with crfconv_scatter_add_rows
         lin::DgradArgs a{dY, H, bn, W, dX1, C1, acc1, dX2, C2, acc2, M, Cout};
         int rc = CRF_OK;
-        if (!(lin::use_fast(M) && (lin::try_dgrad3(a, precision, st, &rc) || lin::try_dgrad2(a, precision, st, &rc))))
+        if (!(lin::use_fast(M) && (lin::try_dgrad3(a, precision, st, &rc) || lin::try_dgrad2(a, precision, st, &rc))) &&
+            !(gprec == 0 && lin::try_dgrad_small(a, st, &rc)))
         rc = lin::dispatch_bn(Ktot, [&](auto bnv) {
             constexpr int BN = decltype(bnv)::value;
             dim3 grid((unsigned)ceil_div(M, lin::BM), (unsigned)ceil_div(Ktot, BN));
@@ -854,6 +859,10 @@ int crfconv_linear_bwd(const float* dY, const float* H, const float* act_ref, co
             int rc2 = CRF_OK;
             if (lin::try_wgrad3(a, precision, st, &rc2)) return rc2 != CRF_OK ? rc2 : reduce_slots();
             if (lin::try_wgrad2(a, precision, st, &rc2)) return rc2 != CRF_OK ? rc2 : reduce_slots();
+        }
+        {
+            int rc2 = CRF_OK;
+            if (gprec == 0 && lin::try_wgrad_direct(a, st, &rc2)) return rc2 != CRF_OK ? rc2 : reduce_slots();
         }
         const int ty = (int)ceil_div(Cout, 64), tz = (int)ceil_div(Ktot, 64);
         int64_t splits = std::max<int64_t>(1, std::min<int64_t>(ceil_div(M, 256), (int64_t)(2 * kNumSMs) / (ty * tz) + 1));

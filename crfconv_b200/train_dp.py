@@ -19,8 +19,8 @@ import types
 
 import torch
 import torch.distributed as dist
-import torch.nn.functional as F
 
+from . import losses
 from .distributed import FlatGradients, init_from_env
 from .multiscale import build_multiscale
 from .point_conv_big import PointConvResNet
@@ -41,12 +41,10 @@ def train_step(model, grads: FlatGradients, optimizer, data, class_weights=None,
     grads.zero()
     y_pred = model(data)
     y_target = data.y.reshape(-1) - 1                                    # trainval.py:100
-    loss_sum = F.cross_entropy(y_pred, y_target, weight=class_weights, ignore_index=ignore_index, reduction="sum")
-    valid = y_target != ignore_index
-    if class_weights is not None:
-        norm = (class_weights[y_target.clamp(min=0)] * valid).sum()
-    else:
-        norm = valid.sum().to(torch.float32)
+    # one forward and one backward kernel (csrc/loss.cu); the normaliser Σ w[t] over the non-ignored points comes with the forward
+    loss_sum, norm = losses.cross_entropy(y_pred, y_target, weight=class_weights, ignore_index=ignore_index, reduction="sum",
+                                          return_normaliser=True)
+    norm = norm.to(torch.float32)
     loss_sum.backward()
     if world_size > 1 and grads.extra.numel():
         grads.extra[0] = norm

@@ -279,6 +279,14 @@ int crfconv_spmm_fwd(const float* x, const int64_t* eptr, const int64_t* col, co
 int crfconv_spmm_bwd(const float* x, const int64_t* eptr, const int64_t* col, const float* w, const float* g, float* dw, float* dx, int64_t N,
                      int C, void* stream);
 
+/* ------------------------------------------------------- training criterion (trainval.py:66-70,100-104: class-weighted cross entropy)
+ * sums[0] += Σ w[t]·(logsumexp(x) − x[t]), sums[1] += Σ w[t] over the rows whose target != ignore_index (two zeroed doubles); C <= 64.
+ * The backward recomputes the softmax: dlogits = g·w[t]·(softmax − onehot), g = *gout (mean == 0) or *gout / sums[1] (mean != 0). */
+int crfconv_cross_entropy_fwd(const float* logits, const int64_t* target, const float* weight, int64_t M, int C, int64_t ignore_index,
+                              double* sums, void* stream);
+int crfconv_cross_entropy_bwd(const float* logits, const int64_t* target, const float* weight, int64_t M, int C, int64_t ignore_index,
+                              const double* sums, const float* gout, int mean, float* dlogits, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.nn.functional as Fn
 
-from crfconv_b200 import train_dp
+from crfconv_b200 import losses, train_dp
 from crfconv_b200.distributed import FlatGradients
 from crfconv_b200.point_conv_big import PointConvResNet
 
@@ -25,7 +25,7 @@ target = (lab.reshape(-1) - 1).contiguous()
 torch.cuda.synchronize()
 for _ in range(steps):
     grads.zero()
-    loss = Fn.cross_entropy(net(data), target)
+    loss = losses.cross_entropy(net(data), target)
     loss.backward()
     torch.cuda.synchronize()
 print("done", float(loss))

@@ -35,3 +35,23 @@ def rel_err_trimmed(a, b, floor=0.0, outlier_frac=2e-5):
     if k:
         d = np.partition(d, d.size - k - 1)[: d.size - k]
     return float(d.max() / max(np.abs(b).max(), floor, 1e-30))
+
+
+def rel_err_rows_trimmed(a, b, floor=0.0, max_rows=None):
+    """(max-norm error, L2 error, rows over 1e-3) of a [rows, C] gradient after setting aside the `max_rows` rows that deviate most
+    (default: 0.4 % of the rows, at least 2).
+    Why rows: a LeakyReLU unit whose pre-activation sits within rounding of 0 may take the other branch than the oracle (the batch
+    statistics are summed in a different order); its backward factor changes by O(1) and with it the WHOLE row of the input
+    gradient dX[i, :] = dH[i, :]·W of that point — C entries, more than the entry-wise trimming of `rel_err_trimmed` sets aside on
+    wide layers with few rows.  Every other row must meet the tolerance."""
+    a = np.asarray(a, dtype=np.float64)
+    a = a.reshape(-1, a.shape[-1])
+    b = np.asarray(b, dtype=np.float64).reshape(a.shape)
+    d = np.abs(a - b).max(axis=1)
+    if max_rows is None:
+        max_rows = max(2, int(np.ceil(0.004 * len(d))))
+    order = np.argsort(d)
+    keep = order[: max(len(order) - max_rows, 1)]
+    scale = max(np.abs(b).max(), floor, 1e-30)
+    l2 = np.linalg.norm((a - b)[keep]) / max(np.linalg.norm(b[keep]), floor * np.sqrt(b[keep].size), 1e-30)
+    return float(d[keep].max() / scale), float(l2), int((d > 1e-3 * scale).sum())

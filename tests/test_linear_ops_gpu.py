@@ -26,6 +26,7 @@ def rel(a, b):
 SHAPES = [  # (M, C1, C2, Cout)
     (9000, 128, 0, 16), (9000, 64, 0, 16), (9000, 16, 0, 16), (9000, 16, 0, 64), (9000, 64, 64, 64), (8200, 8, 0, 8),
     (8200, 32, 32, 32), (8200, 8, 0, 32), (8200, 64, 0, 8), (12345, 32, 0, 8), (8200, 64, 0, 64), (8200, 128, 0, 64), (8200, 6, 0, 32),
+    (1000, 256, 256, 128), (960, 128, 0, 512), (3841, 512, 0, 256), (1280, 256, 256, 256), (320, 512, 0, 64), (1280, 256, 0, 64),      # deep levels: few rows, wide channels (linear_small.cu)
 ]
 
 
@@ -88,12 +89,13 @@ def test_linear_fwd_and_bwd(ops, fast, M, C1, C2, Cout):
         L.crfconv_set_fast_path(prev)
 
 
+@pytest.mark.parametrize("C1,Cout", [(16, 64), (64, 128)])
 @pytest.mark.parametrize("fast", [0, 1])
-def test_residual_activation_reference(ops, fast):
+def test_residual_activation_reference(ops, fast, C1, Cout):
     """act_ref path: the LeakyReLU branch is taken from a saved output (ResNetBBlock's lrelu(BN(h)+residual), point_conv_big.py:88)."""
     from crfconv_b200 import _lib
     L = _lib.lib()
-    M, C1, Cout = 8300, 16, 64
+    M = 8300
     g = torch.Generator(device="cuda").manual_seed(7)
     rn = lambda *s: torch.randn(*s, generator=g, device="cuda")   # noqa: E731
     X1, W, R, dY = rn(M, C1), rn(Cout, C1) / 4, rn(M, Cout), rn(M, Cout)
@@ -122,3 +124,45 @@ def test_residual_activation_reference(ops, fast):
         assert rel(dX, dH @ W.double()) < tol and rel(dW, dH.t() @ X1.double()) < tol
     finally:
         L.crfconv_set_fast_path(prev)
+
+
+@pytest.mark.parametrize("M,C1,Cout,bn_on,bias,gather", [(245760, 128, 13, False, True, False), (50001, 32, 128, True, False, False),
+                                                         (30000, 6, 8, True, False, False), (3840, 32, 16, True, False, True),
+                                                         (977, 8, 32, False, True, True), (15, 64, 13, False, True, False)])
+def test_wgrad_direct_kernel_shapes(ops, M, C1, Cout, bn_on, bias, gather):
+    """The fragment-order weight-gradient kernel (linear_direct.cu) on the shapes the tiled kernels do not cover: Cout = 13 / 128,
+    6 input channels, bias gradient, gathered rows (Upsampling.lin), ragged row counts."""
+    g = torch.Generator(device="cuda").manual_seed(M + C1 + Cout)
+    rn = lambda *s: torch.randn(*s, generator=g, device="cuda")   # noqa: E731
+    B, rows_dst = 3, M // 3 if M % 3 == 0 else M
+    if M % 3:
+        B = 1
+    rows_src = max(rows_dst // 4, 1)
+    Xs = rn(B * rows_src if gather else M, C1)
+    idx = torch.randint(0, rows_src, (M,), generator=g, device="cuda") if gather else None
+    W = rn(Cout, C1) / C1 ** 0.5
+    dY = rn(M, Cout)
+    A = Xs.double()
+    if gather:
+        A = A[(torch.arange(M, device="cuda") // rows_dst) * rows_src + idx]
+    H = bn = None
+    dH = dY.double()
+    if bn_on:
+        H = (A @ W.double().t()).float()
+        gamma, beta = 1 + 0.2 * rn(Cout), 0.2 * rn(Cout)
+        bn = ops.BN(Cout, dY.device)
+        st = torch.cat([H.double().sum(0), (H.double() ** 2).sum(0)]).float()
+        bn.stats.zero_(); bn.stats.view(-1, 2 * Cout)[0].copy_(st)
+        ops.bn_finalize_fwd(bn, M, gamma, beta, 1e-5, 0.1, True, None, None)
+        Hd = H.double()
+        mu, var = Hd.mean(0), Hd.var(0, unbiased=False)
+        Hh = (Hd - mu) * (var + 1e-5).rsqrt()
+        dV = torch.where(Hh * gamma.double() + beta.double() > 0, dY.double(), dY.double() * 0.1)
+        ops.bn_backward_prepare(dY, H, bn, 0.1, torch.zeros(Cout, device="cuda"), torch.zeros(Cout, device="cuda"))
+        dH = gamma.double() * (var + 1e-5).rsqrt() * (dV - dV.mean(0) - Hh * (dV * Hh).mean(0))
+    dW = torch.zeros_like(W)
+    db = torch.zeros(Cout, device="cuda") if bias else None
+    ops.linear_bwd(dY, H, bn, 0.1 if bn_on else 1.0, Xs, W, idx1=idx, rows_dst=rows_dst, rows_src=rows_src, dW=dW, dbias=db)
+    assert rel(dW, dH.t() @ A) < 2e-5
+    if bias:
+        assert rel(db, dH.sum(0)) < 2e-5

@@ -105,3 +105,33 @@ def test_direct_gradient_accumulation_equals_autograd_accumulation():
     a, b = flats
     assert float((a - b).abs().max()) <= 2e-4 * float(a.abs().max()), float((a - b).abs().max() / a.abs().max())
     assert float(b.abs().max()) > 0
+
+
+@pytest.mark.parametrize("M,C,weighted,ignore", [(245760, 13, True, -1), (5001, 19, False, 3), (7, 8, True, -100), (4096, 40, True, 0)])
+def test_cross_entropy_matches_torch(M, C, weighted, ignore):
+    """csrc/loss.cu vs F.cross_entropy (fp64): loss, normaliser and gradient for 'mean' and 'sum', class weights, ignore_index."""
+    import torch.nn.functional as Fn
+    from crfconv_b200 import losses
+    g = torch.Generator().manual_seed(M + C)
+    x = (3 * torch.randn(M, C, generator=g)).cuda()
+    t = torch.randint(0, C, (M,), generator=g).cuda()
+    if ignore >= 0:
+        t[::5] = ignore
+    elif M > 10:
+        t[::7] = ignore
+    w = (0.5 + torch.rand(C, generator=g)).cuda() if weighted else None
+    for red in ("mean", "sum"):
+        xa = x.clone().requires_grad_(True)
+        xb = x.double().clone().requires_grad_(True)
+        la, norm = losses.cross_entropy(xa, t, weight=w, ignore_index=ignore, reduction=red, return_normaliser=True)
+        lb = Fn.cross_entropy(xb, t, weight=w.double() if weighted else None, ignore_index=ignore, reduction=red)
+        (2.5 * la).backward()
+        (2.5 * lb).backward()
+        assert abs(float(la) - float(lb)) <= 1e-5 * abs(float(lb))
+        valid = t != ignore
+        nref = (w[t.clamp(min=0)] * valid).sum().double() if weighted else valid.sum().double()
+        assert abs(float(norm) - float(nref)) <= 1e-6 * float(nref)
+        err = (xa.grad.double() - xb.grad).abs().max() / xb.grad.abs().max()
+        assert float(err) < 1e-5, (red, float(err))
+        if bool((~valid).any()):
+            assert float(xa.grad[~valid].abs().max()) == 0.0
