@@ -9,6 +9,8 @@ signatures and ``state_dict`` keys, running on the sm_100a kernels:
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F  # noqa: F401  (kept for API parity with the reference module)
@@ -70,6 +72,85 @@ class _PointConvFunction(torch.autograd.Function):
         return (dx.view(B, Ns, d) if dx is not None else None, None, None, None, dW1, dg1, db1, dW2, dg2, db2, None, None, None, None, None)
 
 
+FUSED_EDGE_MLP = os.environ.get("CRFCONV_FUSED_POINTCONV", "1") != "0"
+_REL_CACHE = {"key": None, "val": None}
+
+
+def _relpos_moments_cached(sup, cen, nbr):
+    """Relative positions and their moments depend on the geometry only: the two ResNet blocks of a level (conv1_1 / conv1_2: same
+    positions, same neighbour table) share one pass.  Single-entry cache keyed on the storage and version counters of the inputs
+    (an in-place update, e.g. the input copy before a CUDA-graph replay, bumps the version; replays re-run the captured launch)."""
+    key = (sup.data_ptr(), cen.data_ptr(), nbr.data_ptr(), tuple(sup.shape), tuple(cen.shape), tuple(nbr.shape), sup._version, cen._version,
+           nbr._version, torch.cuda.is_current_stream_capturing())
+    if _REL_CACHE["key"] == key:
+        return _REL_CACHE["val"]
+    mom = torch.zeros(ops.STAT_SLOTS * 9, dtype=torch.float32, device=sup.device)
+    rel = ops.pcf_relpos_moments(sup, cen, nbr, mom)
+    _REL_CACHE["key"], _REL_CACHE["val"] = key, (rel, mom, sup, cen, nbr)     # the inputs are kept alive so that the addresses stay theirs
+    return _REL_CACHE["val"]
+
+
+class _PointConvFusedFunction(torch.autograd.Function):
+    """The same layer with the 3→d→d edge MLP recomputed from the relative positions in every pass (csrc/pointconv_fused.cu, d = 8):
+    no [E, d] tensor is written — BN1 statistics come from the moments of r, BN2 statistics and out = sc2 ⊙ Σ h2 ⊙ x_j + sh2 ⊙ Σ x_j
+    from one pass, the backward needs two passes and derives dW1 / dW2 from per-matrix sums."""
+
+    @staticmethod
+    def forward(ctx, x, support, centres, idx, W1, g1, b1, W2, g2, b2, bn1, bn2, slope1, gbuf=None):
+        if not x.is_cuda:
+            raise RuntimeError("crfconv_b200 layers run on CUDA tensors only (no CPU fallback)")
+        B, Ns, d = x.shape
+        Nq, K = idx.shape[1], idx.shape[2]
+        E = B * Nq * K
+        dev = x.device
+        x2 = ops.as2d(x)
+        sup = support.detach().float().contiguous()
+        cen = centres.detach().float().contiguous()
+        nbr = idx.detach().contiguous().to(torch.int64)
+        W1c, W2c = W1.detach().contiguous().float(), W2.detach().contiguous().float()
+        S = ops.STAT_SLOTS
+        nf, _ = ops.pcf_scratch_floats()
+        z = ops.Flat(nf, torch.float32, dev)                    # one zero fill: BN1 statistics | BN2 statistics | activation sums
+        stats1, stats2, asum = z.take(S * 2 * d), z.take(S * 2 * d), z.take(S * (d + d * (d + 1) // 2))
+        rel, mom = _relpos_moments_cached(sup, cen, nbr)[:2]                               # [E, 3], Σr, Σrrᵀ
+        st1, fin1 = bn_forward_state(d, dev, E, bn1, True, stats1)
+        ops.pcf_stats1(mom, W1c, stats1); fin1()                                          # h1 = W1·r is linear in r
+        st2, fin2 = bn_forward_state(d, dev, E, bn2, True, stats2)
+        P, Q = ops.pcf_fwd(x2, rel, nbr, W1c, W2c, st1, slope1, stats2, asum, B, Ns, Nq, K); fin2()
+        out = ops.pcf_out(P, Q, st2)
+        ctx.dims, ctx.st, ctx.slope1 = (B, Ns, Nq, K, d), (st1, st2), slope1
+        ctx.gbuf = gbuf if (gbuf is not None and all(b is not None for b in gbuf)) else None
+        ctx.save_for_backward(x2, nbr, rel, W1c, W2c, mom, asum)
+        return out.view(B, Nq, d)
+
+    @staticmethod
+    def backward(ctx, g):
+        x2, nbr, rel, W1c, W2c, mom, asum = ctx.saved_tensors
+        B, Ns, Nq, K, d = ctx.dims
+        st1, st2 = ctx.st
+        dev = g.device
+        g2 = ops.as2d(g)
+        if ctx.gbuf is not None:
+            dW1, dg1, db1, dW2, dg2, db2 = ctx.gbuf
+        else:
+            small = ops.Flat(W1c.numel() + W2c.numel() + 4 * d, torch.float32, dev)
+            dW1, dW2 = small.take(*W1c.shape), small.take(*W2c.shape)
+            dg1, db1, dg2, db2 = (small.take(d) for _ in range(4))
+        S = ops.STAT_SLOTS
+        _, nb = ops.pcf_scratch_floats()
+        z = ops.Flat(nb, torch.float32, dev)
+        sums2, mdw, sums1, s1 = z.take(S * 2 * d), z.take(S * d * d), z.take(S * 2 * d), z.take(S * 3 * d)
+        dx = torch.zeros_like(x2) if ctx.needs_input_grad[0] else None
+        ops.pcf_bwd1(x2, rel, nbr, g2, W1c, W2c, st1, ctx.slope1, st2, dx, sums2, mdw, B, Ns, Nq, K)
+        ops.bn_finalize_bwd(sums2, st2, dg2, db2)
+        ops.pcf_bwd2(x2, rel, nbr, g2, W1c, W2c, st1, ctx.slope1, st2, sums1, s1, B, Ns, Nq, K)
+        ops.bn_finalize_bwd(sums1, st1, dg1, db1)
+        ops.pcf_param_grads(mom, asum, mdw, s1, W1c, W2c, st1, st2, dW1, dW2)
+        if ctx.gbuf is not None:
+            return (dx.view(B, Ns, d) if dx is not None else None,) + (None,) * 13
+        return (dx.view(B, Ns, d) if dx is not None else None, None, None, None, dW1, dg1, db1, dW2, dg2, db2, None, None, None, None)
+
+
 class _GatherMax(torch.autograd.Function):
     """out[b,i,:] = max_k x[b, idx[b,i,k], :]   (ResNetBBlock.max_pooling, point_conv_big.py:74-77)."""
 
@@ -124,6 +205,11 @@ class PointConv(nn.Module):
             raise RuntimeError("PointConv: weight_nn must keep the reference's (LeakyReLU, None) activations to be fused")
         b1, b2 = m1.bn.batch_norm, m2.bn.batch_norm
         from .common import direct_grad_buffers
+        if (FUSED_EDGE_MLP and x.is_cuda and x.shape[-1] == ops.pcf_width() and x.dtype == torch.float32 and
+                (self.training or not (b1.track_running_stats or b2.track_running_stats))):
+            return _PointConvFusedFunction.apply(x, support, centres, neighbor_idx, m1.lin.weight, b1.weight, b1.bias, m2.lin.weight,
+                                                 b2.weight, b2.bias, b1, b2, m1.slope,
+                                                 direct_grad_buffers(m1.lin.weight, b1.weight, b1.bias, m2.lin.weight, b2.weight, b2.bias))
         return _PointConvFunction.apply(x, support, centres, neighbor_idx, m1.lin.weight, b1.weight, b1.bias, m2.lin.weight, b2.weight,
                                         b2.bias, b1, b2, self.training, m1.slope,
                                         direct_grad_buffers(m1.lin.weight, b1.weight, b1.bias, m2.lin.weight, b2.weight, b2.bias))
