@@ -534,6 +534,82 @@ __global__ void __launch_bounds__(256) compat_bwd_kernel(const float* __restrict
     }
 }
 
+// Shared-memory versions for F <= 64 (the network's decoder has F = 8, 16, 32, 64): the augmented matrix of the Gauss-Jordan sweep
+// and all operands of the three products live in shared memory, 1024 threads.  The global-scratch kernels above paid three dependent
+// global round trips per pivot (286 us forward / 375 us backward at F = 64, ≈0.5 ms of a PointConvResNet step on its critical path).
+__global__ void __launch_bounds__(1024) compat_fwd_smem_kernel(const float* __restrict__ c, float* __restrict__ Cm, float* __restrict__ Minv,
+                                                               int F) {
+    extern __shared__ __align__(16) double sm_d[];              // aug [F][2F] | colp [F] | c as doubles [F][F]
+    pdl_trigger();
+    pdl_wait();
+    double* aug = sm_d;
+    double* colp = aug + F * 2 * F;
+    double* cs = colp + F;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < F * F; i += nt) cs[i] = (double)c[i];
+    __syncthreads();
+    for (int i = tid; i < F * F; i += nt) {
+        const int r = i / F, cc = i % F;
+        double s = 0.0;
+        for (int k = 0; k < F; ++k) s += cs[k * F + r] * cs[k * F + cc];
+        Cm[i] = (float)s;
+        aug[r * 2 * F + cc] = s + (r == cc ? 1.0 : 0.0);
+        aug[r * 2 * F + F + cc] = (r == cc ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    // thread (r0, j) owns column j of rows r0, r0 + rstep, ...: no index arithmetic inside the sweep (the 1024-thread CTA is issue-bound;
+    // a div / mod per element made a pivot cost 2 us)
+    const int W = 2 * F, j = tid % W, r0 = tid / W, rstep = nt / W;          // W divides nt (W <= 128, nt = 256 or 1024)
+    for (int pcol = 0; pcol < F; ++pcol) {
+        const double ip = 1.0 / aug[pcol * W + pcol];
+        const double pj = aug[pcol * W + j] * ip;                // scaled pivot-row entry of this thread's column
+        if (tid < F) colp[tid] = aug[tid * W + pcol];
+        __syncthreads();
+        for (int r = r0; r < F; r += rstep) {
+            if (r != pcol) aug[r * W + j] -= colp[r] * pj;
+            else aug[r * W + j] = pj;
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < F * F; i += nt) Minv[i] = (float)aug[(i / F) * 2 * F + F + (i % F)];
+}
+
+__global__ void __launch_bounds__(1024) compat_bwd_smem_kernel(const float* __restrict__ c, const float* __restrict__ Minv,
+                                                               const float* __restrict__ GC, const float* __restrict__ GM, float* Gc, int F) {
+    extern __shared__ __align__(16) double sm_d[];              // T [F][F+1] | G [F][F+1] | then floats: Minv [F][F+1], GM / c [F][F+1]
+    pdl_trigger();
+    pdl_wait();
+    const int L = F + 1;                                        // odd pitch: column walks (stride L) are bank-conflict free
+    double* T = sm_d;
+    double* G = T + F * L;
+    float* Ms = reinterpret_cast<float*>(G + F * L);
+    float* Xs = Ms + F * L;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < F * F; i += nt) { Ms[(i / F) * L + i % F] = Minv[i]; Xs[(i / F) * L + i % F] = GM[i]; }
+    __syncthreads();
+    for (int i = tid; i < F * F; i += nt) {                     // T = Minvᵀ·GM
+        const int r = i / F, cc = i % F;
+        double s = 0.0;
+        for (int k = 0; k < F; ++k) s += (double)Ms[k * L + r] * (double)Xs[k * L + cc];
+        T[r * L + cc] = s;
+    }
+    __syncthreads();
+    for (int i = tid; i < F * F; i += nt) {                     // G = GC − T·Minvᵀ
+        const int r = i / F, cc = i % F;
+        double s = 0.0;
+        for (int k = 0; k < F; ++k) s += T[r * L + k] * (double)Ms[cc * L + k];
+        G[r * L + cc] = (double)GC[i] - s;
+    }
+    for (int i = tid; i < F * F; i += nt) Xs[(i / F) * L + i % F] = c[i];   // GM's last reads are behind the barrier above
+    __syncthreads();
+    for (int i = tid; i < F * F; i += nt) {                     // Gc += c·(G + Gᵀ)
+        const int r = i / F, cc = i % F;
+        double s = 0.0;
+        for (int k = 0; k < F; ++k) s += (double)Xs[r * L + k] * (G[k * L + cc] + G[cc * L + k]);
+        Gc[i] += (float)s;
+    }
+}
+
 template <typename Fn>
 inline int dispatch_f(int F, Fn&& fn) {
     switch (F) {
@@ -555,6 +631,14 @@ extern "C" {
 
 int crfconv_crf_compat_fwd(const float* c, float* Cm, float* Minv, double* scratch, int F, void* stream) {
     if (!c || !Cm || !Minv || !scratch || F <= 0 || F > 128) return CRF_ERR_INVALID_ARG;
+    if (F <= 64) {
+        const size_t smem = ((size_t)F * 2 * F + F + (size_t)F * F) * sizeof(double);
+        static bool attr = false;
+        if (!attr) { CRF_CUDA(cudaFuncSetAttribute(mf::compat_fwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024)); attr = true; }
+        CRF_CUDA(launch_k(mf::compat_fwd_smem_kernel, dim3(1), dim3(F >= 32 ? 1024 : 256), smem, (cudaStream_t)stream, c, Cm, Minv, F));
+        CRF_LAUNCH_CHECK();
+        return CRF_OK;
+    }
     CRF_CUDA(launch_k(mf::compat_fwd_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, c, Cm, Minv, scratch, F));
     CRF_LAUNCH_CHECK();
     return CRF_OK;
@@ -563,6 +647,14 @@ int crfconv_crf_compat_fwd(const float* c, float* Cm, float* Minv, double* scrat
 int crfconv_crf_compat_bwd(const float* c, const float* Minv, const float* GC, const float* GM, float* Gc, double* scratch, int F,
                            void* stream) {
     if (!c || !Minv || !GC || !GM || !Gc || !scratch || F <= 0 || F > 128) return CRF_ERR_INVALID_ARG;
+    if (F <= 64) {
+        const size_t smem = (size_t)2 * F * (F + 1) * sizeof(double) + (size_t)2 * F * (F + 1) * sizeof(float);
+        static bool attr = false;
+        if (!attr) { CRF_CUDA(cudaFuncSetAttribute(mf::compat_bwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024)); attr = true; }
+        CRF_CUDA(launch_k(mf::compat_bwd_smem_kernel, dim3(1), dim3(F >= 32 ? 1024 : 256), smem, (cudaStream_t)stream, c, Minv, GC, GM, Gc, F));
+        CRF_LAUNCH_CHECK();
+        return CRF_OK;
+    }
     CRF_CUDA(launch_k(mf::compat_bwd_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, c, Minv, GC, GM, Gc, scratch, F));
     CRF_LAUNCH_CHECK();
     return CRF_OK;

@@ -863,6 +863,7 @@ int crfconv_linear_bwd(const float* dY, const float* H, const float* act_ref, co
         {
             int rc2 = CRF_OK;
             if (gprec == 0 && lin::try_wgrad_direct(a, st, &rc2)) return rc2 != CRF_OK ? rc2 : reduce_slots();
+            if (gprec == 0 && lin::try_wgrad_rows(a, st, &rc2)) return rc2 != CRF_OK ? rc2 : reduce_slots();
         }
         const int ty = (int)ceil_div(Cout, 64), tz = (int)ceil_div(Ktot, 64);
         int64_t splits = std::max<int64_t>(1, std::min<int64_t>(ceil_div(M, 256), (int64_t)(2 * kNumSMs) / (ty * tz) + 1));

@@ -65,6 +65,7 @@ bool try_wgrad_direct(const WgradArgs& a, cudaStream_t st, int* rc);
 // few rows, wide channels (deep levels): 32-row tiles with register prefetch (linear_small.cu)
 bool try_fwd_small(const FwdArgs& a, cudaStream_t st, int* rc);
 bool try_dgrad_small(const DgradArgs& a, cudaStream_t st, int* rc);
+bool try_wgrad_rows(WgradArgs a, cudaStream_t st, int* rc);
 // CUDA-core kernels for hidden-width layers (linear_narrow.cu); w == nullptr ⇒ dgrad only
 bool try_narrow_fwd(const FwdArgs& a, cudaStream_t st, int* rc);
 bool try_narrow_bwd(const DgradArgs& d, const WgradArgs* w, cudaStream_t st, int* rc);

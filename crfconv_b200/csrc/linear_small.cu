@@ -245,7 +245,128 @@ __global__ void __launch_bounds__(kThreads) dgrad_small_kernel(const DgradArgs a
     }
 }
 
-// experiment knob: CRFCONV_NO_SMALL = 1 (no forward), 2 (no input gradient), 3 (neither)
+// ------------------------------------------------------------------------------------------------------------- weight gradient
+// dW[co, k] += Σ_m dH[m, co]·A[m, k] for few rows and a WIDE output (e.g. 512 × 256 at 960 rows): 64 × 64 output tile per CTA, the
+// rows split over blockIdx.x in 32-row steps with the next step's dH / A float4s prefetched into registers (the generic kernel
+// reloads 64-row tiles synchronously with scalar, per-element-guarded loads: 35-65 us for ≈4 MB).  Partial tiles meet in the
+// kGradSlots slots (or directly in dW) through fp32 atomics, like lin::wgrad_kernel.
+template <bool REF>
+__global__ void __launch_bounds__(kThreads) wgrad_rows_kernel(const WgradArgs a) {
+    constexpr int WS = 64 + 8;
+    __shared__ __align__(16) float Ds[BM][WS];                   // dH rows   [m][co]
+    __shared__ __align__(16) float Xs[BM][WS];                   // A rows    [m][k]
+    __shared__ float4 s_par[64];
+    __shared__ float2 s_pro[64];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int Ktot = a.C1 + a.C2, C = a.Cout;
+    const int co0 = blockIdx.y * 64, k0 = blockIdx.z * 64;
+    const int64_t mbeg = (int64_t)blockIdx.x * a.rows_per_cta, mend = min(a.M, mbeg + a.rows_per_cta);
+    const bool plain = a.bn.scale == nullptr;
+    if (tid < 64) {
+        float4 pr = make_float4(1.f, 0.f, 0.f, 0.f);
+        const int k = co0 + tid;
+        if (!plain && k < C) {
+            const float sc = __ldg(a.bn.scale + k), sh = __ldg(a.bn.shift + k), mu = __ldg(a.bn.mean + k), is = __ldg(a.bn.invstd + k);
+            const float k1 = __ldg(a.bn.k1 + k), k2 = __ldg(a.bn.k2 + k);
+            pr = make_float4(sc, sh, -sc * is * k2, -sc * k1 + sc * is * k2 * mu);
+        }
+        s_par[tid] = pr;
+        float2 pp = make_float2(1.f, 0.f);
+        const int kk = k0 + tid;
+        if (a.scale1 && kk < a.C1) pp = make_float2(__ldg(a.scale1 + kk), __ldg(a.shift1 + kk));
+        s_pro[tid] = pp;
+    }
+    const int wr = (w & 3) * 16, wc = (w >> 2) * 32;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) acc[i][jj] = 0.0f;
+    const int c16 = tid & 15, rr = tid >> 4;                      // 16 float4 per 64-wide row, 16 rows per pass, 2 passes per step
+    const int cD = co0 + 4 * c16, cX = k0 + 4 * c16;
+    const bool okD = cD < C, okX = cX < Ktot, seg1 = cX < a.C1;
+    float4 rd[2], rh[2], rf[2], rx[2];
+    bool rok[2];
+    auto gload = [&](int64_t mt) {
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+            const int64_t m = mt + rr + 16 * jj;
+            rok[jj] = m < mend;
+            rd[jj] = rh[jj] = rf[jj] = rx[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rok[jj] && okD) {
+                rd[jj] = ldg4(a.dY + m * C + cD);
+                if (!plain) rh[jj] = ldg4(a.H + m * C + cD);
+                if (REF) rf[jj] = ldg4(a.bn.act_ref + m * C + cD);
+            }
+            if (rok[jj] && okX) {
+                if (seg1) {
+                    int64_t srow = m;
+                    if (a.idx1) srow = (m / a.rows_dst) * a.rows_src + __ldg(a.idx1 + m);
+                    rx[jj] = ldg4(a.X1 + srow * a.C1 + cX);
+                } else {
+                    rx[jj] = ldg4(a.X2 + m * a.C2 + (cX - a.C1));
+                }
+            }
+        }
+    };
+    auto sstore = [&]() {
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+            const int r = rr + 16 * jj;
+            float4 d = rd[jj];
+            if (!plain && rok[jj] && okD) {
+                const float dy[4] = {rd[jj].x, rd[jj].y, rd[jj].z, rd[jj].w}, h[4] = {rh[jj].x, rh[jj].y, rh[jj].z, rh[jj].w};
+                const float ref[4] = {rf[jj].x, rf[jj].y, rf[jj].z, rf[jj].w};
+                float o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float4 p = s_par[4 * c16 + e];
+                    const float pre = REF ? ref[e] : fmaf(h[e], p.x, p.y);
+                    const float dv = pre > 0.f ? dy[e] : dy[e] * a.bn.slope;
+                    o[e] = fmaf(p.x, dv, fmaf(p.z, h[e], p.w));
+                }
+                d = make_float4(o[0], o[1], o[2], o[3]);
+            }
+            *reinterpret_cast<float4*>(&Ds[r][4 * c16]) = d;
+            float4 x = rx[jj];
+            if (a.scale1 && seg1 && rok[jj] && okX) {
+                const float2 p0 = s_pro[4 * c16], p1 = s_pro[4 * c16 + 1], p2 = s_pro[4 * c16 + 2], p3 = s_pro[4 * c16 + 3];
+                x = make_float4(lrelu(fmaf(x.x, p0.x, p0.y), a.slope1), lrelu(fmaf(x.y, p1.x, p1.y), a.slope1),
+                                lrelu(fmaf(x.z, p2.x, p2.y), a.slope1), lrelu(fmaf(x.w, p3.x, p3.y), a.slope1));
+            }
+            *reinterpret_cast<float4*>(&Xs[r][4 * c16]) = x;
+        }
+    };
+    gload(mbeg);
+    __syncthreads();                                              // s_par / s_pro visible
+    for (int64_t mt = mbeg; mt < mend; mt += BM) {
+        sstore();
+        __syncthreads();
+        if (mt + BM < mend) gload(mt + BM);
+#pragma unroll
+        for (int ks = 0; ks < BM / 8; ++ks) {
+            const float af[4] = {Ds[ks * 8 + t][wr + g], Ds[ks * 8 + t][wr + g + 8], Ds[ks * 8 + t + 4][wr + g], Ds[ks * 8 + t + 4][wr + g + 8]};
+            FragA fa;
+            make_frag_a<true>(fa, af);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                FragB fb;
+                make_frag_b<true>(fb, Xs[ks * 8 + t][wc + nt * 8 + g], Xs[ks * 8 + t + 4][wc + nt * 8 + g]);
+                mma_frag<true>(acc[nt], fa, fb);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int co = co0 + wr + g + (e >= 2 ? 8 : 0), k = k0 + wc + nt * 8 + 2 * t + (e & 1);
+            if (co < C && k < Ktot) atomicAdd(a.dW + a.slot_stride * (blockIdx.x % kGradSlots) + (int64_t)co * Ktot + k, acc[nt][e]);
+        }
+}
+
+// experiment knob: CRFCONV_NO_SMALL bit mask: 1 = no forward, 2 = no input gradient, 4 = no weight gradient
 inline int disabled_mask() {
     static const int v = [] { const char* e = std::getenv("CRFCONV_NO_SMALL"); return e ? std::atoi(e) : 0; }();
     return v;
@@ -288,6 +409,25 @@ bool try_dgrad_small(const DgradArgs& a, cudaStream_t st, int* rc) {
     const bool ref = a.bn.scale && a.bn.act_ref;
     if (BN == 64) { if (ref) dgrad_small_kernel<64, true><<<grid, kThreads, smem, st>>>(a); else dgrad_small_kernel<64, false><<<grid, kThreads, smem, st>>>(a); }
     else          { if (ref) dgrad_small_kernel<32, true><<<grid, kThreads, smem, st>>>(a); else dgrad_small_kernel<32, false><<<grid, kThreads, smem, st>>>(a); }
+    const cudaError_t e = cudaPeekAtLastError();
+    *rc = e == cudaSuccess ? CRF_OK : (int)e;
+    return true;
+}
+
+bool try_wgrad_rows(WgradArgs a, cudaStream_t st, int* rc) {
+    using namespace sm;
+    const int Ktot = a.C1 + a.C2;
+    if (disabled_mask() & 4) return false;
+    if (a.dbias || (a.Cout & 3) || (a.C1 & 3) || (a.C2 & 3) || a.C1 <= 0 || a.Cout < 32 || Ktot < 32) return false;
+    if (!al16(a.dY) || !al16(a.X1) || (a.C2 && !al16(a.X2)) || (a.bn.scale && !al16(a.H)) || (a.bn.scale && a.bn.act_ref && !al16(a.bn.act_ref))) return false;
+    const int ty = (int)ceil_div(a.Cout, 64), tz = (int)ceil_div(Ktot, 64);
+    if (!few_rows(a.M, 1)) return false;
+    int64_t splits = std::max<int64_t>(1, std::min<int64_t>(ceil_div(a.M, (int64_t)BM), (int64_t)(3 * kNumSMs) / (ty * tz) + 1));
+    a.rows_per_cta = ceil_div(ceil_div(a.M, splits), (int64_t)BM) * BM;
+    splits = ceil_div(a.M, a.rows_per_cta);
+    dim3 grid((unsigned)splits, (unsigned)ty, (unsigned)tz);
+    if (a.bn.scale && a.bn.act_ref) wgrad_rows_kernel<true><<<grid, kThreads, 0, st>>>(a);
+    else wgrad_rows_kernel<false><<<grid, kThreads, 0, st>>>(a);
     const cudaError_t e = cudaPeekAtLastError();
     *rc = e == cudaSuccess ? CRF_OK : (int)e;
     return true;

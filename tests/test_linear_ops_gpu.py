@@ -128,10 +128,12 @@ def test_residual_activation_reference(ops, fast, C1, Cout):
 
 @pytest.mark.parametrize("M,C1,Cout,bn_on,bias,gather", [(245760, 128, 13, False, True, False), (50001, 32, 128, True, False, False),
                                                          (30000, 6, 8, True, False, False), (3840, 32, 16, True, False, True),
-                                                         (977, 8, 32, False, True, True), (15, 64, 13, False, True, False)])
+                                                         (977, 8, 32, False, True, True), (15, 64, 13, False, True, False),
+                                                         (3840, 256, 128, True, False, True), (961, 512, 256, False, False, False)])
 def test_wgrad_direct_kernel_shapes(ops, M, C1, Cout, bn_on, bias, gather):
     """The fragment-order weight-gradient kernel (linear_direct.cu) on the shapes the tiled kernels do not cover: Cout = 13 / 128,
-    6 input channels, bias gradient, gathered rows (Upsampling.lin), ragged row counts."""
+    6 input channels, bias gradient, gathered rows (Upsampling.lin), ragged row counts; the last two cases are wide outputs over few
+    rows (linear_small.cu wgrad_rows_kernel), one of them gathered."""
     g = torch.Generator(device="cuda").manual_seed(M + C1 + Cout)
     rn = lambda *s: torch.randn(*s, generator=g, device="cuda")   # noqa: E731
     B, rows_dst = 3, M // 3 if M % 3 == 0 else M
