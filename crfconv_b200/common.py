@@ -42,6 +42,26 @@ def _slope_of(activation):
     return None
 
 
+# When a list, BatchNorm layers append their num_batches_tracked buffers here instead of launching one `+= 1` kernel each; whoever set
+# it (PointConvResNet.forward) bumps them all with one torch._foreach_add_ (46 launches → 1 per step).
+_NBT_DEFER = None
+
+
+def deferred_counters_begin():
+    global _NBT_DEFER
+    if _NBT_DEFER is not None:
+        return False
+    _NBT_DEFER = []
+    return True
+
+
+def deferred_counters_end():
+    global _NBT_DEFER
+    lst, _NBT_DEFER = _NBT_DEFER, None
+    if lst:
+        torch._foreach_add_(lst, 1)
+
+
 def bn_forward_state(C, device, count, bn_module, training, stats=None, defer_counters=None):
     """Allocates the per-call BN scratch; returns (state, finalize) where finalize() must run after the producing GEMM.
     `defer_counters` (a list): collect the num_batches_tracked buffers instead of bumping each with its own kernel; the caller
@@ -53,7 +73,9 @@ def bn_forward_state(C, device, count, bn_module, training, stats=None, defer_co
                             bn_module.momentum if bn_module.momentum is not None else 0.1, training,
                             bn_module.running_mean, bn_module.running_var)
         if training and bn_module.track_running_stats and bn_module.num_batches_tracked is not None:
-            if defer_counters is not None:
+            if _NBT_DEFER is not None:
+                _NBT_DEFER.append(bn_module.num_batches_tracked)
+            elif defer_counters is not None:
                 defer_counters.append(bn_module.num_batches_tracked)
             else:
                 bn_module.num_batches_tracked.add_(1)

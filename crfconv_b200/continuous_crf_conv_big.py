@@ -84,7 +84,7 @@ class _CRFConvFunction(torch.autograd.Function):
         def tr(bn):
             return training or not bn.track_running_stats
 
-        fstats = ops.Flat(ops.STAT_SLOTS * 2 * (4 * F + 2 * Co), torch.float32, dev)
+        fstats = ops.Flat(ops.STAT_SLOTS * 2 * (4 * F + 2 * Co), torch.float32, dev, scratch=True)
         nbt = []
 
         # unary_nn / pairwise_nn, layer 1 and 2 (:58-59) — two independent chains on two streams; every buffer is allocated on the
@@ -305,7 +305,7 @@ class _CRFConvFusedFunction(torch.autograd.Function):
 
         # one zero-filled allocation: [tcgen05 statistics slots of out_nn and fusion_nn | 8 counters]; partial-sum scratches need no init
         CI = ops.counter_ints()
-        zf = ops.Flat(2 * ops.STAT_SLOTS * 2 * Co + 8 * CI, torch.float32, dev)
+        zf = ops.Flat(2 * ops.STAT_SLOTS * 2 * Co + 8 * CI, torch.float32, dev, scratch=True)
         st_o, st_f = zf.take(ops.STAT_SLOTS * 2 * Co), zf.take(ops.STAT_SLOTS * 2 * Co)
         cnt = zf.take(8 * CI).view(torch.int32).view(8, CI)
         parts = torch.empty((4, NP), dtype=torch.float32, device=dev)
@@ -346,7 +346,10 @@ class _CRFConvFusedFunction(torch.autograd.Function):
         Hf = ops.linear_fwd_bn(H3, Wf, sf, bns[5], cnt[5], scale1=so.scale, shift1=so.shift, slope1=sl[4], X2=P)   # fusion_nn (:76)
         out = ops.bn_act_fwd(Hf, sf, sl[5])
         nbt = [b.num_batches_tracked for b in bns if b.track_running_stats and b.num_batches_tracked is not None]
-        if nbt:
+        from . import common as _common
+        if nbt and _common._NBT_DEFER is not None:
+            _common._NBT_DEFER.extend(nbt)                # bumped once per step by the network's forward
+        elif nbt:
             torch._foreach_add_(nbt, 1)
 
         ctx.dims = (B, N, Nc, K, F, Co, Cu, Cp, steps)

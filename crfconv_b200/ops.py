@@ -80,6 +80,50 @@ def as2d(x):
     return x.reshape(-1, x.shape[-1]).contiguous()
 
 
+# ---- per-step arena for scratch that is zero on entry and consumed inside the call that takes it -------------------------------------
+# A PointConvResNet step needs ≈130 small zero-initialised buffers (BatchNorm Σ / Σ² slots, backward sums, weight-gradient partial
+# slots): as separate torch.zeros they are 130 fill kernels per step (≈0.35 ms of launches in a 7 ms step).  The network's forward
+# calls scratch_begin_step(): ONE memset re-zeroes what the previous step dirtied, and zeros_scratch() hands out slices.  Invariant:
+# arena[off:] is all zeros.  Only for buffers that are dead when the call that took them returns (never for saved / returned tensors).
+class _ZeroArena:
+    CAP = 16 * 1024 * 1024          # floats (64 MB)
+
+    def __init__(self, device):
+        self.buf = torch.zeros(self.CAP, dtype=torch.float32, device=device)
+        self.off = 0
+
+
+_ARENAS = {}
+
+
+def _arena_key(device):
+    device = torch.device(device)
+    return device.index if device.index is not None else torch.cuda.current_device()
+
+
+def scratch_begin_step(device):
+    """Start of a step (the network's forward): re-zero the part of the arena the previous step used and rewind."""
+    key = _arena_key(device)
+    a = _ARENAS.get(key)
+    if a is None:
+        if torch.cuda.is_current_stream_capturing():
+            return                                   # never allocate the arena inside a graph's private pool
+        a = _ARENAS[key] = _ZeroArena(device)
+    if a.off:
+        a.buf[:a.off].zero_()
+    a.off = 0
+
+
+def zeros_scratch(numel, device):
+    a = _ARENAS.get(_arena_key(device))
+    n = (int(numel) + 63) & ~63                      # 256-byte granules
+    if a is None or a.off + n > a.CAP:
+        return torch.zeros(int(numel), dtype=torch.float32, device=device)
+    v = a.buf[a.off:a.off + int(numel)]
+    a.off += n
+    return v
+
+
 class BN:
     """Per-BatchNorm scratch: slotted f32 Σ/Σ² partial accumulators, fused affine (scale, shift), saved mean/invstd, backward k1/k2."""
     __slots__ = ("C", "stats", "scale", "shift", "mean", "invstd", "k1", "k2", "count", "training")
@@ -87,7 +131,7 @@ class BN:
     def __init__(self, C, device, stats=None, alloc_stats=True):
         self.C = C
         if stats is None and alloc_stats:
-            stats = torch.zeros(STAT_SLOTS * 2 * C, dtype=torch.float32, device=device)   # zeroed
+            stats = zeros_scratch(STAT_SLOTS * 2 * C, device)   # zeroed; consumed by the finalize right after the producing GEMM
         self.stats = stats
         buf = torch.empty(6, C, dtype=torch.float32, device=device)
         self.scale, self.shift, self.mean, self.invstd, self.k1, self.k2 = buf.unbind(0)
@@ -126,8 +170,9 @@ def grad_slots_reduce(scratch, dW_flat, n, stride):
 class Flat:
     """One zero-filled allocation carved into views (a single memset instead of one fill kernel per small tensor)."""
 
-    def __init__(self, numel, dtype, device):
-        self.buf = torch.zeros(int(numel), dtype=dtype, device=device)
+    def __init__(self, numel, dtype, device, scratch=False):
+        """scratch=True: every view dies inside the call that takes it (zeros_scratch arena)."""
+        self.buf = zeros_scratch(numel, device) if (scratch and dtype == torch.float32) else torch.zeros(int(numel), dtype=dtype, device=device)
         self.off = 0
 
     def take(self, *shape):
@@ -163,7 +208,7 @@ def bn_backward_prepare(dY, H, bn: BN, slope, dgamma, dbeta, act_ref=None, sums=
     `sums` (optional) = zero-initialised f64 scratch of STAT_SLOTS·2·C entries."""
     L = _lib.lib()
     if sums is None:
-        sums = torch.zeros(STAT_SLOTS * 2 * bn.C, dtype=torch.float32, device=H.device)
+        sums = zeros_scratch(STAT_SLOTS * 2 * bn.C, H.device)
     with _call(f"bn_bwd_reduce[{bn.C}]", 1, _nbytes(dY, H, act_ref)):
         rc = L.crfconv_bn_bwd_reduce(_p(dY), _p(H), _p(act_ref), _p(bn.scale), _p(bn.shift), _p(bn.mean), _p(bn.invstd), float(slope),
                                      _p(sums), H.shape[0], bn.C, _lib.stream_ptr())
@@ -187,7 +232,7 @@ def linear_bwd(dY, H, bn, slope, X1, W, *, scale1=None, shift1=None, slope1=1.0,
     if dW is not None and Cout * (C1 + C2) > 1024 and scratch_stride == 0:
         scratch = None      # wide outputs: a CTA's adds are spread over >1024 addresses, direct atomics are cheaper than a reduce pass
     elif dW is not None and scratch is None:
-        scratch = torch.zeros(GRAD_SLOTS * Cout * (C1 + C2), dtype=torch.float32, device=dY.device)
+        scratch = zeros_scratch(GRAD_SLOTS * Cout * (C1 + C2), dY.device)
     nb = _nbytes(dY, H if b else None, act_ref, X1 if dW is not None else None, X2 if dW is not None else None, dX1, dX2,
                  dX1 if acc1 else None, dX2 if acc2 else None)
     with _call(f"linear_bwd[{Cout}<-{C1 + C2}]" + ("" if dW is not None else ":dgrad") + ("" if (dX1 is not None or dX2 is not None) else ":wgrad"),

@@ -138,7 +138,7 @@ class _PointConvFusedFunction(torch.autograd.Function):
             dg1, db1, dg2, db2 = (small.take(d) for _ in range(4))
         S = ops.STAT_SLOTS
         _, nb = ops.pcf_scratch_floats()
-        z = ops.Flat(nb, torch.float32, dev)
+        z = ops.Flat(nb, torch.float32, dev, scratch=True)
         sums2, mdw, sums1, s1 = z.take(S * 2 * d), z.take(S * d * d), z.take(S * 2 * d), z.take(S * 3 * d)
         dx = torch.zeros_like(x2) if ctx.needs_input_grad[0] else None
         ops.pcf_bwd1(x2, rel, nbr, g2, W1c, W2c, st1, ctx.slope1, st2, dx, sums2, mdw, B, Ns, Nq, K)
@@ -293,6 +293,16 @@ class PointConvResNet(Base):
         )
 
     def forward(self, data):
+        from . import common as _common
+        ops.scratch_begin_step(data.x.device)               # one memset instead of ≈130 zero-fill kernels (ops.zeros_scratch)
+        owner = _common.deferred_counters_begin()           # one num_batches_tracked bump instead of 46
+        try:
+            return self._forward(data)
+        finally:
+            if owner:
+                _common.deferred_counters_end()
+
+    def _forward(self, data):
         x, multiscale = data.x, data.multiscale
 
         x1 = self.conv1_1(x, multiscale[0].pos, multiscale[0].neighbor_idx)
