@@ -318,9 +318,16 @@ __global__ void __launch_bounds__(256, REF ? 3 : 4) bn_bwd_reduce_kernel(const f
         const int c = cs * 4 + (e & 3);
         atomicAdd(sums + (size_t)(blockIdx.x % (fin.part ? 32 : kStatSlots)) * 2 * C + (e < 4 ? 0 : C) + c, tot);
     }
-    if (fin.part) {                                               // k1 / k2 / dγ / dβ by the last CTA (C == 64, checked by the launcher)
+    if (fin.part) {                                               // k1 / k2 / dγ / dβ by the last CTA (C <= 128, checked by the launcher)
         __shared__ double s_red[256];
-        cl::bwd_fin_tail<64, 256>(fin, 32, s_red);
+        if (!cl::arrive_is_last(fin.counter)) return;
+        if (tid < 2 * C) {
+            double acc = 0.0;
+            for (int p = 0; p < 32; ++p) acc += (double)__ldcg(fin.part + (size_t)p * 2 * C + tid);
+            s_red[tid] = acc;
+        }
+        __syncthreads();
+        if (tid < C) cl::bn_bwd_finalize(fin, s_red[tid], s_red[C + tid], tid);
     }
 }
 
@@ -903,7 +910,7 @@ int crfconv_bn_bwd_reduce_fin(const float* dY, const float* H, const float* act_
                               const float* mean, const float* invstd, float slope, float* sums, int64_t M, int C, unsigned int* counter,
                               float* k1, float* k2, float* dgamma, float* dbeta, void* stream) {
     if (!sums || !counter || !k1 || !k2) return CRF_ERR_INVALID_ARG;
-    if (C != 64 || M <= 0) {
+    if (C > 128 || C < 4 || (C & 3) || (256 % (C / 4)) != 0 || M <= 0) {
         const int rc = crfconv_bn_bwd_reduce(dY, H, act_ref, scale, shift, mean, invstd, slope, sums, M, C, stream);
         if (rc != CRF_OK) return rc;
         return crfconv_bn_finalize_bwd(sums, M, k1, k2, dgamma, dbeta, C, stream);

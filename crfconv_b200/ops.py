@@ -209,13 +209,22 @@ def bn_backward_prepare(dY, H, bn: BN, slope, dgamma, dbeta, act_ref=None, sums=
     L = _lib.lib()
     if sums is None:
         sums = zeros_scratch(STAT_SLOTS * 2 * bn.C, H.device)
-    with _call(f"bn_bwd_reduce[{bn.C}]", 1, _nbytes(dY, H, act_ref)):
-        rc = L.crfconv_bn_bwd_reduce(_p(dY), _p(H), _p(act_ref), _p(bn.scale), _p(bn.shift), _p(bn.mean), _p(bn.invstd), float(slope),
-                                     _p(sums), H.shape[0], bn.C, _lib.stream_ptr())
-    _lib.check(rc, "bn_bwd_reduce")
-    COUNTERS["launches"] += 1
-    rc = L.crfconv_bn_finalize_bwd(_p(sums), bn.count, _p(bn.k1), _p(bn.k2), _p(dgamma), _p(dbeta), bn.C, _lib.stream_ptr())
-    _lib.check(rc, "bn_finalize_bwd")
+    if bn.C <= 128 and bn.count == H.shape[0]:
+        # one launch: the last CTA of the reduction folds the slots into k1 / k2 / dγ / dβ (two-level arrival tickets)
+        counter = zeros_scratch(counter_ints(), H.device)
+        with _call(f"bn_bwd_reduce[{bn.C}]", 1, _nbytes(dY, H, act_ref)):
+            rc = L.crfconv_bn_bwd_reduce_fin(_p(dY), _p(H), _p(act_ref), _p(bn.scale), _p(bn.shift), _p(bn.mean), _p(bn.invstd), float(slope),
+                                             _p(sums), H.shape[0], bn.C, _p(counter), _p(bn.k1), _p(bn.k2), _p(dgamma), _p(dbeta),
+                                             _lib.stream_ptr())
+        _lib.check(rc, "bn_bwd_reduce_fin")
+    else:
+        with _call(f"bn_bwd_reduce[{bn.C}]", 1, _nbytes(dY, H, act_ref)):
+            rc = L.crfconv_bn_bwd_reduce(_p(dY), _p(H), _p(act_ref), _p(bn.scale), _p(bn.shift), _p(bn.mean), _p(bn.invstd), float(slope),
+                                         _p(sums), H.shape[0], bn.C, _lib.stream_ptr())
+        _lib.check(rc, "bn_bwd_reduce")
+        COUNTERS["launches"] += 1
+        rc = L.crfconv_bn_finalize_bwd(_p(sums), bn.count, _p(bn.k1), _p(bn.k2), _p(dgamma), _p(dbeta), bn.C, _lib.stream_ptr())
+        _lib.check(rc, "bn_finalize_bwd")
     if not bn.training:      # eval-mode BN is a fixed affine map: dH = scale·dV
         bn.k1.zero_()
         bn.k2.zero_()
