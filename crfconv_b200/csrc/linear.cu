@@ -743,6 +743,7 @@ int crfconv_linear_fwd(const float* X1, int C1, const float* scale1, const float
     if (precision == 0) {
         int rc2 = CRF_OK;
         if (lin::try_fwd_small(a, st, &rc2)) return rc2;
+        if (lin::try_upproj_fwd(a, st, &rc2)) return rc2;
     }
     if (precision == 2) precision = 1;     // generic kernels: single-pass TF32 stands in for single-pass bf16
     return lin::dispatch_bn(Cout, [&](auto bn) {
@@ -845,7 +846,7 @@ int crfconv_linear_bwd(const float* dY, const float* H, const float* act_ref, co
         lin::DgradArgs a{dY, H, bn, W, dX1, C1, acc1, dX2, C2, acc2, M, Cout};
         int rc = CRF_OK;
         if (!(lin::use_fast(M) && (lin::try_dgrad3(a, precision, st, &rc) || lin::try_dgrad2(a, precision, st, &rc))) &&
-            !(gprec == 0 && lin::try_dgrad_small(a, st, &rc)))
+            !(gprec == 0 && (lin::try_dgrad_small(a, st, &rc) || lin::try_upproj_dgrad(a, st, &rc))))
         rc = lin::dispatch_bn(Ktot, [&](auto bnv) {
             constexpr int BN = decltype(bnv)::value;
             dim3 grid((unsigned)ceil_div(M, lin::BM), (unsigned)ceil_div(Ktot, BN));

@@ -62,6 +62,8 @@ bool try_wgrad3(const WgradArgs& a, int precision, cudaStream_t st, int* rc);   
 bool try_dgrad3(const DgradArgs& a, int precision, cudaStream_t st, int* rc);   // linear3d.cu
 // narrow layers over many rows: operands straight from global memory in fragment order (linear_direct.cu)
 bool try_wgrad_direct(const WgradArgs& a, cudaStream_t st, int* rc);
+bool try_upproj_fwd(const FwdArgs& a, cudaStream_t st, int* rc);      // narrow input → wide output (output-bound streams)
+bool try_upproj_dgrad(const DgradArgs& a, cudaStream_t st, int* rc);
 // few rows, wide channels (deep levels): 32-row tiles with register prefetch (linear_small.cu)
 bool try_fwd_small(const FwdArgs& a, cudaStream_t st, int* rc);
 bool try_dgrad_small(const DgradArgs& a, cudaStream_t st, int* rc);

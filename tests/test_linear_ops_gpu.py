@@ -168,3 +168,32 @@ def test_wgrad_direct_kernel_shapes(ops, M, C1, Cout, bn_on, bias, gather):
     assert rel(dW, dH.t() @ A) < 2e-5
     if bias:
         assert rel(db, dH.sum(0)) < 2e-5
+
+
+@pytest.mark.parametrize("M,K,N,pro", [(245760, 32, 128, False), (20001, 32, 128, True), (9000, 8, 64, True), (8200, 6, 32, False), (8193, 16, 128, False)])
+def test_up_projection_forward(ops, M, K, N, pro):
+    """Narrow input → wide output (linear_direct.cu upproj_kernel): H, Σ / Σ² statistics, optional BN + LeakyReLU prologue."""
+    g = torch.Generator(device="cuda").manual_seed(M + K + N)
+    rn = lambda *s: torch.randn(*s, generator=g, device="cuda")   # noqa: E731
+    X, W = rn(M, K) + 0.3, rn(N, K) / K ** 0.5
+    sc, sh = (1 + 0.2 * rn(K), 0.2 * rn(K)) if pro else (None, None)
+    bn = ops.BN(N, X.device)
+    H = ops.linear_fwd(X, W, scale1=sc, shift1=sh, slope1=0.1, stats=bn.stats)
+    A = X.double()
+    if pro:
+        A = lrelu(A * sc.double() + sh.double(), 0.1)
+    Hr = A @ W.double().t()
+    assert rel(H, Hr) < 2e-5
+    st = bn.stats.view(-1, 2 * N).double().sum(0)
+    assert rel(st[:N], Hr.sum(0)) < 1e-4 and rel(st[N:], (Hr ** 2).sum(0)) < 1e-4
+
+
+@pytest.mark.parametrize("M,Cout,Ktot", [(245760, 13, 128), (20001, 19, 128), (9000, 8, 64), (8200, 13, 32)])
+def test_up_projection_input_gradient(ops, M, Cout, Ktot):
+    """dX = dY[M, Cout]·W[Cout, Ktot] of a plain Linear with few outputs (the class head) — same kernel, weights indexed transposed."""
+    g = torch.Generator(device="cuda").manual_seed(M + Cout)
+    rn = lambda *s: torch.randn(*s, generator=g, device="cuda")   # noqa: E731
+    dY, W, X = rn(M, Cout), rn(Cout, Ktot) / Ktot ** 0.5, rn(M, Ktot)
+    dX = torch.full((M, Ktot), float("nan"), device="cuda")
+    ops.linear_bwd(dY, None, None, 1.0, X, W, dX1=dX)
+    assert rel(dX, dY.double() @ W.double()) < 2e-5
