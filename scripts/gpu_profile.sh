@@ -9,6 +9,7 @@ timeout 300 python bench.py --steps 100 --warmup 5 2>/dev/null | tail -1 > gpuru
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -1 > gpurun_out/bench_${tag}_reference.json
 for c in C3 C4 C5; do timeout 400 python bench.py --config $c --steps 20 2>/dev/null | tail -1 > gpurun_out/bench_${tag}_$c.json; done
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/ncu_launches_$tag.csv python scripts/step_once.py 2 > /dev/null 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/net_launches_$tag.csv python scripts/net_once.py 3 > /dev/null 2>&1
 timeout 900 ncu --set full --clock-control none --csv --page raw --log-file gpurun_out/ncu_full_$tag.csv python scripts/step_once.py 1 > /dev/null 2>&1
 timeout 300 python scripts/knn_sub_profile.py time > gpurun_out/knn_sub_$tag.txt 2>&1
 ls -la gpurun_out | tail -12

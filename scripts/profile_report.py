@@ -139,9 +139,12 @@ def metrics_csv(path, out_json=None, skip_prefixes=("at::", "knn::")):
         name = short(r[iK])
         rec = {"kernel": name}
         for k, i in cols:
-            if i is None or r[i] in ("", "n/a"):
+            if i is None or r[i] in ("", "n/a", "no data"):
                 continue
-            v = float(r[i].replace(",", ""))
+            try:
+                v = float(r[i].replace(",", ""))
+            except ValueError:
+                continue
             u = units[i]
             if k == "us":
                 v = v / 1e3 if u in ("ns", "nsecond") else (v * 1e3 if u in ("ms", "msecond") else v)
