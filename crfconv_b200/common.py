@@ -62,6 +62,21 @@ def deferred_counters_end():
         torch._foreach_add_(lst, 1)
 
 
+# Weight gradients feed nothing downstream in the backward pass.  At the deep levels of the network (≤ 2,560 points per cloud) the input-
+# gradient and weight-gradient kernels of a layer are latency-bound launches on 30-300 CTAs each: the weight gradient runs on its own
+# stream (a parallel branch of the captured graph) and is joined before the layer's backward returns.
+import os as _os
+WGRAD_SIDE_MAX_ROWS = int(_os.environ.get("CRFCONV_WGRAD_SIDE_MAX_ROWS", "16384"))
+_WGRAD_STREAMS = {}
+
+
+def _wgrad_side_stream(dev):
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _WGRAD_STREAMS:
+        _WGRAD_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _WGRAD_STREAMS[key]
+
+
 def bn_forward_state(C, device, count, bn_module, training, stats=None, defer_counters=None):
     """Allocates the per-call BN scratch; returns (state, finalize) where finalize() must run after the producing GEMM.
     `defer_counters` (a list): collect the num_batches_tracked buffers instead of bumping each with its own kernel; the caller
@@ -159,13 +174,26 @@ class _LinearBNAct(torch.autograd.Function):
                 st.k1.zero_(); st.k2.zero_()   # activation without BN: fixed affine (scale 1)
             else:
                 st = None
-        ops.linear_bwd(g2, H, st, slope, a1, Wc, idx1=gidx, rows_dst=rows_dst, rows_src=rows_src, X2=a2, dX1=dX1, dX2=dX2, dW=dW,
-                       dbias=dbias)
+        join = None
+        if (dX1 is not None or dX2 is not None) and M <= WGRAD_SIDE_MAX_ROWS:
+            main, ws = torch.cuda.current_stream(dev), _wgrad_side_stream(dev)
+            fork, join = torch.cuda.Event(), torch.cuda.Event()
+            fork.record(main)
+            ws.wait_event(fork)
+            with torch.cuda.stream(ws):                      # dW (and dbias): a parallel branch
+                ops.linear_bwd(g2, H, st, slope, a1, Wc, idx1=gidx, rows_dst=rows_dst, rows_src=rows_src, X2=a2, dW=dW, dbias=dbias)
+                join.record(ws)
+            ops.linear_bwd(g2, H, st, slope, a1, Wc, idx1=gidx, rows_dst=rows_dst, rows_src=rows_src, X2=a2, dX1=dX1, dX2=dX2)
+        else:
+            ops.linear_bwd(g2, H, st, slope, a1, Wc, idx1=gidx, rows_dst=rows_dst, rows_src=rows_src, X2=a2, dX1=dX1, dX2=dX2, dW=dW,
+                           dbias=dbias)
         s1, s2, sR = ctx.shapes
         if dX1 is not None and gidx is not None:           # gradient wrt gathered rows → scatter onto the source rows
             full = torch.zeros((s1[0] * s1[1], s1[2]), dtype=torch.float32, device=dev)
             ops.scatter_add_rows(dX1, gidx, full, s1[0], rows_dst, rows_src)
             dX1 = full
+        if join is not None:
+            torch.cuda.current_stream(dev).wait_event(join)
         return (dX1.view(s1) if dX1 is not None else None, dX2.view(s2) if dX2 is not None else None, None,
                 dR.view(sR) if (dR is not None and nig[3]) else None, dW if (nig[4] and not direct[0]) else None,
                 dbias if (nig[5] and not direct[1]) else None, dgamma if (nig[6] and not direct[2]) else None,

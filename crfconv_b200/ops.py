@@ -83,14 +83,15 @@ def as2d(x):
 # ---- per-step arena for scratch that is zero on entry and consumed inside the call that takes it -------------------------------------
 # A PointConvResNet step needs ≈130 small zero-initialised buffers (BatchNorm Σ / Σ² slots, backward sums, weight-gradient partial
 # slots): as separate torch.zeros they are 130 fill kernels per step (≈0.35 ms of launches in a 7 ms step).  The network's forward
-# calls scratch_begin_step(): ONE memset re-zeroes what the previous step dirtied, and zeros_scratch() hands out slices.  Invariant:
-# arena[off:] is all zeros.  Only for buffers that are dead when the call that took them returns (never for saved / returned tensors).
+# calls scratch_begin_step(): ONE memset re-zeroes what earlier steps dirtied, and zeros_scratch() hands out slices.  Invariant after
+# begin_step: the whole arena is zero; during a step arena[off:] is zero.  Only for buffers that are dead when the call that took them returns (never for saved / returned tensors).
 class _ZeroArena:
     CAP = 16 * 1024 * 1024          # floats (64 MB)
 
     def __init__(self, device):
         self.buf = torch.zeros(self.CAP, dtype=torch.float32, device=device)
         self.off = 0
+        self.hw = 0                 # highest offset any step reached: a captured step replays its memset / its slices without telling Python
 
 
 _ARENAS = {}
@@ -109,8 +110,9 @@ def scratch_begin_step(device):
         if torch.cuda.is_current_stream_capturing():
             return                                   # never allocate the arena inside a graph's private pool
         a = _ARENAS[key] = _ZeroArena(device)
-    if a.off:
-        a.buf[:a.off].zero_()
+    a.hw = max(a.hw, a.off)
+    if a.hw:
+        a.buf[:a.hw].zero_()                         # everything any earlier step (eager or a graph replay) may have dirtied
     a.off = 0
 
 
