@@ -70,16 +70,16 @@ SIGNATURES = {
     "crfconv_crf_compat_fwd": (_int, [_vp, _vp, _vp, _vp, _int, _vp]),
     "crfconv_crf_compat_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "crfconv_crf_upsample_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
-    "crfconv_pcf_width": (_int, []),
-    "crfconv_pcf_fwd_scratch_floats": (_int, []),
-    "crfconv_pcf_bwd_scratch_floats": (_int, []),
+    "crfconv_pcf_supported": (_int, [_int]),
+    "crfconv_pcf_fwd_scratch_floats": (_int, [_int]),
+    "crfconv_pcf_bwd_scratch_floats": (_int, [_int]),
     "crfconv_pcf_relpos_moments": (_int, [_vp] * 5 + [_i64, _i64, _i64, _int, _vp]),
-    "crfconv_pcf_stats1": (_int, [_vp, _vp, _vp, _vp]),
-    "crfconv_pcf_fwd": (_int, [_vp] * 7 + [_f32] + [_vp] * 4 + [_i64, _i64, _i64, _int, _vp]),
-    "crfconv_pcf_out": (_int, [_vp] * 5 + [_i64, _vp]),
-    "crfconv_pcf_bwd1": (_int, [_vp] * 8 + [_f32] + [_vp] * 7 + [_i64, _i64, _i64, _int, _vp]),
-    "crfconv_pcf_bwd2": (_int, [_vp] * 8 + [_f32] + [_vp] * 9 + [_i64, _i64, _i64, _int, _vp]),
-    "crfconv_pcf_param_grads": (_int, [_vp] * 19),
+    "crfconv_pcf_stats1": (_int, [_vp, _vp, _vp, _int, _vp]),
+    "crfconv_pcf_fwd": (_int, [_vp] * 7 + [_f32] + [_vp] * 4 + [_i64, _i64, _i64, _int, _int, _vp]),
+    "crfconv_pcf_out": (_int, [_vp] * 5 + [_i64, _int, _vp]),
+    "crfconv_pcf_bwd1": (_int, [_vp] * 8 + [_f32] + [_vp] * 7 + [_i64, _i64, _i64, _int, _int, _vp]),
+    "crfconv_pcf_bwd2": (_int, [_vp] * 8 + [_f32] + [_vp] * 9 + [_i64, _i64, _i64, _int, _int, _vp]),
+    "crfconv_pcf_param_grads": (_int, [_vp] * 18 + [_int, _vp]),
     "crfconv_cross_entropy_fwd": (_int, [_vp, _vp, _vp, _i64, _int, _i64, _vp, _vp]),
     "crfconv_cross_entropy_bwd": (_int, [_vp, _vp, _vp, _i64, _int, _i64, _vp, _vp, _int, _vp, _vp]),
     "crfconv_crf_upsample_fwd_packed": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),

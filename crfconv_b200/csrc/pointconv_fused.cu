@@ -1,5 +1,6 @@
-// PointConv (models/point_conv_big.py:8-58) without per-edge tensors, hidden width d = 8 (level 0 of PointConvResNet: 245,760 points,
-// 3.9 M edges — the [E, 8] tensors H1, H2, dWgt, dA1 of the layer-by-layer path are 126 MB each and cost 0.87 ms per PointConv).
+// PointConv (models/point_conv_big.py:8-58) without per-edge tensors, hidden width d = 8 / 16 (levels 0 and 1 of PointConvResNet: 245,760
+// points and 3.9 M edges at d = 8 — the [E, 8] tensors H1, H2, dWgt, dA1 of the layer-by-layer path are 126 MB each and cost 0.87 ms per
+// PointConv — and 983 k edges at d = 16).
 //
 //   w_e = BN2( W2·lrelu(BN1(W1·r_e)) ),  r_e = c_i − s_j,  out_i = Σ_k w_ik ⊙ x_j          (BatchNorm over all E edges)
 //
@@ -12,8 +13,9 @@
 //             param_grads      dW2 and dW1 from the sums alone (the BatchNorm backward is affine in per-edge quantities):
 //                 dW2[c,b] = sc2[c]·( Σdw[c]a1[b] − k1'[c]·Σa1[b] − k2'[c]·is2[c]·( (W2·Σa1a1ᵀ)[c,b] − mu2[c]·Σa1[b] ) )
 //                 dW1[c,a] = sc1[c]·( Σdv1[c]r[a] − k1[c]·Σr[a]  − k2[c]·is1[c]·( (W1·Σrrᵀ)[c,a]   − mu1[c]·Σr[a]  ) )
-// One thread owns one centre point and walks its K edges; plain fp32 FMAs (no tensor cores: 8×8), sums go to kStatSlots partial
-// slots and are folded in double precision.  Positions carry no gradient (as in the layer-by-layer path).
+// One thread owns 8 channels of one centre point (d / 8 adjacent lanes per point; h1 / a1 are computed redundantly, h2 and everything
+// downstream for the own channels; the input-gradient pass exchanges dh2 by shuffle) and walks the point's K edges; plain fp32 FMAs, sums
+// go to kStatSlots partial slots and are folded in double precision.  Positions carry no gradient (as in the layer-by-layer path).
 #include <algorithm>
 
 #include "../../include/crfconv_b200.h"
@@ -22,10 +24,9 @@
 namespace crf {
 namespace pcf {
 
-constexpr int D = 8, kThreads = 128;
+constexpr int DC = 8;                      // channels per thread
+constexpr int kThreads = 128;
 constexpr int kMom = 9;                    // Σr (3) | Σrrᵀ upper triangle xx xy xz yy yz zz (6)
-constexpr int kTri = D * (D + 1) / 2;      // 36
-constexpr int kASum = D + kTri;            // Σa1 | Σa1a1ᵀ upper triangle (row-major, b <= c)
 
 __device__ __forceinline__ float lrelu(float v, float s) { return v > 0.f ? v : v * s; }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -33,24 +34,22 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// block-wide sum of NV per-thread values into slot (blockIdx.x % kStatSlots) of a [kStatSlots][NV] float buffer
-template <int NV>
-__device__ __forceinline__ void block_sums_to_slot(float (&v)[NV], float* slots, float* s_red /* [kThreads / 32][NV] */) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// Sum of a per-thread array over all threads of the CTA that own the same channel block, into slot (blockIdx.x % kStatSlots) of a
+// [kStatSlots][total] float buffer.  map(i, blk) = position of local element i of channel block blk in the global layout.
+template <int LPP, int NV, typename Map>
+__device__ __forceinline__ void block_sums_to_slot(float (&v)[NV], float* slots, int total, float* s_acc, Map map) {
+    const int lane = threadIdx.x & 31, blk = lane % LPP;
+    for (int i = threadIdx.x; i < total; i += kThreads) s_acc[i] = 0.f;
+    __syncthreads();
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         float x = v[i];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 0) s_red[warp * NV + i] = x;
+        for (int o = 16; o >= LPP; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane < LPP) atomicAdd(&s_acc[map(i, blk)], x);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < NV; i += kThreads) {
-        float tot = 0.f;
-#pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) tot += s_red[w * NV + i];
-        atomicAdd(slots + (size_t)(blockIdx.x % kStatSlots) * NV + i, tot);
-    }
+    for (int i = threadIdx.x; i < total; i += kThreads) atomicAdd(slots + (size_t)(blockIdx.x % kStatSlots) * total + i, s_acc[i]);
     __syncthreads();
 }
 
@@ -99,12 +98,9 @@ __device__ __forceinline__ double sym3(const double* t, int a, int b) {
     const int lo = a < b ? a : b, hi = a < b ? b : a;
     return t[lo == 0 ? hi : (lo == 1 ? 2 + hi : 5)];
 }
-__device__ __forceinline__ int tri(int b, int c) {        // b <= c
-    return b * D - b * (b - 1) / 2 + (c - b);
-}
 
 // Σh1[c] = W1[c]·Σr,  Σh1²[c] = W1[c]ᵀ·(Σrrᵀ)·W1[c]   → slot 0 of a [kStatSlots][2D] BatchNorm statistics buffer (other slots stay zero)
-__global__ void stats1_kernel(const float* __restrict__ mom, const float* __restrict__ W1, float* stats1) {
+__global__ void stats1_kernel(const float* __restrict__ mom, const float* __restrict__ W1, float* stats1, int D) {
     __shared__ double m[kMom];
     if (threadIdx.x < kMom) m[threadIdx.x] = fold_slots(mom, kMom, threadIdx.x);
     __syncthreads();
@@ -120,20 +116,24 @@ __global__ void stats1_kernel(const float* __restrict__ mom, const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------------------- the edge MLP, recomputed
+template <int D>
 struct EdgeW {                              // shared-memory image of the weights and the BatchNorm-1 affine
     float4 W1[D];                           // (w0, w1, w2, 0)
-    float4 W2[D][D / 4];                    // row c: W2[c][0..7]
+    float4 W2[D][D / 4];                    // row c: W2[c][0..D)
     float sc1[D], sh1[D];
 };
-__device__ __forceinline__ void stage_edge_w(EdgeW& s, const float* W1, const float* W2, const float* sc1, const float* sh1) {
+template <int D>
+__device__ __forceinline__ void stage_edge_w(EdgeW<D>& s, const float* W1, const float* W2, const float* sc1, const float* sh1) {
     for (int i = threadIdx.x; i < D; i += kThreads) {
         s.W1[i] = make_float4(__ldg(W1 + i * 3), __ldg(W1 + i * 3 + 1), __ldg(W1 + i * 3 + 2), 0.f);
         s.sc1[i] = __ldg(sc1 + i); s.sh1[i] = __ldg(sh1 + i);
     }
     for (int i = threadIdx.x; i < D * D / 4; i += kThreads) s.W2[i / (D / 4)][i % (D / 4)] = ldg4(W2 + 4 * i);
 }
-__device__ __forceinline__ void edge_mlp(const EdgeW& s, float rx, float ry, float rz, float slope1, float (&h1)[D], float (&pre1)[D],
-                                         float (&a1)[D], float (&h2)[D]) {
+// h1, pre1, a1 for all D channels; h2 for the thread's own channels c0 .. c0 + 7
+template <int D>
+__device__ __forceinline__ void edge_mlp(const EdgeW<D>& s, int c0, float rx, float ry, float rz, float slope1, float (&h1)[D],
+                                         float (&pre1)[D], float (&a1)[D], float (&h2)[DC]) {
 #pragma unroll
     for (int c = 0; c < D; ++c) {
         const float4 w = s.W1[c];
@@ -142,14 +142,20 @@ __device__ __forceinline__ void edge_mlp(const EdgeW& s, float rx, float ry, flo
         a1[c] = lrelu(pre1[c], slope1);
     }
 #pragma unroll
-    for (int c = 0; c < D; ++c) {
-        const float4 w0 = s.W2[c][0], w1 = s.W2[c][1];
-        h2[c] = fmaf(w0.x, a1[0], fmaf(w0.y, a1[1], fmaf(w0.z, a1[2], fmaf(w0.w, a1[3],
-                fmaf(w1.x, a1[4], fmaf(w1.y, a1[5], fmaf(w1.z, a1[6], w1.w * a1[7])))))));
+    for (int c = 0; c < DC; ++c) {
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < D / 4; ++q) {
+            const float4 w = s.W2[c0 + c][q];
+            acc = fmaf(w.x, a1[4 * q], fmaf(w.y, a1[4 * q + 1], fmaf(w.z, a1[4 * q + 2], fmaf(w.w, a1[4 * q + 3], acc))));
+        }
+        h2[c] = acc;
     }
 }
-__device__ __forceinline__ void load_x8(const float* x, int64_t row, float (&v)[D]) {
-    const float4 a = ldg4(x + row * D), b = ldg4(x + row * D + 4);
+// the thread's 8 channels of row `row` of a [rows, D] tensor
+template <int D>
+__device__ __forceinline__ void load_x8(const float* x, int64_t row, int c0, float (&v)[DC]) {
+    const float4 a = ldg4(x + row * D + c0), b = ldg4(x + row * D + c0 + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
@@ -182,62 +188,89 @@ __device__ __forceinline__ void for_edges(const float* rel, const int64_t* idx, 
     }
 }
 
+// Every kernel: thread t of the grid ↔ (point p = t / LPP, channel block blk = t % LPP).  The LPP threads of a point are adjacent lanes
+// and run the same trip counts (rows·LPP is padded per warp by the `p < rows` clamp below: a clamped thread contributes nothing).
 struct FwdArgs {
     const float* x; const float* rel; const int64_t* idx;
     const float* W1; const float* W2; const float* sc1; const float* sh1; float slope1;
     float* P; float* Q;                     // [rows, D]
-    float* stats2;                          // [kStatSlots][2D]  Σh2 | Σh2²
-    float* asum;                            // [kStatSlots][kASum]
+    float* stats2;                          // [kStatSlots][2D]        Σh2 | Σh2²
+    float* asum;                            // [kStatSlots][D + D·D]   Σa1 | Σa1a1ᵀ (d = 8: upper triangle only, rest zero)
     int64_t rows, Ns, Nq; int K;
 };
 
-__global__ void __launch_bounds__(kThreads, 3) fwd_kernel(const FwdArgs a) {
-    __shared__ EdgeW sw;
-    __shared__ float s_red[(kThreads / 32) * (2 * D + kASum)];
+template <int D>
+__global__ void __launch_bounds__(kThreads, D == 8 ? 3 : 2) fwd_kernel(const FwdArgs a) {
+    constexpr int LPP = D / DC;
+    constexpr int NA = LPP == 1 ? DC + DC * (DC + 1) / 2 : DC + DC * D;     // Σa1 (own) | rows of Σa1a1ᵀ (own; d = 8: upper triangle)
+    __shared__ EdgeW<D> sw;
+    __shared__ float s_acc[D + D * D];
     stage_edge_w(sw, a.W1, a.W2, a.sc1, a.sh1);
     __syncthreads();
-    float st[2 * D], as[kASum];
+    float st[2 * DC], as[NA];
 #pragma unroll
-    for (int i = 0; i < 2 * D; ++i) st[i] = 0.f;
+    for (int i = 0; i < 2 * DC; ++i) st[i] = 0.f;
 #pragma unroll
-    for (int i = 0; i < kASum; ++i) as[i] = 0.f;
-    for (int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x; p < a.rows; p += (int64_t)gridDim.x * kThreads) {
+    for (int i = 0; i < NA; ++i) as[i] = 0.f;
+    const int64_t nthr = (int64_t)gridDim.x * kThreads;
+    for (int64_t tt = (int64_t)blockIdx.x * kThreads + threadIdx.x; tt < a.rows * LPP; tt += nthr) {
+        const int64_t p = tt / LPP;
+        const int c0 = (int)(tt % LPP) * DC;
         const int64_t base = (p / a.Nq) * a.Ns;
-        float P[D], Q[D];
+        float P[DC], Q[DC];
 #pragma unroll
-        for (int c = 0; c < D; ++c) P[c] = Q[c] = 0.f;
+        for (int c = 0; c < DC; ++c) P[c] = Q[c] = 0.f;
         for_edges(a.rel, a.idx, p, a.K, [&](float rx, float ry, float rz, int64_t j) {
-            float xj[D], h1[D], pre1[D], a1[D], h2[D];
-            load_x8(a.x, base + j, xj);
-            edge_mlp(sw, rx, ry, rz, a.slope1, h1, pre1, a1, h2);
+            float xj[DC], h1[D], pre1[D], a1[D], h2[DC];
+            load_x8<D>(a.x, base + j, c0, xj);
+            edge_mlp<D>(sw, c0, rx, ry, rz, a.slope1, h1, pre1, a1, h2);
 #pragma unroll
-            for (int c = 0; c < D; ++c) {
+            for (int c = 0; c < DC; ++c) {
                 P[c] = fmaf(h2[c], xj[c], P[c]);
                 Q[c] += xj[c];
                 st[c] += h2[c];
-                st[D + c] = fmaf(h2[c], h2[c], st[D + c]);
-                as[c] += a1[c];
+                st[DC + c] = fmaf(h2[c], h2[c], st[DC + c]);
             }
-            int t = D;
+            if constexpr (LPP == 1) {
 #pragma unroll
-            for (int b = 0; b < D; ++b)
+                for (int c = 0; c < DC; ++c) as[c] += a1[c];
+                int t = DC;
 #pragma unroll
-                for (int c = b; c < D; ++c) { as[t] = fmaf(a1[b], a1[c], as[t]); ++t; }
+                for (int b = 0; b < DC; ++b)
+#pragma unroll
+                    for (int c = b; c < DC; ++c) { as[t] = fmaf(a1[b], a1[c], as[t]); ++t; }
+            } else {
+#pragma unroll
+                for (int b = 0; b < DC; ++b) {
+                    const float ab = c0 == 0 ? a1[b] : a1[DC + b];           // LPP == 2: own rows are a1[c0 + b]
+                    as[b] += ab;
+#pragma unroll
+                    for (int c = 0; c < D; ++c) as[DC + b * D + c] = fmaf(ab, a1[c], as[DC + b * D + c]);
+                }
+            }
         });
-        float4* Pp = reinterpret_cast<float4*>(a.P + p * D);
-        float4* Qp = reinterpret_cast<float4*>(a.Q + p * D);
+        float4* Pp = reinterpret_cast<float4*>(a.P + p * D + c0);
+        float4* Qp = reinterpret_cast<float4*>(a.Q + p * D + c0);
         Pp[0] = make_float4(P[0], P[1], P[2], P[3]); Pp[1] = make_float4(P[4], P[5], P[6], P[7]);
         Qp[0] = make_float4(Q[0], Q[1], Q[2], Q[3]); Qp[1] = make_float4(Q[4], Q[5], Q[6], Q[7]);
     }
-    block_sums_to_slot<2 * D>(st, a.stats2, s_red);
-    block_sums_to_slot<kASum>(as, a.asum, s_red);
+    block_sums_to_slot<LPP>(st, a.stats2, 2 * D, s_acc, [](int i, int blk) { return (i < DC ? 0 : D - DC) + blk * DC + i; });
+    block_sums_to_slot<LPP>(as, a.asum, D + D * D, s_acc, [](int i, int blk) {
+        if (i < DC) return blk * DC + i;
+        if (LPP == 1) {                                            // i-th upper-triangle element ↔ (b, c)
+            int t = i - DC, b = 0;
+            while (t >= DC - b) { t -= DC - b; ++b; }
+            return D + b * D + (b + t);
+        }
+        return D + (blk * DC + (i - DC) / D) * D + (i - DC) % D;
+    });
 }
 
 // out = sc2 ⊙ P + sh2 ⊙ Q
 __global__ void __launch_bounds__(256) out_kernel(const float* __restrict__ P, const float* __restrict__ Q, const float* __restrict__ sc2,
-                                                  const float* __restrict__ sh2, float* __restrict__ out, int64_t total4) {
+                                                  const float* __restrict__ sh2, float* __restrict__ out, int64_t total4, int D4) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % (D / 4)) * 4;
+        const int c = (int)(i % D4) * 4;
         const float4 p = ldg4(P + 4 * i), q = ldg4(Q + 4 * i), sc = ldg4(sc2 + c), sh = ldg4(sh2 + c);
         reinterpret_cast<float4*>(out)[i] = make_float4(fmaf(sc.x, p.x, sh.x * q.x), fmaf(sc.y, p.y, sh.y * q.y), fmaf(sc.z, p.z, sh.z * q.z),
                                                         fmaf(sc.w, p.w, sh.w * q.w));
@@ -255,48 +288,53 @@ struct Bwd1Args {
     int64_t rows, Ns, Nq; int K;
 };
 
-__global__ void __launch_bounds__(kThreads, 3) bwd1_kernel(const Bwd1Args a) {
-    __shared__ EdgeW sw;
+template <int D>
+__global__ void __launch_bounds__(kThreads, D == 8 ? 3 : 2) bwd1_kernel(const Bwd1Args a) {
+    constexpr int LPP = D / DC;
+    __shared__ EdgeW<D> sw;
     __shared__ float s_c[4][D];             // sc2, sh2, mu2, is2
-    __shared__ float s_red[(kThreads / 32) * D * D];
+    __shared__ float s_acc[D * D];
     stage_edge_w(sw, a.W1, a.W2, a.sc1, a.sh1);
     if (threadIdx.x < D) {
         s_c[0][threadIdx.x] = __ldg(a.sc2 + threadIdx.x); s_c[1][threadIdx.x] = __ldg(a.sh2 + threadIdx.x);
         s_c[2][threadIdx.x] = __ldg(a.mu2 + threadIdx.x); s_c[3][threadIdx.x] = __ldg(a.is2 + threadIdx.x);
     }
     __syncthreads();
-    float sm[2 * D], md[D * D];
+    float sm[2 * DC], md[DC * D];
 #pragma unroll
-    for (int i = 0; i < 2 * D; ++i) sm[i] = 0.f;
+    for (int i = 0; i < 2 * DC; ++i) sm[i] = 0.f;
 #pragma unroll
-    for (int i = 0; i < D * D; ++i) md[i] = 0.f;
-    for (int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x; p < a.rows; p += (int64_t)gridDim.x * kThreads) {
+    for (int i = 0; i < DC * D; ++i) md[i] = 0.f;
+    const int64_t nthr = (int64_t)gridDim.x * kThreads;
+    for (int64_t tt = (int64_t)blockIdx.x * kThreads + threadIdx.x; tt < a.rows * LPP; tt += nthr) {
+        const int64_t p = tt / LPP;
+        const int c0 = (int)(tt % LPP) * DC;
         const int64_t base = (p / a.Nq) * a.Ns;
-        float g[D];
-        load_x8(a.g, p, g);
+        float g[DC];
+        load_x8<D>(a.g, p, c0, g);
         for_edges(a.rel, a.idx, p, a.K, [&](float rx, float ry, float rz, int64_t j) {
             const int64_t row = base + j;
-            float xj[D], h1[D], pre1[D], a1[D], h2[D], w[D];
-            load_x8(a.x, row, xj);
-            edge_mlp(sw, rx, ry, rz, a.slope1, h1, pre1, a1, h2);
+            float xj[DC], h1[D], pre1[D], a1[D], h2[DC], w[DC];
+            load_x8<D>(a.x, row, c0, xj);
+            edge_mlp<D>(sw, c0, rx, ry, rz, a.slope1, h1, pre1, a1, h2);
 #pragma unroll
-            for (int c = 0; c < D; ++c) {
+            for (int c = 0; c < DC; ++c) {
                 const float dw = g[c] * xj[c];
-                const float hh = (h2[c] - s_c[2][c]) * s_c[3][c];
+                const float hh = (h2[c] - s_c[2][c0 + c]) * s_c[3][c0 + c];
                 sm[c] += dw;
-                sm[D + c] = fmaf(dw, hh, sm[D + c]);
-                w[c] = fmaf(h2[c], s_c[0][c], s_c[1][c]) * g[c];
+                sm[DC + c] = fmaf(dw, hh, sm[DC + c]);
+                w[c] = fmaf(h2[c], s_c[0][c0 + c], s_c[1][c0 + c]) * g[c];
 #pragma unroll
                 for (int b = 0; b < D; ++b) md[c * D + b] = fmaf(dw, a1[b], md[c * D + b]);
             }
             if (a.dx) {
-                red_add_v4(a.dx + row * D, w[0], w[1], w[2], w[3]);
-                red_add_v4(a.dx + row * D + 4, w[4], w[5], w[6], w[7]);
+                red_add_v4(a.dx + row * D + c0, w[0], w[1], w[2], w[3]);
+                red_add_v4(a.dx + row * D + c0 + 4, w[4], w[5], w[6], w[7]);
             }
         });
     }
-    block_sums_to_slot<2 * D>(sm, a.sums2, s_red);
-    block_sums_to_slot<D * D>(md, a.mdw, s_red);
+    block_sums_to_slot<LPP>(sm, a.sums2, 2 * D, s_acc, [](int i, int blk) { return (i < DC ? 0 : D - DC) + blk * DC + i; });
+    block_sums_to_slot<LPP>(md, a.mdw, D * D, s_acc, [](int i, int blk) { return (blk * DC + i / D) * D + i % D; });
 }
 
 // ---------------------------------------------------------------------------------------------------- backward, pass 2
@@ -310,11 +348,13 @@ struct Bwd2Args {
     int64_t rows, Ns, Nq; int K;
 };
 
-__global__ void __launch_bounds__(kThreads, 3) bwd2_kernel(const Bwd2Args a) {
-    __shared__ EdgeW sw;
-    __shared__ float4 s_w2t[D][D / 4];      // column b of W2: W2[0..7][b]
+template <int D>
+__global__ void __launch_bounds__(kThreads, D == 8 ? 3 : 2) bwd2_kernel(const Bwd2Args a) {
+    constexpr int LPP = D / DC;
+    __shared__ EdgeW<D> sw;
+    __shared__ float4 s_w2t[D][D / 4];      // column b of W2: W2[0..D)[b]
     __shared__ float s_c[5][D];             // A = sc2, Bc, Cc (dh2 = A·dw + Bc + Cc·h2), mu1, is1
-    __shared__ float s_red[(kThreads / 32) * 3 * D];
+    __shared__ float s_acc[3 * D];
     stage_edge_w(sw, a.W1, a.W2, a.sc1, a.sh1);
     for (int i = threadIdx.x; i < D * D / 4; i += kThreads) {
         const int b = i / (D / 4), q = i % (D / 4);
@@ -328,36 +368,64 @@ __global__ void __launch_bounds__(kThreads, 3) bwd2_kernel(const Bwd2Args a) {
         s_c[3][c] = __ldg(a.mu1 + c); s_c[4][c] = __ldg(a.is1 + c);
     }
     __syncthreads();
-    float sm[2 * D], s1[3 * D];
+    float sm[2 * DC], s1[3 * DC];
 #pragma unroll
-    for (int i = 0; i < 2 * D; ++i) sm[i] = 0.f;
+    for (int i = 0; i < 2 * DC; ++i) sm[i] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 3 * D; ++i) s1[i] = 0.f;
-    for (int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x; p < a.rows; p += (int64_t)gridDim.x * kThreads) {
+    for (int i = 0; i < 3 * DC; ++i) s1[i] = 0.f;
+    const int64_t nthr = (int64_t)gridDim.x * kThreads;
+    const int64_t total = a.rows * LPP;
+    // all lanes of a warp run the same number of trips (the dh2 exchange below is a warp shuffle): clamp instead of exiting
+    const int64_t trips = (total + nthr - 1) / nthr;
+    for (int64_t it = 0; it < trips; ++it) {
+        const int64_t t0 = (int64_t)blockIdx.x * kThreads + threadIdx.x + it * nthr;
+        const bool live = t0 < total;
+        const int64_t tt = live ? t0 : total - LPP + (t0 % LPP);          // a clamped thread keeps its channel block and adds nothing
+        const int64_t p = tt / LPP;
+        const int c0 = (int)(tt % LPP) * DC;
         const int64_t base = (p / a.Nq) * a.Ns;
-        float g[D];
-        load_x8(a.g, p, g);
+        float g[DC];
+        load_x8<D>(a.g, p, c0, g);
         for_edges(a.rel, a.idx, p, a.K, [&](float rx, float ry, float rz, int64_t j) {
-            float xj[D], h1[D], pre1[D], a1[D], h2[D], dh2[D];
-            load_x8(a.x, base + j, xj);
-            edge_mlp(sw, rx, ry, rz, a.slope1, h1, pre1, a1, h2);
+            float xj[DC], h1[D], pre1[D], a1[D], h2[DC], dh2[D];
+            load_x8<D>(a.x, base + j, c0, xj);
+            edge_mlp<D>(sw, c0, rx, ry, rz, a.slope1, h1, pre1, a1, h2);
+            float own[DC];
 #pragma unroll
-            for (int c = 0; c < D; ++c) dh2[c] = fmaf(s_c[0][c], g[c] * xj[c], fmaf(s_c[2][c], h2[c], s_c[1][c]));
+            for (int c = 0; c < DC; ++c) own[c] = fmaf(s_c[0][c0 + c], g[c] * xj[c], fmaf(s_c[2][c0 + c], h2[c], s_c[1][c0 + c]));
+            if constexpr (LPP == 1) {
 #pragma unroll
-            for (int b = 0; b < D; ++b) {
-                const float4 w0 = s_w2t[b][0], w1 = s_w2t[b][1];
-                const float da = fmaf(w0.x, dh2[0], fmaf(w0.y, dh2[1], fmaf(w0.z, dh2[2], fmaf(w0.w, dh2[3],
-                                 fmaf(w1.x, dh2[4], fmaf(w1.y, dh2[5], fmaf(w1.z, dh2[6], w1.w * dh2[7])))))));
-                const float dv = pre1[b] > 0.f ? da : da * a.slope1;
-                const float hh = (h1[b] - s_c[3][b]) * s_c[4][b];
+                for (int c = 0; c < DC; ++c) dh2[c] = own[c];
+            } else {                                                     // the partner lane owns the other 8 channels of dh2
+#pragma unroll
+                for (int c = 0; c < DC; ++c) {
+                    const float other = __shfl_xor_sync(0xffffffffu, own[c], 1);
+                    dh2[c] = c0 == 0 ? own[c] : other;
+                    dh2[DC + c] = c0 == 0 ? other : own[c];
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < DC; ++b) {
+                const int bb = c0 + b;
+                float da = 0.f;
+#pragma unroll
+                for (int q = 0; q < D / 4; ++q) {
+                    const float4 w = s_w2t[bb][q];
+                    da = fmaf(w.x, dh2[4 * q], fmaf(w.y, dh2[4 * q + 1], fmaf(w.z, dh2[4 * q + 2], fmaf(w.w, dh2[4 * q + 3], da))));
+                }
+                const float pre = LPP == 1 ? pre1[b] : (c0 == 0 ? pre1[b] : pre1[DC + b]);
+                const float hb = LPP == 1 ? h1[b] : (c0 == 0 ? h1[b] : h1[DC + b]);
+                float dv = pre > 0.f ? da : da * a.slope1;
+                if (!live) dv = 0.f;
+                const float hh = (hb - s_c[3][bb]) * s_c[4][bb];
                 sm[b] += dv;
-                sm[D + b] = fmaf(dv, hh, sm[D + b]);
+                sm[DC + b] = fmaf(dv, hh, sm[DC + b]);
                 s1[3 * b] = fmaf(dv, rx, s1[3 * b]); s1[3 * b + 1] = fmaf(dv, ry, s1[3 * b + 1]); s1[3 * b + 2] = fmaf(dv, rz, s1[3 * b + 2]);
             }
         });
     }
-    block_sums_to_slot<2 * D>(sm, a.sums1, s_red);
-    block_sums_to_slot<3 * D>(s1, a.s1, s_red);
+    block_sums_to_slot<LPP>(sm, a.sums1, 2 * D, s_acc, [](int i, int blk) { return (i < DC ? 0 : D - DC) + blk * DC + i; });
+    block_sums_to_slot<LPP>(s1, a.s1, 3 * D, s_acc, [](int i, int blk) { return blk * 3 * DC + i; });
 }
 
 // ---------------------------------------------------------------------------------------------------- parameter gradients from the sums
@@ -367,33 +435,43 @@ struct ParamArgs {
     const float* sc1; const float* mu1; const float* is1; const float* k1a; const float* k2a;    // BatchNorm 1 (after its backward finalize)
     const float* sc2; const float* mu2; const float* is2; const float* k1b; const float* k2b;    // BatchNorm 2
     float* dW1; float* dW2;                 // [D,3], [D,D]   +=
+    int D;
 };
 
 __global__ void param_grads_kernel(const ParamArgs a) {
-    __shared__ double m[kMom], as[kASum], md[D * D], s1[3 * D];
-    const int tid = threadIdx.x;
+    extern __shared__ double sh_d[];        // mom [9] | asum [D + D·D] | mdw [D·D] | s1 [3D]
+    const int D = a.D, tid = threadIdx.x, NA = D + D * D;
+    double* m = sh_d;
+    double* as = m + kMom;
+    double* md = as + NA;
+    double* s1 = md + D * D;
     for (int i = tid; i < kMom; i += blockDim.x) m[i] = fold_slots(a.mom, kMom, i);
-    for (int i = tid; i < kASum; i += blockDim.x) as[i] = fold_slots(a.asum, kASum, i);
+    for (int i = tid; i < NA; i += blockDim.x) as[i] = fold_slots(a.asum, NA, i);
     for (int i = tid; i < D * D; i += blockDim.x) md[i] = fold_slots(a.mdw, D * D, i);
     for (int i = tid; i < 3 * D; i += blockDim.x) s1[i] = fold_slots(a.s1, 3 * D, i);
     __syncthreads();
-    if (tid < D * D) {                      // dW2[c][b]
-        const int c = tid / D, b = tid % D;
+    const bool upper = D == DC;             // d = 8 stores only the upper triangle of Σa1a1ᵀ
+    for (int i = tid; i < D * D; i += blockDim.x) {            // dW2[c][b]
+        const int c = i / D, b = i % D;
         double wsaa = 0.0;
-        for (int q = 0; q < D; ++q) wsaa += (double)a.W2[c * D + q] * as[D + (q <= b ? tri(q, b) : tri(b, q))];
+        for (int q = 0; q < D; ++q) wsaa += (double)a.W2[c * D + q] * as[D + ((upper && q > b) ? b * D + q : q * D + b)];
         const double sc = a.sc2[c], mu = a.mu2[c], is = a.is2[c], k1 = a.k1b[c], k2 = a.k2b[c];
-        a.dW2[tid] += (float)(sc * (md[tid] - k1 * as[b] - k2 * is * (wsaa - mu * as[b])));
+        a.dW2[i] += (float)(sc * (md[i] - k1 * as[b] - k2 * is * (wsaa - mu * as[b])));
     }
-    if (tid < 3 * D) {                      // dW1[c][x]
-        const int c = tid / 3, x = tid % 3;
+    for (int i = tid; i < 3 * D; i += blockDim.x) {            // dW1[c][x]
+        const int c = i / 3, x = i % 3;
         double wsrr = 0.0;
         for (int q = 0; q < 3; ++q) wsrr += (double)a.W1[c * 3 + q] * sym3(m + 3, q, x);
         const double sc = a.sc1[c], mu = a.mu1[c], is = a.is1[c], k1 = a.k1a[c], k2 = a.k2a[c];
-        a.dW1[tid] += (float)(sc * (s1[tid] - k1 * m[x] - k2 * is * (wsrr - mu * m[x])));
+        a.dW1[i] += (float)(sc * (s1[i] - k1 * m[x] - k2 * is * (wsrr - mu * m[x])));
     }
 }
 
-inline unsigned point_grid(int64_t rows) { return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(rows, (int64_t)kThreads), (int64_t)kNumSMs * 3)); }
+template <int D>
+inline unsigned point_grid(int64_t rows) {
+    return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(rows * (D / DC), (int64_t)kThreads), (int64_t)kNumSMs * (D == 8 ? 3 : 2)));
+}
+inline bool width_ok(int D) { return D == 8 || D == 16; }
 
 }  // namespace pcf
 }  // namespace crf
@@ -402,10 +480,12 @@ using namespace crf;
 
 extern "C" {
 
-int crfconv_pcf_width(void) { return pcf::D; }
-// floats of the zero-initialised scratch of one forward (moments | BN1 statistics | BN2 statistics | activation sums) and one backward
-int crfconv_pcf_fwd_scratch_floats(void) { return kStatSlots * (pcf::kMom + 2 * pcf::D + 2 * pcf::D + pcf::kASum); }
-int crfconv_pcf_bwd_scratch_floats(void) { return kStatSlots * (2 * pcf::D + pcf::D * pcf::D + 2 * pcf::D + 3 * pcf::D); }
+// 1 when the hidden width d is covered (8, 16)
+int crfconv_pcf_supported(int D) { return pcf::width_ok(D) ? 1 : 0; }
+// floats of the zero-initialised scratch: forward = BN1 statistics | BN2 statistics | activation sums (the moments are separate: 64·9);
+// backward = Σdw sums | Σ dw a1ᵀ | Σdv1 sums | Σ dv1 rᵀ
+int crfconv_pcf_fwd_scratch_floats(int D) { return kStatSlots * (2 * D + 2 * D + D + D * D); }
+int crfconv_pcf_bwd_scratch_floats(int D) { return kStatSlots * (2 * D + D * D + 2 * D + 3 * D); }
 
 // rel[e] = centre − support[idx[e]] and the moments Σr, Σrrᵀ (mom: [CRFCONV_STAT_SLOTS][9] zeroed floats)
 int crfconv_pcf_relpos_moments(const float* support, const float* centres, const int64_t* idx, float* rel, float* mom, int64_t B, int64_t Ns,
@@ -418,63 +498,71 @@ int crfconv_pcf_relpos_moments(const float* support, const float* centres, const
     return CRF_OK;
 }
 
-// BN1 statistics of h1 = W1·r from the moments → stats1 [CRFCONV_STAT_SLOTS][16] (slot 0; zeroed by the caller)
-int crfconv_pcf_stats1(const float* mom, const float* W1, float* stats1, void* stream) {
-    if (!mom || !W1 || !stats1) return CRF_ERR_INVALID_ARG;
-    pcf::stats1_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(mom, W1, stats1);
+// BN1 statistics of h1 = W1·r from the moments → stats1 [CRFCONV_STAT_SLOTS][2D] (slot 0; zeroed by the caller)
+int crfconv_pcf_stats1(const float* mom, const float* W1, float* stats1, int D, void* stream) {
+    if (!mom || !W1 || !stats1 || !pcf::width_ok(D)) return CRF_ERR_INVALID_ARG;
+    pcf::stats1_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(mom, W1, stats1, D);
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }
 
 int crfconv_pcf_fwd(const float* x, const float* rel, const int64_t* idx, const float* W1, const float* W2, const float* sc1, const float* sh1,
-                    float slope1, float* P, float* Q, float* stats2, float* asum, int64_t B, int64_t Ns, int64_t Nq, int K, void* stream) {
+                    float slope1, float* P, float* Q, float* stats2, float* asum, int64_t B, int64_t Ns, int64_t Nq, int K, int D, void* stream) {
     if (B <= 0 || Ns <= 0 || Nq <= 0 || K <= 0 || !x || !rel || !idx || !W1 || !W2 || !sc1 || !sh1 || !P || !Q || !stats2 || !asum)
         return CRF_ERR_INVALID_ARG;
+    if (!pcf::width_ok(D)) return CRF_ERR_UNSUPPORTED;
     pcf::FwdArgs a{x, rel, idx, W1, W2, sc1, sh1, slope1, P, Q, stats2, asum, B * Nq, Ns, Nq, K};
-    pcf::fwd_kernel<<<pcf::point_grid(a.rows), pcf::kThreads, 0, (cudaStream_t)stream>>>(a);
+    if (D == 8) pcf::fwd_kernel<8><<<pcf::point_grid<8>(a.rows), pcf::kThreads, 0, (cudaStream_t)stream>>>(a);
+    else pcf::fwd_kernel<16><<<pcf::point_grid<16>(a.rows), pcf::kThreads, 0, (cudaStream_t)stream>>>(a);
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }
 
-int crfconv_pcf_out(const float* P, const float* Q, const float* sc2, const float* sh2, float* out, int64_t rows, void* stream) {
-    if (rows <= 0 || !P || !Q || !sc2 || !sh2 || !out) return CRF_ERR_INVALID_ARG;
-    const int64_t total4 = rows * (pcf::D / 4);
-    pcf::out_kernel<<<(unsigned)std::min<int64_t>(ceil_div(total4, (int64_t)256), (int64_t)kNumSMs * 8), 256, 0, (cudaStream_t)stream>>>(P, Q, sc2, sh2, out, total4);
+int crfconv_pcf_out(const float* P, const float* Q, const float* sc2, const float* sh2, float* out, int64_t rows, int D, void* stream) {
+    if (rows <= 0 || !P || !Q || !sc2 || !sh2 || !out || !pcf::width_ok(D)) return CRF_ERR_INVALID_ARG;
+    const int64_t total4 = rows * (D / 4);
+    pcf::out_kernel<<<(unsigned)std::min<int64_t>(ceil_div(total4, (int64_t)256), (int64_t)kNumSMs * 8), 256, 0, (cudaStream_t)stream>>>(P, Q, sc2, sh2, out, total4, D / 4);
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }
 
 int crfconv_pcf_bwd1(const float* x, const float* rel, const int64_t* idx, const float* g, const float* W1, const float* W2, const float* sc1,
                      const float* sh1, float slope1, const float* sc2, const float* sh2, const float* mu2, const float* is2, float* dx,
-                     float* sums2, float* mdw, int64_t B, int64_t Ns, int64_t Nq, int K, void* stream) {
+                     float* sums2, float* mdw, int64_t B, int64_t Ns, int64_t Nq, int K, int D, void* stream) {
     if (B <= 0 || Ns <= 0 || Nq <= 0 || K <= 0 || !x || !rel || !idx || !g || !W1 || !W2 || !sc1 || !sh1 || !sc2 || !sh2 || !mu2 || !is2 || !sums2 || !mdw)
         return CRF_ERR_INVALID_ARG;
+    if (!pcf::width_ok(D)) return CRF_ERR_UNSUPPORTED;
     pcf::Bwd1Args a{x, rel, idx, g, W1, W2, sc1, sh1, slope1, sc2, sh2, mu2, is2, dx, sums2, mdw, B * Nq, Ns, Nq, K};
-    pcf::bwd1_kernel<<<pcf::point_grid(a.rows), pcf::kThreads, 0, (cudaStream_t)stream>>>(a);
+    if (D == 8) pcf::bwd1_kernel<8><<<pcf::point_grid<8>(a.rows), pcf::kThreads, 0, (cudaStream_t)stream>>>(a);
+    else pcf::bwd1_kernel<16><<<pcf::point_grid<16>(a.rows), pcf::kThreads, 0, (cudaStream_t)stream>>>(a);
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }
 
 int crfconv_pcf_bwd2(const float* x, const float* rel, const int64_t* idx, const float* g, const float* W1, const float* W2, const float* sc1,
                      const float* sh1, float slope1, const float* mu1, const float* is1, const float* sc2, const float* mu2, const float* is2,
-                     const float* k1b, const float* k2b, float* sums1, float* s1, int64_t B, int64_t Ns, int64_t Nq, int K, void* stream) {
+                     const float* k1b, const float* k2b, float* sums1, float* s1, int64_t B, int64_t Ns, int64_t Nq, int K, int D, void* stream) {
     if (B <= 0 || Ns <= 0 || Nq <= 0 || K <= 0 || !x || !rel || !idx || !g || !W1 || !W2 || !sc1 || !sh1 || !mu1 || !is1 || !sc2 || !mu2 || !is2 || !k1b ||
         !k2b || !sums1 || !s1)
         return CRF_ERR_INVALID_ARG;
+    if (!pcf::width_ok(D)) return CRF_ERR_UNSUPPORTED;
     pcf::Bwd2Args a{x, rel, idx, g, W1, W2, sc1, sh1, slope1, mu1, is1, sc2, mu2, is2, k1b, k2b, sums1, s1, B * Nq, Ns, Nq, K};
-    pcf::bwd2_kernel<<<pcf::point_grid(a.rows), pcf::kThreads, 0, (cudaStream_t)stream>>>(a);
+    if (D == 8) pcf::bwd2_kernel<8><<<pcf::point_grid<8>(a.rows), pcf::kThreads, 0, (cudaStream_t)stream>>>(a);
+    else pcf::bwd2_kernel<16><<<pcf::point_grid<16>(a.rows), pcf::kThreads, 0, (cudaStream_t)stream>>>(a);
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }
 
-// dW1 [8,3] and dW2 [8,8] (+=) from the sums of the forward and the two backward passes and the finalized BatchNorm-backward constants
+// dW1 [D,3] and dW2 [D,D] (+=) from the sums of the forward and the two backward passes and the finalized BatchNorm-backward constants
 int crfconv_pcf_param_grads(const float* mom, const float* asum, const float* mdw, const float* s1, const float* W1, const float* W2,
                             const float* sc1, const float* mu1, const float* is1, const float* k1a, const float* k2a, const float* sc2,
-                            const float* mu2, const float* is2, const float* k1b, const float* k2b, float* dW1, float* dW2, void* stream) {
+                            const float* mu2, const float* is2, const float* k1b, const float* k2b, float* dW1, float* dW2, int D, void* stream) {
     if (!mom || !asum || !mdw || !s1 || !W1 || !W2 || !sc1 || !mu1 || !is1 || !k1a || !k2a || !sc2 || !mu2 || !is2 || !k1b || !k2b || !dW1 || !dW2)
         return CRF_ERR_INVALID_ARG;
-    pcf::ParamArgs a{mom, asum, mdw, s1, W1, W2, sc1, mu1, is1, k1a, k2a, sc2, mu2, is2, k1b, k2b, dW1, dW2};
-    pcf::param_grads_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(a);
+    if (!pcf::width_ok(D)) return CRF_ERR_UNSUPPORTED;
+    pcf::ParamArgs a{mom, asum, mdw, s1, W1, W2, sc1, mu1, is1, k1a, k2a, sc2, mu2, is2, k1b, k2b, dW1, dW2, D};
+    const size_t smem = (size_t)(pcf::kMom + D + D * D + D * D + 3 * D) * sizeof(double);
+    pcf::param_grads_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(a);
     CRF_LAUNCH_CHECK();
     return CRF_OK;
 }

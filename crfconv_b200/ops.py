@@ -372,13 +372,13 @@ def pointconv_aggregate_bwd(x, H2, bn: BN, idx, g, dx, B, Ns, Nq, K):
 
 
 # ---- PointConv without per-edge tensors (csrc/pointconv_fused.cu, hidden width 8) ------------------------------------------------
-def pcf_width():
-    return _lib.lib().crfconv_pcf_width()
+def pcf_supported(d):
+    return bool(_lib.lib().crfconv_pcf_supported(int(d)))
 
 
-def pcf_scratch_floats():
+def pcf_scratch_floats(d):
     L = _lib.lib()
-    return L.crfconv_pcf_fwd_scratch_floats(), L.crfconv_pcf_bwd_scratch_floats()
+    return L.crfconv_pcf_fwd_scratch_floats(int(d)), L.crfconv_pcf_bwd_scratch_floats(int(d))
 
 
 def pcf_relpos_moments(support, centres, idx, mom):
@@ -395,7 +395,7 @@ def pcf_relpos_moments(support, centres, idx, mom):
 def pcf_stats1(mom, W1, stats1):
     L = _lib.lib()
     COUNTERS["launches"] += 1
-    _lib.check(L.crfconv_pcf_stats1(_p(mom), _p(W1), _p(stats1), _lib.stream_ptr()), "pcf_stats1")
+    _lib.check(L.crfconv_pcf_stats1(_p(mom), _p(W1), _p(stats1), int(W1.shape[0]), _lib.stream_ptr()), "pcf_stats1")
 
 
 def pcf_fwd(x, rel, idx, W1, W2, bn1: BN, slope1, stats2, asum, B, Ns, Nq, K):
@@ -405,7 +405,7 @@ def pcf_fwd(x, rel, idx, W1, W2, bn1: BN, slope1, stats2, asum, B, Ns, Nq, K):
     Q = torch.empty((B * Nq, d), dtype=torch.float32, device=x.device)
     with _call("pcf_fwd", 1, _nbytes(x, rel, idx, P, Q)):
         rc = L.crfconv_pcf_fwd(_p(x), _p(rel), _p(idx), _p(W1), _p(W2), _p(bn1.scale), _p(bn1.shift), float(slope1), _p(P), _p(Q), _p(stats2),
-                               _p(asum), B, Ns, Nq, K, _lib.stream_ptr())
+                               _p(asum), B, Ns, Nq, K, d, _lib.stream_ptr())
     _lib.check(rc, "pcf_fwd")
     return P, Q
 
@@ -414,7 +414,7 @@ def pcf_out(P, Q, bn2: BN):
     L = _lib.lib()
     out = torch.empty_like(P)
     with _call("pcf_out", 1, _nbytes(P, Q, out)):
-        rc = L.crfconv_pcf_out(_p(P), _p(Q), _p(bn2.scale), _p(bn2.shift), _p(out), P.shape[0], _lib.stream_ptr())
+        rc = L.crfconv_pcf_out(_p(P), _p(Q), _p(bn2.scale), _p(bn2.shift), _p(out), P.shape[0], P.shape[1], _lib.stream_ptr())
     _lib.check(rc, "pcf_out")
     return out
 
@@ -423,7 +423,7 @@ def pcf_bwd1(x, rel, idx, g, W1, W2, bn1: BN, slope1, bn2: BN, dx, sums2, mdw, B
     L = _lib.lib()
     with _call("pcf_bwd1", 1, _nbytes(x, rel, idx, g, dx, dx)):
         rc = L.crfconv_pcf_bwd1(_p(x), _p(rel), _p(idx), _p(g), _p(W1), _p(W2), _p(bn1.scale), _p(bn1.shift), float(slope1), _p(bn2.scale),
-                                _p(bn2.shift), _p(bn2.mean), _p(bn2.invstd), _p(dx), _p(sums2), _p(mdw), B, Ns, Nq, K, _lib.stream_ptr())
+                                _p(bn2.shift), _p(bn2.mean), _p(bn2.invstd), _p(dx), _p(sums2), _p(mdw), B, Ns, Nq, K, x.shape[1], _lib.stream_ptr())
     _lib.check(rc, "pcf_bwd1")
 
 
@@ -432,7 +432,7 @@ def pcf_bwd2(x, rel, idx, g, W1, W2, bn1: BN, slope1, bn2: BN, sums1, s1, B, Ns,
     with _call("pcf_bwd2", 1, _nbytes(x, rel, idx, g)):
         rc = L.crfconv_pcf_bwd2(_p(x), _p(rel), _p(idx), _p(g), _p(W1), _p(W2), _p(bn1.scale), _p(bn1.shift), float(slope1), _p(bn1.mean),
                                 _p(bn1.invstd), _p(bn2.scale), _p(bn2.mean), _p(bn2.invstd), _p(bn2.k1), _p(bn2.k2), _p(sums1), _p(s1),
-                                B, Ns, Nq, K, _lib.stream_ptr())
+                                B, Ns, Nq, K, x.shape[1], _lib.stream_ptr())
     _lib.check(rc, "pcf_bwd2")
 
 
@@ -448,7 +448,7 @@ def pcf_param_grads(mom, asum, mdw, s1, W1, W2, bn1: BN, bn2: BN, dW1, dW2):
     COUNTERS["launches"] += 1
     rc = L.crfconv_pcf_param_grads(_p(mom), _p(asum), _p(mdw), _p(s1), _p(W1), _p(W2), _p(bn1.scale), _p(bn1.mean), _p(bn1.invstd), _p(bn1.k1),
                                    _p(bn1.k2), _p(bn2.scale), _p(bn2.mean), _p(bn2.invstd), _p(bn2.k1), _p(bn2.k2), _p(dW1), _p(dW2),
-                                   _lib.stream_ptr())
+                                   int(W2.shape[0]), _lib.stream_ptr())
     _lib.check(rc, "pcf_param_grads")
 
 

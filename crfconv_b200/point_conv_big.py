@@ -91,7 +91,7 @@ def _relpos_moments_cached(sup, cen, nbr):
 
 
 class _PointConvFusedFunction(torch.autograd.Function):
-    """The same layer with the 3→d→d edge MLP recomputed from the relative positions in every pass (csrc/pointconv_fused.cu, d = 8):
+    """The same layer with the 3→d→d edge MLP recomputed from the relative positions in every pass (csrc/pointconv_fused.cu, d = 8 / 16):
     no [E, d] tensor is written — BN1 statistics come from the moments of r, BN2 statistics and out = sc2 ⊙ Σ h2 ⊙ x_j + sh2 ⊙ Σ x_j
     from one pass, the backward needs two passes and derives dW1 / dW2 from per-matrix sums."""
 
@@ -109,9 +109,9 @@ class _PointConvFusedFunction(torch.autograd.Function):
         nbr = idx.detach().contiguous().to(torch.int64)
         W1c, W2c = W1.detach().contiguous().float(), W2.detach().contiguous().float()
         S = ops.STAT_SLOTS
-        nf, _ = ops.pcf_scratch_floats()
+        nf, _ = ops.pcf_scratch_floats(d)
         z = ops.Flat(nf, torch.float32, dev)                    # one zero fill: BN1 statistics | BN2 statistics | activation sums
-        stats1, stats2, asum = z.take(S * 2 * d), z.take(S * 2 * d), z.take(S * (d + d * (d + 1) // 2))
+        stats1, stats2, asum = z.take(S * 2 * d), z.take(S * 2 * d), z.take(S * (d + d * d))
         rel, mom = _relpos_moments_cached(sup, cen, nbr)[:2]                               # [E, 3], Σr, Σrrᵀ
         st1, fin1 = bn_forward_state(d, dev, E, bn1, True, stats1)
         ops.pcf_stats1(mom, W1c, stats1); fin1()                                          # h1 = W1·r is linear in r
@@ -137,7 +137,7 @@ class _PointConvFusedFunction(torch.autograd.Function):
             dW1, dW2 = small.take(*W1c.shape), small.take(*W2c.shape)
             dg1, db1, dg2, db2 = (small.take(d) for _ in range(4))
         S = ops.STAT_SLOTS
-        _, nb = ops.pcf_scratch_floats()
+        _, nb = ops.pcf_scratch_floats(d)
         z = ops.Flat(nb, torch.float32, dev, scratch=True)
         sums2, mdw, sums1, s1 = z.take(S * 2 * d), z.take(S * d * d), z.take(S * 2 * d), z.take(S * 3 * d)
         dx = torch.zeros_like(x2) if ctx.needs_input_grad[0] else None
@@ -205,7 +205,7 @@ class PointConv(nn.Module):
             raise RuntimeError("PointConv: weight_nn must keep the reference's (LeakyReLU, None) activations to be fused")
         b1, b2 = m1.bn.batch_norm, m2.bn.batch_norm
         from .common import direct_grad_buffers
-        if (FUSED_EDGE_MLP and x.is_cuda and x.shape[-1] == ops.pcf_width() and x.dtype == torch.float32 and
+        if (FUSED_EDGE_MLP and x.is_cuda and ops.pcf_supported(x.shape[-1]) and x.dtype == torch.float32 and
                 (self.training or not (b1.track_running_stats or b2.track_running_stats))):
             return _PointConvFusedFunction.apply(x, support, centres, neighbor_idx, m1.lin.weight, b1.weight, b1.bias, m2.lin.weight,
                                                  b2.weight, b2.bias, b1, b2, m1.slope,

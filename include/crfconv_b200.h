@@ -279,34 +279,34 @@ int crfconv_spmm_fwd(const float* x, const int64_t* eptr, const int64_t* col, co
 int crfconv_spmm_bwd(const float* x, const int64_t* eptr, const int64_t* col, const float* w, const float* g, float* dw, float* dx, int64_t N,
                      int C, void* stream);
 
-/* ------------------------------------------------------- PointConv without per-edge tensors (hidden width 8: level 0 of PointConvResNet)
- * models/point_conv_big.py:8-58.  out_i = Σ_k BN2(W2·lrelu(BN1(W1·r_ik))) ⊙ x_j with the 3→8→8 edge MLP recomputed from r in every pass;
+/* ------------------------------------------------------- PointConv without per-edge tensors (hidden width D = 8 / 16: levels 0 and 1)
+ * models/point_conv_big.py:8-58.  out_i = Σ_k BN2(W2·lrelu(BN1(W1·r_ik))) ⊙ x_j with the 3→D→D edge MLP recomputed from r in every pass;
  * only sums cross kernels (csrc/pointconv_fused.cu).  All scratch buffers are [CRFCONV_STAT_SLOTS][n] zero-initialised floats. */
-int crfconv_pcf_width(void);
-int crfconv_pcf_fwd_scratch_floats(void);
-int crfconv_pcf_bwd_scratch_floats(void);
+int crfconv_pcf_supported(int D);
+int crfconv_pcf_fwd_scratch_floats(int D);
+int crfconv_pcf_bwd_scratch_floats(int D);
 /* rel [B·Nq·K, 3] = centre − support[idx] and mom [SLOTS][9] = Σr | Σrrᵀ (upper triangle) */
 int crfconv_pcf_relpos_moments(const float* support, const float* centres, const int64_t* idx, float* rel, float* mom, int64_t B, int64_t Ns,
                                int64_t Nq, int K, void* stream);
-/* Σh1, Σh1² of h1 = W1·r from the moments → slot 0 of stats1 [SLOTS][16] (then crfconv_bn_finalize_fwd with count = B·Nq·K) */
-int crfconv_pcf_stats1(const float* mom, const float* W1, float* stats1, void* stream);
-/* P_i = Σ_k h2 ⊙ x_j, Q_i = Σ_k x_j; stats2 [SLOTS][16] += Σh2 | Σh2²; asum [SLOTS][44] += Σa1 | Σa1a1ᵀ (upper triangle) */
+/* Σh1, Σh1² of h1 = W1·r from the moments → slot 0 of stats1 [SLOTS][2D] (then crfconv_bn_finalize_fwd with count = B·Nq·K) */
+int crfconv_pcf_stats1(const float* mom, const float* W1, float* stats1, int D, void* stream);
+/* P_i = Σ_k h2 ⊙ x_j, Q_i = Σ_k x_j; stats2 [SLOTS][2D] += Σh2 | Σh2²; asum [SLOTS][D + D·D] += Σa1 | Σa1a1ᵀ (D = 8: upper triangle) */
 int crfconv_pcf_fwd(const float* x, const float* rel, const int64_t* idx, const float* W1, const float* W2, const float* sc1, const float* sh1,
-                    float slope1, float* P, float* Q, float* stats2, float* asum, int64_t B, int64_t Ns, int64_t Nq, int K, void* stream);
+                    float slope1, float* P, float* Q, float* stats2, float* asum, int64_t B, int64_t Ns, int64_t Nq, int K, int D, void* stream);
 /* out = sc2 ⊙ P + sh2 ⊙ Q */
-int crfconv_pcf_out(const float* P, const float* Q, const float* sc2, const float* sh2, float* out, int64_t rows, void* stream);
-/* dw = g_i ⊙ x_j: sums2 [SLOTS][16] += Σdw | Σdw·ĥ2, mdw [SLOTS][64] += Σ dw a1ᵀ; dx[j] += w ⊙ g_i (dx zero-initialised, may be NULL) */
+int crfconv_pcf_out(const float* P, const float* Q, const float* sc2, const float* sh2, float* out, int64_t rows, int D, void* stream);
+/* dw = g_i ⊙ x_j: sums2 [SLOTS][2D] += Σdw | Σdw·ĥ2, mdw [SLOTS][D·D] += Σ dw a1ᵀ; dx[j] += w ⊙ g_i (dx zero-initialised, may be NULL) */
 int crfconv_pcf_bwd1(const float* x, const float* rel, const int64_t* idx, const float* g, const float* W1, const float* W2, const float* sc1,
                      const float* sh1, float slope1, const float* sc2, const float* sh2, const float* mu2, const float* is2, float* dx,
-                     float* sums2, float* mdw, int64_t B, int64_t Ns, int64_t Nq, int K, void* stream);
-/* dv1 = (W2ᵀ·BN2'(dw)) ⊙ lrelu': sums1 [SLOTS][16] += Σdv1 | Σdv1·ĥ1, s1 [SLOTS][24] += Σ dv1 rᵀ   (k1b / k2b: BN2 backward constants) */
+                     float* sums2, float* mdw, int64_t B, int64_t Ns, int64_t Nq, int K, int D, void* stream);
+/* dv1 = (W2ᵀ·BN2'(dw)) ⊙ lrelu': sums1 [SLOTS][2D] += Σdv1 | Σdv1·ĥ1, s1 [SLOTS][3D] += Σ dv1 rᵀ   (k1b / k2b: BN2 backward constants) */
 int crfconv_pcf_bwd2(const float* x, const float* rel, const int64_t* idx, const float* g, const float* W1, const float* W2, const float* sc1,
                      const float* sh1, float slope1, const float* mu1, const float* is1, const float* sc2, const float* mu2, const float* is2,
-                     const float* k1b, const float* k2b, float* sums1, float* s1, int64_t B, int64_t Ns, int64_t Nq, int K, void* stream);
-/* dW1 [8,3] += , dW2 [8,8] += from the sums and both BatchNorms' finalized backward constants */
+                     const float* k1b, const float* k2b, float* sums1, float* s1, int64_t B, int64_t Ns, int64_t Nq, int K, int D, void* stream);
+/* dW1 [D,3] += , dW2 [D,D] += from the sums and both BatchNorms' finalized backward constants */
 int crfconv_pcf_param_grads(const float* mom, const float* asum, const float* mdw, const float* s1, const float* W1, const float* W2,
                             const float* sc1, const float* mu1, const float* is1, const float* k1a, const float* k2a, const float* sc2,
-                            const float* mu2, const float* is2, const float* k1b, const float* k2b, float* dW1, float* dW2, void* stream);
+                            const float* mu2, const float* is2, const float* k1b, const float* k2b, float* dW1, float* dW2, int D, void* stream);
 
 /* ------------------------------------------------------- training criterion (trainval.py:66-70,100-104: class-weighted cross entropy)
  * sums[0] += Σ w[t]·(logsumexp(x) − x[t]), sums[1] += Σ w[t] over the rows whose target != ignore_index (two zeroed doubles); C <= 64.

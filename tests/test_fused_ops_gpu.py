@@ -386,9 +386,10 @@ def test_fused_layer_matches_generic_layer(B, N, Cu, steps):
     _check(errs, tol=1e-3)
 
 
-@pytest.mark.parametrize("B,Ns,Nq,K", [(2, 4096, 4096, 16), (3, 5000, 1250, 16), (1, 777, 777, 7), (6, 40960, 40960, 16)])
-def test_pointconv_without_edge_tensors(B, Ns, Nq, K):
-    """PointConv (hidden width 8) with the edge MLP recomputed in every pass and the weight gradients derived from sums
+@pytest.mark.parametrize("B,Ns,Nq,K,d", [(2, 4096, 4096, 16, 8), (3, 5000, 1250, 16, 8), (1, 777, 777, 7, 8), (6, 40960, 40960, 16, 8),
+                                          (2, 4096, 4096, 16, 16), (3, 5001, 1251, 16, 16), (1, 777, 777, 7, 16), (6, 40960, 10240, 16, 16)])
+def test_pointconv_without_edge_tensors(B, Ns, Nq, K, d):
+    """PointConv (hidden width 8 / 16) with the edge MLP recomputed in every pass and the weight gradients derived from sums
     (csrc/pointconv_fused.cu) against a float64 statement of models/point_conv_big.py:37-58 in torch (autograd), with the layer-by-layer
     kernels (which materialise the [E, 8] tensors) measured beside it: 1e-3 of each tensor's max for both; the fused path must not be
     further from the truth than 3x the layer-by-layer path wherever that matters (> 1e-4)."""
@@ -399,10 +400,10 @@ def test_pointconv_without_edge_tensors(B, Ns, Nq, K):
     sup = (torch.rand(B, Ns, 3, generator=g) * torch.tensor([8.0, 6.0, 3.0])).to(dev)
     cen = sup if Nq == Ns else sup[:, torch.randperm(Ns, generator=g)[:Nq]].contiguous()
     idx = knn_batch(sup, cen, K)
-    x0 = torch.randn(B, Ns, 8, generator=g).to(dev)
-    cot = torch.randn(B, Nq, 8, generator=g).to(dev)
+    x0 = torch.randn(B, Ns, d, generator=g).to(dev)
+    cot = torch.randn(B, Nq, d, generator=g).to(dev)
     torch.manual_seed(1)
-    m = pcb.PointConv(8).to(dev).train()
+    m = pcb.PointConv(d).to(dev).train()
     with torch.no_grad():
         for n, p in m.named_parameters():
             if "batch_norm.weight" in n:
@@ -420,7 +421,7 @@ def test_pointconv_without_edge_tensors(B, Ns, Nq, K):
         return (h - mu) / torch.sqrt(var + 1e-5) * gamma + beta
     a1 = torch.nn.functional.leaky_relu(bn(rel @ P["weight_nn.0.lin.weight"].t(), P["weight_nn.0.bn.batch_norm.weight"], P["weight_nn.0.bn.batch_norm.bias"]), 0.1)
     w = bn(a1 @ P["weight_nn.1.lin.weight"].t(), P["weight_nn.1.bn.batch_norm.weight"], P["weight_nn.1.bn.batch_norm.bias"])
-    ot = (w.view(B, Nq, K, 8) * xt[bi, idx]).sum(2)
+    ot = (w.view(B, Nq, K, d) * xt[bi, idx]).sum(2)
     (ot * cot.double()).sum().backward()
     truth = (ot.detach(), xt.grad, {n: p.grad for n, p in P.items()})
     res = []
