@@ -89,8 +89,13 @@ __global__ void __launch_bounds__(256) relpos_moments_kernel(const float* __rest
 }
 
 __device__ __forceinline__ double fold_slots(const float* slots, int nv, int i) {
+    // all 64 loads are issued before the first add (a rolled loop put an L2 round trip into every iteration: 17-21 us per call)
+    float v[kStatSlots];
+#pragma unroll
+    for (int p = 0; p < kStatSlots; ++p) v[p] = __ldcg(slots + (size_t)p * nv + i);
     double s = 0.0;
-    for (int p = 0; p < kStatSlots; ++p) s += (double)slots[(size_t)p * nv + i];
+#pragma unroll
+    for (int p = 0; p < kStatSlots; ++p) s += (double)v[p];
     return s;
 }
 // symmetric 3×3 from the 6-entry upper triangle
