@@ -137,7 +137,7 @@ struct StepArgs {
 };
 
 template <int F>
-__global__ void __launch_bounds__(256) step_fwd_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(256, F == 16 ? 5 : 1) step_fwd_kernel(const StepArgs a) {
     constexpr int LP = F / 4, PPW = 32 / LP;
     constexpr bool TC = F == 16;                           // hidden width of the hot path: the two F×F products on the tensor cores
     __shared__ __align__(16) float Cs[TC ? 4 : F * F];

@@ -363,8 +363,6 @@ inline int launch(const UpArgs& a, cudaStream_t st) {
 }
 
 inline bool dispatch(const UpArgs& a, cudaStream_t st, int* rc) {
-    static const bool off = [] { const char* e = std::getenv("CRFCONV_NO_UPPROJ"); return e && e[0] == '1'; }();   // experiment knob
-    if (off) return false;
     const int kp = a.K <= 8 ? 8 : (a.K <= 16 ? 16 : 32);
     const int np = a.N <= 32 ? 32 : (a.N <= 64 ? 64 : 128);
 #define CRF_UP(k, n)                      \
