@@ -82,6 +82,9 @@ def bn_forward_state(C, device, count, bn_module, training, stats=None, defer_co
     `defer_counters` (a list): collect the num_batches_tracked buffers instead of bumping each with its own kernel; the caller
     bumps them all with one torch._foreach_add_."""
     st = ops.BN(C, device, stats)
+    if training and bn_module.track_running_stats and bn_module.momentum is None:
+        # cumulative moving average: the factor 1 / num_batches_tracked lives in a device counter; reading it would synchronise every step
+        raise RuntimeError("crfconv_b200: BatchNorm momentum=None (cumulative average) is not supported; use a float momentum")
 
     def finalize():
         ops.bn_finalize_fwd(st, count, bn_module.weight, bn_module.bias, bn_module.eps,
