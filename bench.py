@@ -412,7 +412,15 @@ def run_gpu(args, rank, local_rank, world):
     # Two device-side staging buffers: the H2D copy of step i+1 runs on a copy stream while step i computes (the inputs of
     # every step still cross PCIe inside the timed region); fwd+bwd of each buffer is a captured CUDA graph when --graph.
     copy_stream = torch.cuda.Stream()
-    stage = [{k: torch.empty_like(v, device=dev) for k, v in host[0].items()} for _ in range(2)]
+    # The int64 indices of the reference format are narrowed on the host (16 bits: every index < 65,536), copied packed and widened
+    # on the device by the package's HostStager (crfconv_b200/host_io.py) — packing runs inside the timed region, every step.
+    from crfconv_b200.host_io import HostStager
+    limits = {"neighbor_idx": N_POINTS, "up_idx": N_POINTS // RATIO} if args.pack_index else None
+    stagers = [HostStager(host[0], dev, index_limits=limits, threads=args.pack_threads or max(1, min(16, (os.cpu_count() or 8) // max(world, 1))),
+                          pack=bool(args.pack_index)) for _ in range(2)]
+    stage = [st_.dev for st_ in stagers]
+    h2d_ref_format = h2d
+    h2d = stagers[0].h2d_bytes(host[0])
     for st_ in stage:
         st_["unary"].requires_grad_(True)
         st_["pairwise"].requires_grad_(True)
@@ -432,8 +440,7 @@ def run_gpu(args, rank, local_rank, world):
     e2e_graphs = []
     if args.graph:
         for j in range(2):
-            for k, v in host[j].items():
-                stage[j][k].data.copy_(v)
+            stagers[j].upload(host[j])
             torch.cuda.synchronize()
             gph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gph):
@@ -444,8 +451,7 @@ def run_gpu(args, rank, local_rank, world):
         j = i % 2
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(done[j])                     # the previous user of this staging buffer has finished
-            for k, v in host[j].items():
-                stage[j][k].data.copy_(v, non_blocking=True)
+            stagers[j].upload(host[j], copy_stream)
             ready[j].record(copy_stream)
 
     def e2e_run(n):
@@ -455,8 +461,6 @@ def run_gpu(args, rank, local_rank, world):
         upload(0)
         for i in range(n):
             j = i % 2
-            if i + 1 < n:
-                upload(i + 1)
             cur.wait_event(ready[j])
             if e2e_graphs:
                 e2e_graphs[j].replay()
@@ -465,6 +469,8 @@ def run_gpu(args, rank, local_rank, world):
             fg.all_reduce()
             loss_host.copy_(loss_dev[j], non_blocking=True)
             done[j].record(cur)
+            if i + 1 < n:
+                upload(i + 1)                                   # the host packs step i+1's indices while step i computes
             cur.synchronize()                                   # the caller reads the loss on the host every step
 
     e2e_run(3)
@@ -537,7 +543,10 @@ def run_gpu(args, rank, local_rank, world):
                        "parallelism": f"dp{world}: clouds sharded, one NCCL all-reduce (AVG) of the flat gradient" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps, "h2d_gbs_per_gpu": round(h2d / (ms_e2e / args.steps * 1e-3) / 1e9, 2),
-                    "h2d_probe_gbs_per_gpu": round(probe, 2), "numa": numa},
+                    "h2d_probe_gbs_per_gpu": round(probe, 2), "numa": numa,
+                    "h2d_bytes_reference_format": h2d_ref_format,
+                    "index_packing": ("int64 indices narrowed to 16 bits on the host (%d threads, range-checked), widened on the device; "
+                                      "inside the timed region" % stagers[0].threads) if args.pack_index else "off"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,
             "knn": {"metric": "kNN queries/s", "value": knn_qps, "unit": "queries/s", "config": f"B={B}, N=Q=40960, K=16, device-resident"},
             "cpu_baseline": cb}
@@ -671,6 +680,9 @@ def main():
     ap.add_argument("--config", default="S1", choices=["S1", "C3", "C4", "C5"])
     ap.add_argument("--clouds", type=int, default=0, help="clouds per GPU per step (default: 6 for S1/C3, 8 for C4, 2 for C5)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-pack-index", dest="pack_index", action="store_false",
+                    help="e2e arm: copy the int64 index tensors as they are instead of narrowing them on the host")
+    ap.add_argument("--pack-threads", type=int, default=0, help="host threads of the index packing (default: min(16, cores / ranks); measured 1 / 2 / 4 / 8 / 16 threads: 2.84 / 2.18 / 2.04 / 2.05 / 1.92 ms per step)")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every kernel from Python instead of replaying CUDA graphs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

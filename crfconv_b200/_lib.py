@@ -86,6 +86,8 @@ SIGNATURES = {
     "crfconv_crf_step_fwd_packed": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     "crfconv_crf_upsample_bwd": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
     "crfconv_crf_step_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _vp]),
+    "crfconv_pack_index_host": (_int, [_vp, _i64, _int, _vp, _int]),
+    "crfconv_unpack_index": (_int, [_vp, _i64, _int, _vp, _vp]),
     "crfconv_crf_step_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _i64, _i64, _int, _int, _vp]),
 }
 

@@ -65,8 +65,7 @@ def deferred_counters_end():
 # Weight gradients feed nothing downstream in the backward pass.  At the deep levels of the network (≤ 2,560 points per cloud) the input-
 # gradient and weight-gradient kernels of a layer are latency-bound launches on 30-300 CTAs each: the weight gradient runs on its own
 # stream (a parallel branch of the captured graph) and is joined before the layer's backward returns.
-import os as _os
-WGRAD_SIDE_MAX_ROWS = int(_os.environ.get("CRFCONV_WGRAD_SIDE_MAX_ROWS", "16384"))
+WGRAD_SIDE_MAX_ROWS = 16384
 _WGRAD_STREAMS = {}
 
 

@@ -238,9 +238,8 @@ class _CRFConvFunction(torch.autograd.Function):
                 None, None, *_param_grads(ctx.gbuf, [Gc, *grads]))
 
 
-import os as _os
-WGRAD_BRANCH = _os.environ.get("CRFCONV_WGRAD_BRANCH", "1") != "0"   # fusion_nn's weight gradient on its own stream / graph branch (fused path)
-PACKED = _os.environ.get("CRFCONV_PACKED", "0") != "0"               # experiment (steps = 1): mean-field operands {Hy | z} interleaved into 128-byte rows (crf.cu); measured: no gain
+WGRAD_BRANCH = True   # fusion_nn's weight gradient on its own stream / graph branch (fused path)
+PACKED = False         # measured experiment, off (module attribute, no environment switch; steps = 1): mean-field operands {Hy | z} interleaved into 128-byte rows (crf.cu); measured: no gain
 _WGRAD = {}
 
 

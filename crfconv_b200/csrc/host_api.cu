@@ -3,7 +3,10 @@
 // per-thread device arena, run the device entry points on a private stream and synchronise before returning.
 // There is NO CPU fallback: without a CUDA device these calls return CRFCONV_ERR_NO_DEVICE / a cudaError_t.
 #include <algorithm>
+#include <atomic>
 #include <cstring>
+#include <thread>
+#include <vector>
 
 #include "../../include/crfconv_b200.h"
 #include "common.cuh"
@@ -40,6 +43,35 @@ struct Arena {
 
 thread_local Arena g_arena;
 
+// narrow one contiguous span; returns the OR of all source values (range check by the caller: no branch in the loop, vectorisable)
+template <typename T>
+uint64_t pack_span(const int64_t* src, T* dst, int64_t n) {
+    uint64_t seen = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const uint64_t v = (uint64_t)src[i];
+        seen |= v;
+        dst[i] = (T)v;
+    }
+    return seen;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) unpack_index_kernel(const T* __restrict__ src, int64_t* __restrict__ dst, int64_t n) {
+    // 4 indices per thread: one 8- / 16-byte load, two 128-bit stores
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        alignas(16) T v[4];
+        if constexpr (sizeof(T) == 2) *reinterpret_cast<uint2*>(v) = __ldg(reinterpret_cast<const uint2*>(src + i));
+        else *reinterpret_cast<uint4*>(v) = __ldg(reinterpret_cast<const uint4*>(src + i));
+        longlong2 a, b;
+        a.x = (long long)v[0]; a.y = (long long)v[1]; b.x = (long long)v[2]; b.y = (long long)v[3];
+        *reinterpret_cast<longlong2*>(dst + i) = a;
+        *reinterpret_cast<longlong2*>(dst + i + 2) = b;
+    } else {
+        for (int64_t j = i; j < n; ++j) dst[j] = (int64_t)src[j];
+    }
+}
+
 }  // namespace
 
 using namespace crf;
@@ -57,6 +89,36 @@ const char* crfconv_status_string(int status) {
         case CRFCONV_ERR_NO_DEVICE: return "no CUDA device";
         default: return status > 0 ? cudaGetErrorString((cudaError_t)status) : "unknown status";
     }
+}
+
+int crfconv_pack_index_host(const int64_t* idx, int64_t n, int bits, void* out, int threads) {
+    if (n < 0 || (bits != 16 && bits != 32)) return CRF_ERR_INVALID_ARG;
+    if (n == 0) return CRF_OK;
+    if (!idx || !out) return CRF_ERR_INVALID_ARG;
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(threads, 64), n >> 16));   // >= 64 Ki indices per thread
+    std::atomic<uint64_t> seen{0};
+    auto work = [&](int t) {
+        const int64_t per = ((n + nt - 1) / nt + 15) & ~(int64_t)15, lo = std::min(n, per * t), hi = std::min(n, lo + per);
+        const uint64_t s = bits == 16 ? pack_span(idx + lo, (uint16_t*)out + lo, hi - lo) : pack_span(idx + lo, (uint32_t*)out + lo, hi - lo);
+        seen.fetch_or(s, std::memory_order_relaxed);
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+    // a negative index has bit 63 set, one that does not fit has a bit at or above `bits`: either shows up in the OR
+    return (seen.load() >> bits) ? CRF_ERR_INVALID_ARG : CRF_OK;
+}
+
+int crfconv_unpack_index(const void* packed, int64_t n, int bits, int64_t* out, void* stream) {
+    if (n < 0 || (bits != 16 && bits != 32)) return CRF_ERR_INVALID_ARG;
+    if (n == 0) return CRF_OK;
+    if (!packed || !out || (reinterpret_cast<uintptr_t>(packed) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return CRF_ERR_INVALID_ARG;
+    const unsigned grid = (unsigned)((n + 1023) / 1024);
+    if (bits == 16) unpack_index_kernel<uint16_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)packed, out, n);
+    else unpack_index_kernel<uint32_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint32_t*)packed, out, n);
+    CRF_LAUNCH_CHECK();
+    return CRF_OK;
 }
 
 int crfconv_cpp_knn_batch(const float* batch_data, size_t batch_size, size_t npts, size_t dim, const float* queries,

@@ -683,20 +683,14 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const WgradArgs a) {
     if (a.dbias && blockIdx.z == 0 && tid < 64 && co0 + tid < a.Cout) atomicAdd(a.dbias + co0 + tid, bsum);
 }
 
-inline bool force_generic() {
-    static const bool v = [] { const char* e = getenv("CRFCONV_FORCE_GENERIC"); return e && e[0] == '1'; }();
-    return v;
-}
 // The bf16x3 fast path (≈2^-17 per product) is used from this many rows on; smaller problems are launch-bound anyway and
 // take the generic 3xTF32 kernels (≈2^-21), which keeps ill-conditioned tiny batches inside the 1e-3 parity budget.
-inline int64_t fast_min_rows() {
-    static const int64_t v = [] { const char* e = getenv("CRFCONV_FAST_MIN_ROWS"); return e ? (int64_t)atoll(e) : (int64_t)8192; }();
-    return v;
-}
-static int g_fast_override = -1;   // -1: rule above; 0: never; 1: always (crfconv_set_fast_path, used by the tests)
+// Dispatch between the kernel families is by SHAPE only (no environment switches); the one override is the tests' hook below.
+constexpr int64_t kFastMinRows = 8192;
+static int g_fast_override = -1;   // -1: rule above; 0: never; 1: always (crfconv_set_fast_path: lets the tests reach every family at small sizes)
 inline bool use_fast(int64_t M) {
     if (g_fast_override >= 0) return g_fast_override == 1;
-    return !force_generic() && M >= fast_min_rows();
+    return M >= kFastMinRows;
 }
 
 template <typename F>
@@ -714,7 +708,7 @@ using namespace crf;
 
 extern "C" {
 
-// Test / experiment knob: -1 = default rule (fast bf16x3 kernels from CRFCONV_FAST_MIN_ROWS rows on), 0 = generic kernels
+// Test hook: -1 = default rule (fast bf16x3 kernels from 8,192 rows on), 0 = generic kernels
 // only, 1 = fast kernels whenever the shape allows.  Returns the previous setting.
 int crfconv_set_fast_path(int mode) {
     const int prev = lin::g_fast_override;
@@ -785,7 +779,7 @@ int crfconv_bn_bwd_reduce(const float* dY, const float* H, const float* act_ref,
     if (M == 0) return CRF_OK;
     lin::BnBwd bn{scale, shift, mean, invstd, nullptr, nullptr, act_ref, slope};
     const int rows_per_it = 256 / (C / 4);
-    static const int mult = [] { const char* e = getenv("CRFCONV_REDUCE_CTAS_PER_SM"); return e ? std::max(1, atoi(e)) : 8; }();
+    constexpr int mult = 8;                                    // CTAs per SM: measured best of 2 / 4 / 8 / 16 (profiles/README_r02.md)
     const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(M, rows_per_it * 8), (int64_t)kNumSMs * mult);
     if (act_ref) lin::bn_bwd_reduce_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(dY, H, bn, sums, M, C, cl::BwdFin{});
     else lin::bn_bwd_reduce_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(dY, H, bn, sums, M, C, cl::BwdFin{});

@@ -371,11 +371,6 @@ __global__ void __launch_bounds__(kThreads, 1) fwd3_kernel(const FwdArgs a, cons
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-inline bool disabled() {
-    static const bool v = [] { const char* e = std::getenv("CRFCONV_NO_TCGEN05"); return e && e[0] == '1'; }();
-    return v;
-}
-
 }  // namespace lin3
 
 #ifdef CRF_FWD3_TRACE
@@ -395,7 +390,7 @@ namespace lin {
 // tcgen05 forward: fp32-grade precision only (3xTF32); shapes of the hot path (Cout <= 64, <= 4 slabs of 32 input channels)
 bool try_fwd3(const FwdArgs& a, int precision, cudaStream_t st, int* rc) {
     using namespace lin3;
-    if (disabled() || precision != 0) return false;
+    if (precision != 0) return false;
     if (a.idx1 || (a.scale1 && !(a.slope1 >= 0.f && a.slope1 <= 1.f))) return false;   // gathered rows / expanding slopes: older kernels
     if (a.Cout > 64 || (a.Cout & 3) || (a.C1 & 3) || (a.C2 & 3) || a.C1 <= 0) return false;
     const int nch = (a.C1 + BK - 1) / BK + (a.C2 + BK - 1) / BK;

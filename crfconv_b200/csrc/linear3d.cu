@@ -250,14 +250,6 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad3_kernel(const DgradArgs a, 
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-inline bool disabled() {
-    static const bool v = [] {
-        const char* e = std::getenv("CRFCONV_NO_TCGEN05");
-        const char* d = std::getenv("CRFCONV_NO_DGRAD3");
-        return (e && e[0] == '1') || (d && d[0] == '1');
-    }();
-    return v;
-}
 
 }  // namespace lin3d
 
@@ -265,7 +257,7 @@ namespace lin {
 
 bool try_dgrad3(const DgradArgs& a, int precision, cudaStream_t st, int* rc) {
     using namespace lin3d;
-    if (disabled() || precision != 0) return false;
+    if (precision != 0) return false;
     const int Ktot = a.C1 + a.C2;
     if (a.Cout > 64 || (a.Cout & 3) || Ktot > 128 || Ktot < 16 || (a.C1 & 3) || (a.C2 & 3) || a.bn.act_ref) return false;
     if (!aligned16(a.dY) || (a.bn.scale && !aligned16(a.H))) return false;

@@ -263,10 +263,6 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad3_kernel(const WgradArgs a, 
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-inline bool disabled() {
-    static const bool v = [] { const char* e = std::getenv("CRFCONV_NO_TCGEN05"); return e && e[0] == '1'; }();
-    return v;
-}
 
 }  // namespace lin3w
 
@@ -274,7 +270,7 @@ namespace lin {
 
 bool try_wgrad3(const WgradArgs& a, int precision, cudaStream_t st, int* rc) {
     using namespace lin3w;
-    if (disabled() || precision != 0) return false;
+    if (precision != 0) return false;
     if (a.idx1 || a.dbias || a.bn.act_ref) return false;
     if (a.Cout > 64 || (a.Cout & 3) || (a.C1 & 3) || (a.C2 & 3) || a.C1 <= 0) return false;
     if ((a.C1 + 31) / 32 + (a.C2 + 31) / 32 > kXBlocks) return false;

@@ -351,14 +351,7 @@ namespace lin {
 // measured against the tensor-core kernels on B200 (profiles/README_r01.md) they only win for hidden×hidden layers
 // (16→16 forward 25 vs 28 µs, backward 29 vs 45 µs, GC/GM 27 vs 33 µs per call at 245,760 rows): with one thread per row the
 // per-element BN+LeakyReLU prologue and the per-channel butterfly statistics cost more issue slots than the FFMAs they feed.
-// CRFCONV_NARROW_ALL=1 routes every eligible shape here (for experiments).
-static inline bool narrow_shape(int Cout, int Ktot) {
-    static const bool none = [] { const char* e = getenv("CRFCONV_NO_NARROW"); return e && e[0] == '1'; }();
-    if (none) return false;
-    static const bool all = [] { const char* e = getenv("CRFCONV_NARROW_ALL"); return e && e[0] == '1'; }();
-    if (all) return (Cout <= 16 && Ktot <= 128) || (Ktot <= 16 && Cout <= 64);
-    return Cout <= 16 && Ktot <= 16;
-}
+static inline bool narrow_shape(int Cout, int Ktot) { return Cout <= 16 && Ktot <= 16; }
 
 bool try_narrow_fwd(const FwdArgs& a, cudaStream_t st, int* rc) {
     using namespace narrow;

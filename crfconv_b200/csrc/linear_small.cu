@@ -366,11 +366,6 @@ __global__ void __launch_bounds__(kThreads) wgrad_rows_kernel(const WgradArgs a)
         }
 }
 
-// experiment knob: CRFCONV_NO_SMALL bit mask: 1 = no forward, 2 = no input gradient, 4 = no weight gradient
-inline int disabled_mask() {
-    static const int v = [] { const char* e = std::getenv("CRFCONV_NO_SMALL"); return e ? std::atoi(e) : 0; }();
-    return v;
-}
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 // rows at which the 128-row tiling of the generic kernels still fills the machine
 inline bool few_rows(int64_t M, int ntiles_n) { return ceil_div(M, (int64_t)128) * ntiles_n < 2 * kNumSMs; }
@@ -380,7 +375,6 @@ inline bool few_rows(int64_t M, int ntiles_n) { return ceil_div(M, (int64_t)128)
 bool try_fwd_small(const FwdArgs& a, cudaStream_t st, int* rc) {
     using namespace sm;
     const int Ktot = a.C1 + a.C2;
-    if (disabled_mask() & 1) return false;
     if (a.Cout < 32 || (a.Cout & 3) || (a.C1 & 3) || (a.C2 & 3) || a.C1 <= 0 || Ktot < 32) return false;
     if (!al16(a.X1) || (a.C2 && !al16(a.X2)) || !al16(a.W) || !al16(a.Y) || (a.scale1 && (!al16(a.scale1) || !al16(a.shift1)))) return false;
     const int BN = a.Cout > 32 ? 64 : 32;
@@ -397,7 +391,6 @@ bool try_fwd_small(const FwdArgs& a, cudaStream_t st, int* rc) {
 bool try_dgrad_small(const DgradArgs& a, cudaStream_t st, int* rc) {
     using namespace sm;
     const int Ktot = a.C1 + a.C2;
-    if (disabled_mask() & 2) return false;
     if (Ktot < 32 || (a.Cout & 3) || (a.C1 & 3) || (a.C2 & 3) || a.Cout < 32 || a.Cout > 1024) return false;
     if (!al16(a.dY) || !al16(a.W) || (a.bn.scale && !al16(a.H)) || (a.bn.scale && a.bn.act_ref && !al16(a.bn.act_ref))) return false;
     if ((a.dX1 && (reinterpret_cast<uintptr_t>(a.dX1) & 7)) || (a.dX2 && (reinterpret_cast<uintptr_t>(a.dX2) & 7))) return false;
@@ -417,7 +410,6 @@ bool try_dgrad_small(const DgradArgs& a, cudaStream_t st, int* rc) {
 bool try_wgrad_rows(WgradArgs a, cudaStream_t st, int* rc) {
     using namespace sm;
     const int Ktot = a.C1 + a.C2;
-    if (disabled_mask() & 4) return false;
     if (a.dbias || (a.Cout & 3) || (a.C1 & 3) || (a.C2 & 3) || a.C1 <= 0 || a.Cout < 32 || Ktot < 32) return false;
     if (!al16(a.dY) || !al16(a.X1) || (a.C2 && !al16(a.X2)) || (a.bn.scale && !al16(a.H)) || (a.bn.scale && a.bn.act_ref && !al16(a.bn.act_ref))) return false;
     const int ty = (int)ceil_div(a.Cout, 64), tz = (int)ceil_div(Ktot, 64);

@@ -15,6 +15,20 @@ STAT_SLOTS = 64      # include/crfconv_b200.h: CRFCONV_STAT_SLOTS
 GRAD_SLOTS = 32      # CRFCONV_GRAD_SLOTS
 
 
+# Debug aid: the gather kernels trust their index tensors (a bad index is an out-of-bounds device read where the reference's
+# torch.gather raises).  With CHECK_INDICES = True every forward entry point that takes indices checks their range first
+# (one min/max reduction and a host sync per call — off by default; not usable under CUDA-graph capture).
+CHECK_INDICES = False
+
+
+def check_index(idx, limit, what):
+    if not CHECK_INDICES or idx is None or idx.numel() == 0:
+        return
+    lo, hi = int(idx.min()), int(idx.max())
+    if lo < 0 or hi >= limit:
+        raise IndexError(f"crfconv_b200 {what}: index out of range [{lo}, {hi}] for {limit} rows")
+
+
 COUNTERS = {"launches": 0}       # number of crfconv_b200 kernels launched (bench.py's gpu_launches)
 _PROFILE = None                   # when a dict: name -> list of (start_event, end_event, algorithmic_bytes)
 
@@ -287,6 +301,7 @@ def crf_compat_bwd(c, Minv, GC, GM, Gc, scratch=None):
 
 def crf_upsample_fwd(Hu, bn: BN, up_idx, B, N, Nc):
     L = _lib.lib()
+    check_index(up_idx, Nc, "crf_upsample_fwd")
     F = Hu.shape[1]
     z = torch.empty((B * N, F), dtype=torch.float32, device=Hu.device)
     with _call(f"crf_upsample_fwd[{F}]", 1, _nbytes(Hu, up_idx, z)):
@@ -321,6 +336,7 @@ def crf_upsample_bwd(Gz, G0, up_idx, Gu, B, N, Nc):
 
 def crf_step_fwd(Hy, scale_y, z, xprev, nbr, Cm, Minv, B, N, K):
     L = _lib.lib()
+    check_index(nbr, N, "crf_step_fwd")
     xout = torch.empty_like(z)
     with _call(f"crf_step_fwd[{z.shape[1]}]", 1, _nbytes(Hy, z, xprev, nbr, xout)):
         rc = L.crfconv_crf_step_fwd(_p(Hy), _p(scale_y), _p(z), _p(xprev), _p(nbr), _p(Cm), _p(Minv), _p(xout), B, N, K, z.shape[1],
@@ -342,6 +358,7 @@ def relpos(support, centres, idx):
     """support [B,Ns,3], centres [B,Nq,3], idx [B,Nq,K] → rel [B·Nq·K, 3]."""
     L = _lib.lib()
     B, Ns, _ = support.shape
+    check_index(idx, Ns, "relpos")
     Nq, K = idx.shape[1], idx.shape[2]
     rel = torch.empty((B * Nq * K, 3), dtype=torch.float32, device=support.device)
     with _call("relpos", 1, _nbytes(support, centres, idx, rel)):
@@ -352,6 +369,7 @@ def relpos(support, centres, idx):
 
 def pointconv_aggregate_fwd(x, H2, bn: BN, idx, B, Ns, Nq, K):
     L = _lib.lib()
+    check_index(idx, Ns, "pointconv_aggregate_fwd")
     C = x.shape[1]
     out = torch.empty((B * Nq, C), dtype=torch.float32, device=x.device)
     with _call(f"pointconv_aggregate_fwd[{C}]", 1, _nbytes(x, H2, idx, out)):
@@ -384,6 +402,7 @@ def pcf_scratch_floats(d):
 def pcf_relpos_moments(support, centres, idx, mom):
     L = _lib.lib()
     B, Ns, _ = support.shape
+    check_index(idx, Ns, "pcf_relpos_moments")
     Nq, K = idx.shape[1], idx.shape[2]
     rel = torch.empty((B * Nq * K, 3), dtype=torch.float32, device=support.device)
     with _call("pcf_relpos_moments", 1, _nbytes(support, centres, idx, rel)):
@@ -454,6 +473,7 @@ def pcf_param_grads(mom, asum, mdw, s1, W1, W2, bn1: BN, bn2: BN, dW1, dW2):
 
 def gather_max_fwd(x, idx, B, Ns, Nq, K):
     L = _lib.lib()
+    check_index(idx, Ns, "gather_max_fwd")
     C = x.shape[1]
     out = torch.empty((B * Nq, C), dtype=torch.float32, device=x.device)
     arg = torch.empty((B * Nq, C), dtype=torch.int32, device=x.device)

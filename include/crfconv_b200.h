@@ -316,6 +316,15 @@ int crfconv_cross_entropy_fwd(const float* logits, const int64_t* target, const 
 int crfconv_cross_entropy_bwd(const float* logits, const int64_t* target, const float* weight, int64_t M, int C, int64_t ignore_index,
                               const double* sums, const float* gout, int mean, float* dlogits, void* stream);
 
+/* ------------------------------------------------------- host staging of index tensors (the PCIe leg of an end-to-end step)
+ * The reference hands neighbour / up-sampling indices over as int64 (knn.pyx:58,100 `np.zeros(..., dtype=np.int64)`; models/
+ * continuous_crf_conv_big.py:40-44 gathers with them), i.e. 8 bytes per index whose value is < npts.  crfconv_pack_index_host narrows
+ * `n` HOST int64 indices to `bits` (16 or 32) unsigned bits with `threads` host threads (out: HOST, n·bits/8 bytes, e.g. pinned memory);
+ * CRFCONV_ERR_INVALID_ARG if any index is negative or does not fit — nothing is truncated silently.  crfconv_unpack_index widens the
+ * packed DEVICE buffer back to the int64 DEVICE tensor the kernels read.  Values are bit-exact by construction. */
+int crfconv_pack_index_host(const int64_t* idx, int64_t n, int bits, void* out, int threads);
+int crfconv_unpack_index(const void* packed, int64_t n, int bits, int64_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

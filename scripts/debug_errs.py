@@ -4,6 +4,10 @@ import torch
 from oracle import layers as ol, native as on, synthetic
 from crfconv_b200.continuous_crf_conv_big import ContinuousGaussianCRFConv
 N, steps = int(sys.argv[1]), int(sys.argv[2])
+GENERIC = len(sys.argv) > 3 and sys.argv[3] == 'generic'      # third argument 'generic': the 3xTF32 generic kernels only (crfconv_set_fast_path(0))
+if GENERIC:
+    from crfconv_b200 import _lib
+    _lib.lib().crfconv_set_fast_path(0)
 B = 2
 knn = (lambda s, q, k: on.ref_knn_batch(s, q, k, omp=True)) if on.have_ref_knn() else on.knn_batch
 inp = synthetic.crf_layer_inputs(B, N, 16, 128, 64, 4, seed=N, knn_batch_fn=knn)
@@ -21,7 +25,7 @@ o0 = mo(u0, p0, inp.up_idx, inp.neighbor_idx); (o0 * cot).sum().backward()
 o1 = mp(u1, p1, inp.up_idx.cuda(), inp.neighbor_idx.cuda()); (o1 * cot.cuda()).sum().backward()
 o2 = mo64(u2, p2, inp.up_idx, inp.neighbor_idx); (o2 * cot.double()).sum().backward()
 rel = lambda a, b: float((a.detach().cpu().double() - b.detach().double()).abs().max() / float(b.detach().abs().max()))
-print(f"N={N} T={steps} generic={os.environ.get('CRFCONV_FORCE_GENERIC','0')}   [product vs fp64 oracle | fp32 oracle vs fp64 oracle]")
+print(f"N={N} T={steps} generic={int(GENERIC)}   [product vs fp64 oracle | fp32 oracle vs fp64 oracle]")
 print(f"  out        {rel(o1, o2):.2e} | {rel(o0, o2):.2e}")
 print(f"  d_unary    {rel(u1.grad, u2.grad):.2e} | {rel(u0.grad, u2.grad):.2e}")
 print(f"  d_pair     {rel(p1.grad, p2.grad):.2e} | {rel(p0.grad, p2.grad):.2e}")

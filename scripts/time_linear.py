@@ -1,7 +1,7 @@
 """Device timing of the Linear kernels on the hot-path shapes (development aid, not the bench).
 Each shape is run on NSETS rotating input sets so that consecutive launches never find their inputs in the 126 MB L2;
 20 back-to-back launches per measurement, CUDA events, GB/s = algorithmic bytes (rows × (Cin + Cout) × 4) / time.
-CRFCONV_NO_TCGEN05=1 / CRFCONV_FORCE_GENERIC=1 select the older kernels for A/B runs (read once per process)."""
+GENERIC=1 times the generic kernels instead (crfconv_set_fast_path(0))."""
 import os
 import sys
 
@@ -9,6 +9,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 from crfconv_b200 import ops
+
+if os.environ.get("GENERIC") == "1":
+    ops._lib.lib().crfconv_set_fast_path(0)
 
 M = int(os.environ.get("M", 6 * 40960))
 NSETS = 4
