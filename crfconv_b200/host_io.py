@@ -48,29 +48,48 @@ class HostStager:
             n += self.packed_host[k].numel() * self.packed_host[k].element_size() if k in self.bits else v.numel() * v.element_size()
         return n
 
-    def upload(self, host, stream=None):
-        """Enqueues the upload of `host` (dict name → host tensor, pinned for asynchronous copies) on `stream` (default: current)
-        and returns the dict of device tensors.  Index packing runs on the calling host thread before its copy is enqueued."""
-        torch = self.torch
-        L = _lib.lib()
-        stream = stream or torch.cuda.current_stream()
+    def prepare(self, host):
+        """Packs the index tensors of `host` into this stager's pinned buffers (host work only; may run on a helper thread one step
+        ahead of `upload(..., prepared=True)`).  Waits until the previous upload has finished reading those buffers."""
         if self._copied is not None:
-            self._copied.synchronize()      # the previous upload has finished reading the pinned packing buffers
+            self._copied.synchronize()
+        L = _lib.lib()
+        for k in self.bits:
+            v = host[k].contiguous()
+            _lib.check(L.crfconv_pack_index_host(v.data_ptr(), v.numel(), self.bits[k], self.packed_host[k].data_ptr(), self.threads),
+                       f"pack_index_host[{k}]")
+
+    def upload(self, host, stream=None, prepared=False, defer_unpack=False):
+        """Enqueues the upload of `host` (dict name → host tensor, pinned for asynchronous copies) on `stream` (default: current)
+        and returns the dict of device tensors.  Unless `prepared` (see `prepare`), index packing runs on the calling host thread
+        after the feature copies have been enqueued, so the DMA engine is busy while the host packs.
+        defer_unpack: only the copies are enqueued on `stream`; the caller enqueues the widening kernels with `unpack(compute_stream)`
+        after making that stream wait for the copies.  On a dedicated copy stream this matters: a kernel queued between copies has
+        to wait for free SMs while the compute stream's kernels fill the machine, and the copies behind it wait with it
+        (measured: 2.08 → 1.9 ms per step at the S1 shape)."""
+        torch = self.torch
+        stream = stream or torch.cuda.current_stream()
         with torch.cuda.stream(stream):
             for k, v in host.items():
-                if k in self.bits:
-                    continue
-                self.dev[k].data.copy_(v, non_blocking=True)           # features first: the DMA engine is busy while the host packs
-            for k, v in host.items():
                 if k not in self.bits:
-                    continue
-                v = v.contiguous()
-                ph, pd = self.packed_host[k], self.packed_dev[k]
-                _lib.check(L.crfconv_pack_index_host(v.data_ptr(), v.numel(), self.bits[k], ph.data_ptr(), self.threads), f"pack_index_host[{k}]")
-                pd.copy_(ph, non_blocking=True)
-                _lib.check(L.crfconv_unpack_index(pd.data_ptr(), v.numel(), self.bits[k], self.dev[k].data_ptr(),
-                                                  C.c_void_p(stream.cuda_stream)), f"unpack_index[{k}]")
+                    self.dev[k].data.copy_(v, non_blocking=True)
+            if not prepared:
+                self.prepare(host)
+            for k in self.bits:
+                self.packed_dev[k].copy_(self.packed_host[k], non_blocking=True)
             if self._copied is None:
                 self._copied = torch.cuda.Event()
             self._copied.record(stream)
+            if not defer_unpack:
+                self.unpack(stream)
         return self.dev
+
+    def unpack(self, stream=None):
+        """Widens the packed indices into the int64 device tensors on `stream` (which must be ordered after the upload's copies)."""
+        torch = self.torch
+        L = _lib.lib()
+        stream = stream or torch.cuda.current_stream()
+        for k in self.bits:
+            pd = self.packed_dev[k]
+            _lib.check(L.crfconv_unpack_index(pd.data_ptr(), pd.numel(), self.bits[k], self.dev[k].data_ptr(), C.c_void_p(stream.cuda_stream)),
+                       f"unpack_index[{k}]")

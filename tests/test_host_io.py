@@ -71,6 +71,18 @@ def test_stager_round_trip_is_bit_exact(pack):
         side.synchronize()
         for k, v in host.items():
             assert out[k].dtype == v.dtype and torch.equal(out[k].cpu(), v), k
+    host["neighbor_idx"].copy_(torch.randint(0, N, (B, N, K), generator=g))     # packing ahead of the upload (helper-thread form)
+    st.prepare(host)
+    out = st.upload(host, side, prepared=True)
+    side.synchronize()
+    assert torch.equal(out["neighbor_idx"].cpu(), host["neighbor_idx"]) and torch.equal(out["up_idx"].cpu(), host["up_idx"])
+    host["neighbor_idx"].copy_(torch.randint(0, N, (B, N, K), generator=g))     # widening deferred to the consumer's stream
+    out = st.upload(host, side, defer_unpack=True)
+    main = torch.cuda.current_stream()
+    main.wait_stream(side)
+    st.unpack(main)
+    main.synchronize()
+    assert torch.equal(out["neighbor_idx"].cpu(), host["neighbor_idx"]) and torch.equal(out["pairwise"].cpu(), host["pairwise"])
     ref = sum(v.numel() * v.element_size() for v in host.values())
     assert st.h2d_bytes(host) == (ref - 6 * (B * N + B * N * K) - 4 * B * 777 if pack else ref)
     if pack:
