@@ -292,6 +292,27 @@ def _timed(torch, dist, world, dev, step, steps, barrier):
     return ms
 
 
+
+def warm_up(torch, dist, world, dev, step, min_steps, min_seconds=0.5, chunk=8):
+    """Untimed warm-up: at least `min_steps` steps and `min_seconds` of load (so that nvidia-smi samples land under load).  The
+    number of steps must be the SAME on every rank — a step contains the gradient all-reduce, and ranks that stop on their own
+    clocks would issue different numbers of collectives (a hang waiting for the NCCL watchdog).  Rank 0's clock decides, chunk by
+    chunk, and the decision is broadcast."""
+    t_w = time.perf_counter()
+    i = 0
+    while True:
+        for _ in range(chunk):
+            step(i)
+            i += 1
+        torch.cuda.synchronize()
+        more = i < min_steps or time.perf_counter() - t_w < min_seconds
+        if world > 1:
+            flag = torch.tensor([1 if more else 0], device=dev, dtype=torch.int32)
+            dist.broadcast(flag, 0)
+            more = bool(int(flag.item()))
+        if not more:
+            return i
+
 def _ncu_traffic(name):
     """DRAM bytes (read + write) of one step from the committed ncu capture (profiles/ncu_r02_metrics.json), or None."""
     try:
@@ -389,13 +410,7 @@ def run_gpu(args, rank, local_rank, world):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    t_w = time.perf_counter()
-    i = 0
-    while i < max(args.warmup, 3) or time.perf_counter() - t_w < 0.5:
-        step(i)
-        i += 1
-        if i % 16 == 0:
-            torch.cuda.synchronize()
+    warm_up(torch, dist, world, dev, step, max(args.warmup, 3))
     barrier()
     ops.COUNTERS["launches"] = 0
     ms = _timed(torch, dist, world, dev, step, args.steps, barrier)
@@ -615,11 +630,7 @@ def run_gpu_network(args, rank, local_rank, world, dev, numa):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    t_w = time.perf_counter()
-    i = 0
-    while i < max(args.warmup, 3) or time.perf_counter() - t_w < 0.5:
-        step(i)
-        i += 1
+    warm_up(torch, dist, world, dev, step, max(args.warmup, 3), chunk=4)
     barrier()
     ms = _timed(torch, dist, world, dev, step, args.steps, barrier)
     clocks = sampler.stop() if rank == 0 else None

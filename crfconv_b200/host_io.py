@@ -52,7 +52,8 @@ class HostStager:
         """Packs the index tensors of `host` into this stager's pinned buffers (host work only; may run on a helper thread one step
         ahead of `upload(..., prepared=True)`).  Waits until the previous upload has finished reading those buffers."""
         if self._copied is not None:
-            self._copied.synchronize()
+            with self.torch.cuda.device(self.device):       # a helper thread starts on device 0: keep it off other ranks' GPUs
+                self._copied.synchronize()
         L = _lib.lib()
         for k in self.bits:
             v = host[k].contiguous()

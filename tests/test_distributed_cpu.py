@@ -102,3 +102,51 @@ def test_flat_gradient_allreduce_matches_single_process():
         assert torch.allclose(after, ref, rtol=1e-5, atol=1e-5)
     assert torch.allclose(res[0][2] + res[1][2], ref, rtol=1e-5, atol=1e-5)
     assert not torch.allclose(res[0][2], ref, rtol=1e-3, atol=1e-3)        # a shard alone is NOT the full gradient
+
+
+def _warmup_worker(rank, world, port, q):
+    """bench.warm_up: rank 1's steps are slower than rank 0's, so their own clocks would stop the warm-up after different step counts;
+    every step holds a collective, so the counts MUST agree (rank 0 decides, the decision is broadcast)."""
+    import sys
+    import time
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        class _NoCuda:                      # warm_up only calls torch.cuda.synchronize(); the rest is the real torch
+            def __getattr__(self, name):
+                return getattr(torch, name)
+
+            class cuda:
+                @staticmethod
+                def synchronize():
+                    pass
+        calls = []
+
+        def step(i):
+            time.sleep(0.002 if rank == 0 else 0.0005)        # unsynchronised local work of different length ...
+            t = torch.ones(1)
+            dist.all_reduce(t)                                 # ... and the step's collective
+            calls.append(i)
+        n = bench.warm_up(_NoCuda(), dist, world, torch.device("cpu"), step, min_steps=3, min_seconds=0.15, chunk=4)
+        t = torch.tensor([float(n)])
+        dist.all_reduce(t)                                     # a mismatch would already have dead-locked above; this checks the count
+        q.put((rank, n, len(calls), float(t.item())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bench_warm_up_runs_the_same_number_of_steps_on_every_rank():
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_warmup_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=150) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    assert all(p.exitcode == 0 for p in procs)
+    (_, n0, c0, s0), (_, n1, c1, s1) = res
+    assert n0 == n1 == c0 == c1 and n0 >= 4 and n0 % 4 == 0 and s0 == s1 == 2.0 * n0
