@@ -430,12 +430,15 @@ def run_gpu(args, rank, local_rank, world):
     # The int64 indices of the reference format are narrowed on the host (16 bits: every index < 65,536), copied packed and widened
     # on the device by the package's HostStager (crfconv_b200/host_io.py) — packing runs inside the timed region, every step.
     from crfconv_b200.host_io import HostStager
-    limits = {"neighbor_idx": N_POINTS, "up_idx": N_POINTS // RATIO} if args.pack_index else None
-    stagers = [HostStager(host[0], dev, index_limits=limits, threads=args.pack_threads or max(1, min(16, len(os.sched_getaffinity(0)) // (1 if numa.get("cpus") else max(world, 1)))),
-                          pack=bool(args.pack_index)) for _ in range(2)]
+    limits = {"neighbor_idx": N_POINTS, "up_idx": N_POINTS // RATIO}
+    pack_threads = args.pack_threads or max(1, min(16, len(os.sched_getaffinity(0)) // (1 if numa.get("cpus") else max(world, 1))))
+    # both forms fill the SAME device tensors (the captured graphs read those): packed indices, or the int64 tensors as they are
+    stagers_by_mode = {True: [HostStager(host[0], dev, index_limits=limits, threads=pack_threads, pack=True) for _ in range(2)]}
+    stagers_by_mode[False] = [HostStager(host[0], dev, pack=False, dev_tensors=stagers_by_mode[True][j].dev) for j in range(2)]
+    use_pack = args.pack_index != "off"
+    stagers = stagers_by_mode[use_pack]
     stage = [st_.dev for st_ in stagers]
     h2d_ref_format = h2d
-    h2d = stagers[0].h2d_bytes(host[0])
     for st_ in stage:
         st_["unary"].requires_grad_(True)
         st_["pairwise"].requires_grad_(True)
@@ -503,18 +506,37 @@ def run_gpu(args, rank, local_rank, world):
                 prepare(i + 2)                                  # waits (on the helper thread) until step i's copies have left the pinned buffers
             cur.synchronize()                                   # the caller reads the loss on the host every step
 
-    e2e_run(3)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    e2e_run(args.steps)
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_e2e], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
+
+    def e2e_timed(n):
+        barrier()
+        e0.record()
+        e2e_run(n)
+        e1.record()
+        barrier()
+        ms_ = e0.elapsed_time(e1)
+        if world > 1:
+            t_ = torch.tensor([ms_], device=dev)
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            ms_ = float(t_.item())
+        return ms_
+
+    # --pack-index auto: whether narrowing the indices pays depends on the host (its packing threads compete with the other ranks'
+    # packing and with the DMA reads for host memory bandwidth): both forms are timed for a few steps after their own warm-up and
+    # the faster one — the same on every rank, the times are all-reduced — runs the timed region.
+    tune = None
+    if args.pack_index == "auto":
+        trial = {}
+        for mode in (True, False):
+            stagers = stagers_by_mode[mode]
+            e2e_run(3)
+            trial[mode] = e2e_timed(8) / 8
+        use_pack = trial[True] <= trial[False]
+        tune = {"packed_ms_per_step": round(trial[True], 4), "plain_ms_per_step": round(trial[False], 4), "steps_each": 8}
+    stagers = stagers_by_mode[use_pack]
+    h2d = stagers[0].h2d_bytes(host[0])
+    e2e_run(3)
+    ms_e2e = e2e_timed(args.steps)
     e2e_value = world * B * N_POINTS / (ms_e2e / args.steps * 1e-3)
     probe = h2d_probe(torch, dev, host[0], barrier)              # every rank copies at once, no compute: the host-side ceiling
     if world > 1:
@@ -575,8 +597,10 @@ def run_gpu(args, rank, local_rank, world):
                     "ms_per_step": ms_e2e / args.steps, "h2d_gbs_per_gpu": round(h2d / (ms_e2e / args.steps * 1e-3) / 1e9, 2),
                     "h2d_probe_gbs_per_gpu": round(probe, 2), "numa": numa,
                     "h2d_bytes_reference_format": h2d_ref_format,
-                    "index_packing": ("int64 indices narrowed to 16 bits on the host (helper thread + %d packing threads, range-checked, every step, "
-                                      "inside the timed region), widened on the device" % stagers[0].threads) if args.pack_index else "off"},
+                    "index_packing": {"mode": args.pack_index, "used": bool(use_pack), "auto_tune": tune,
+                                      "how": ("int64 indices narrowed to 16 bits on the host (helper thread + %d packing threads, range-checked, "
+                                              "every step, inside the timed region), widened on the device" % pack_threads) if use_pack
+                                             else "int64 index tensors copied as they are"}},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,
             "knn": {"metric": "kNN queries/s", "value": knn_qps, "unit": "queries/s", "config": f"B={B}, N=Q=40960, K=16, device-resident"},
             "cpu_baseline": cb}
@@ -706,8 +730,8 @@ def main():
     ap.add_argument("--config", default="S1", choices=["S1", "C3", "C4", "C5"])
     ap.add_argument("--clouds", type=int, default=0, help="clouds per GPU per step (default: 6 for S1/C3, 8 for C4, 2 for C5)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-pack-index", dest="pack_index", action="store_false",
-                    help="e2e arm: copy the int64 index tensors as they are instead of narrowing them on the host")
+    ap.add_argument("--pack-index", default="auto", choices=["auto", "on", "off"],
+                    help="e2e arm: narrow the int64 index tensors to 16 bits on the host before the copy (auto: time both forms, keep the faster)")
     ap.add_argument("--pack-threads", type=int, default=0, help="host threads of the index packing (default: min(16, cores / ranks); measured 1 / 2 / 4 / 8 / 16 threads: 2.84 / 2.18 / 2.04 / 2.05 / 1.92 ms per step)")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every kernel from Python instead of replaying CUDA graphs")
     args = ap.parse_args()

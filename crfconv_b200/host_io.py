@@ -22,9 +22,10 @@ def index_bits(limit: int) -> int:
 
 
 class HostStager:
-    def __init__(self, example, device, index_limits=None, threads=None, pack=True):
+    def __init__(self, example, device, index_limits=None, threads=None, pack=True, dev_tensors=None):
         """example: dict name → host tensor (float32 features / int64 indices) giving shapes and dtypes; index_limits: dict name →
-        exclusive upper bound of that index tensor's values (default: 2**31, i.e. 32-bit packing); pack=False copies int64 as is."""
+        exclusive upper bound of that index tensor's values (default: 2**31, i.e. 32-bit packing); pack=False copies int64 as is;
+        dev_tensors: adopt these device tensors as the destination instead of allocating new ones."""
         import torch
         self.torch = torch
         self.device = device
@@ -33,7 +34,7 @@ class HostStager:
         self._copied = None                 # event after the last upload's copies: the pinned packing buffers are reused
         index_limits = index_limits or {}
         for k, v in example.items():
-            self.dev[k] = torch.empty(v.shape, dtype=v.dtype, device=device)
+            self.dev[k] = dev_tensors[k] if dev_tensors is not None else torch.empty(v.shape, dtype=v.dtype, device=device)
             if pack and v.dtype == torch.int64:
                 bits = index_bits(int(index_limits.get(k, 1 << 31)))
                 dt = torch.int16 if bits == 16 else torch.int32
