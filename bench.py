@@ -431,7 +431,9 @@ def run_gpu(args, rank, local_rank, world):
     # on the device by the package's HostStager (crfconv_b200/host_io.py) — packing runs inside the timed region, every step.
     from crfconv_b200.host_io import HostStager
     limits = {"neighbor_idx": N_POINTS, "up_idx": N_POINTS // RATIO}
-    pack_threads = args.pack_threads or max(1, min(16, len(os.sched_getaffinity(0)) // (1 if numa.get("cpus") else max(world, 1))))
+    # packing threads: this rank's share of the cores minus the main thread (which spins in cudaStreamSynchronize) and NCCL's
+    cores_per_rank = len(os.sched_getaffinity(0)) // (1 if numa.get("cpus") else max(world, 1))
+    pack_threads = args.pack_threads or max(1, min(16, cores_per_rank - 2))
     # both forms fill the SAME device tensors (the captured graphs read those): packed indices, or the int64 tensors as they are
     stagers_by_mode = {True: [HostStager(host[0], dev, index_limits=limits, threads=pack_threads, pack=True) for _ in range(2)]}
     stagers_by_mode[False] = [HostStager(host[0], dev, pack=False, dev_tensors=stagers_by_mode[True][j].dev) for j in range(2)]

@@ -80,7 +80,7 @@ class HostStager:
             for k in self.bits:
                 self.packed_dev[k].copy_(self.packed_host[k], non_blocking=True)
             if self._copied is None:
-                self._copied = torch.cuda.Event()
+                self._copied = torch.cuda.Event(blocking=True)    # the waiter (often a helper thread) sleeps instead of spinning on a core
             self._copied.record(stream)
             if not defer_unpack:
                 self.unpack(stream)

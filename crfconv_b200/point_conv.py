@@ -8,7 +8,7 @@ and ``state_dict`` keys (``mlp1.{0,1,3,4}``, ``mlp2.{0,1}``, ``mlp3.{0,1}``, ``m
 removes self loops and adds one per node (:46-48) and the residual is ``x`` itself; with a ``(pos_src, pos_dst)`` pair the graph is
 bipartite, no self loops are touched, and the residual is the max over each target's sources (:50-53).  ``mlp4`` (:37-41) projects
 the residual when the channel counts differ; its ``nn.Linear`` has a bias, which the BatchNorm that follows cancels in the output
-(its gradient is identically zero and is returned as ``None``) and which only shifts the running mean (``_lin_bias_bn``).
+(its gradient is identically zero and is returned as zeros) and which only shifts the running mean (``_lin_bias_bn``).
 
 Runs on the dense PointConv kernels (csrc/pointconv.cu + the Linear/BN chains), which take a [N, K] neighbour table and compute
 ``mlp1``'s BatchNorm statistics over all N·K edges — so the graph must be REGULAR after the self-loop step (``knn_graph``);
@@ -56,7 +56,9 @@ def _lin_bias_bn(x, lin, bn, training):
             with torch.no_grad():
                 m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
                 bn.running_mean.add_(m * b)
-        return y
+        if torch.is_grad_enabled() and lin.bias.requires_grad:
+            y = y + 0.0 * lin.bias.sum()      # the bias gradient is identically zero: hand autograd zeros (not None) like the reference, so
+        return y                              # that an optimizer's weight decay treats the parameter the same way
     with torch.no_grad():
         bn.running_mean.sub_(b)
     try:
