@@ -110,11 +110,19 @@ class FlatGradients:
             buf = self._shared_span()
             if buf is None:
                 chunks = list(self.flat[:self.numel].split([p.numel() for p in self.params]))
-                torch._foreach_copy_([c.view_as(p.grad) for c, p in zip(chunks, self.params)], [p.grad for p in self.params])
+                have = [(c, p) for c, p in zip(chunks, self.params) if p.grad is not None]
+                if len(have) < len(self.params):
+                    self.flat[:self.numel].zero_()                  # a parameter this rank's step did not reach contributes zeros
+                if have:
+                    torch._foreach_copy_([c.view_as(p.grad) for c, p in have], [p.grad for _, p in have])
                 dist.all_reduce(self.flat, op=op)
                 if average and not avg_op:
                     self.flat.div_(world)
-                torch._foreach_copy_([p.grad for p in self.params], [c.view_as(p.grad) for c, p in zip(chunks, self.params)])
+                if have:
+                    torch._foreach_copy_([p.grad for _, p in have], [c.view_as(p.grad) for c, p in have])
+                for c, p in zip(chunks, self.params):
+                    if p.grad is None:
+                        p.grad = c.view_as(p).clone()               # ... and receives what the other ranks computed for it
                 return self.flat
         dist.all_reduce(buf, op=op)
         if average and not avg_op:

@@ -46,6 +46,8 @@ class GraphedStep:
             for k in dst:
                 GraphedStep.copy_inputs(dst[k], src[k])
         elif isinstance(dst, (list, tuple)):
+            if len(dst) != len(src):
+                raise ValueError(f"captured input has {len(dst)} entries, new batch has {len(src)}")
             for a, b in zip(dst, src):
                 GraphedStep.copy_inputs(a, b)
         elif hasattr(dst, "__dict__"):

@@ -48,6 +48,21 @@ def _worker(rank, world, port, q):
         fa.all_reduce(average=False)
         adopted = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
         assert torch.allclose(adopted, fg.flat, rtol=1e-5, atol=1e-5)
+        # a parameter one rank's step never reached (grad None there) contributes zeros and receives the other ranks' sum
+        fa.zero()
+        if rank == 0:
+            ((model(xs) - ys) ** 2).sum().backward()
+            mine = [p.grad.clone() for p in model.parameters()]
+        else:
+            (model[0](xs) ** 2).sum().backward()                    # the second Linear is not reached on rank 1
+            assert model[2].weight.grad is None
+            mine = [p.grad.clone() if p.grad is not None else torch.zeros_like(p) for p in model.parameters()]
+        fa.all_reduce(average=False)
+        summed = [m.clone() for m in mine]
+        for m in summed:
+            dist.all_reduce(m)
+        for p, m in zip(model.parameters(), summed):
+            assert p.grad is not None and torch.allclose(p.grad, m, rtol=1e-6, atol=1e-6)
         q.put((rank, xs.shape[0], before, fg.flat.clone()))
     finally:
         dist.destroy_process_group()
