@@ -17,6 +17,10 @@ e2e          : same metric through the public API with HOST (pinned) inputs: H2D
                up_idx / neighbor_idx; C3-C5: points, features, labels — the pyramid is then built on the GPU inside the timed
                region) and a D2H read of the loss every step.  Ranks bind to their GPU's NUMA node before allocating pinned memory;
                `e2e.h2d_gbs_per_gpu` and `e2e.h2d_probe_gbs_per_gpu` (all ranks copying at once, no compute) locate the host-side ceiling.
+               S1: the inputs go through `crfconv_b200.host_io.HostStager`; with --pack-index on the int64 index tensors are narrowed
+               to 16 bits on the host (every step, inside the timed region), copied packed and widened on the device; `auto`
+               (default) times both forms for 8 steps each and runs the timed region with the faster one (`e2e.index_packing`).
+               `h2d_bytes_per_step` counts the bytes actually copied, `h2d_bytes_reference_format` the int64 form.
 roofline     : the WHOLE step against SURVEY.md §8(d)'s algorithmic bytes (S1: 79,298,560 B per cloud fwd+bwd; C3-C5: the shape
                walker `network_algo_bytes`) — `frac` is the north_star fraction.  `roofline.dominant_kernel` names the single
                kernel with the largest share of the step; `kernels` lists every kernel call with its own bytes and GB/s.
@@ -734,7 +738,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pack-index", default="auto", choices=["auto", "on", "off"],
                     help="e2e arm: narrow the int64 index tensors to 16 bits on the host before the copy (auto: time both forms, keep the faster)")
-    ap.add_argument("--pack-threads", type=int, default=0, help="host threads of the index packing (default: min(16, cores / ranks); measured 1 / 2 / 4 / 8 / 16 threads: 2.84 / 2.18 / 2.04 / 2.05 / 1.92 ms per step)")
+    ap.add_argument("--pack-threads", type=int, default=0, help="host threads of the index packing (default: min(16, cores per rank - 2); measured 1 / 2 / 4 / 8 / 16 threads: 2.84 / 2.18 / 2.04 / 2.05 / 1.92 ms per step)")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every kernel from Python instead of replaying CUDA graphs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -747,7 +751,8 @@ def main():
         # launched without torchrun: re-launch under torch.distributed.run, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", str(29500 + os.getpid() % 2000), os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps),
-               "--warmup", str(args.warmup), "--config", args.config, "--clouds", str(args.clouds)] + ([] if args.graph else ["--no-graph"])
+               "--warmup", str(args.warmup), "--config", args.config, "--clouds", str(args.clouds), "--pack-index", args.pack_index,
+               "--pack-threads", str(args.pack_threads)] + ([] if args.graph else ["--no-graph"])
         sys.exit(subprocess.call(cmd))
     run_gpu(args, rank, local_rank, world)
 
