@@ -31,3 +31,14 @@ def test_product_arm_refuses_to_run_without_a_gpu():
                        timeout=600, cwd=ROOT)
     assert r.returncode != 0
     assert not [l for l in r.stdout.strip().splitlines() if l.startswith("{") and '"value"' in l]
+
+
+def test_algorithmic_bytes_match_the_survey():
+    """79,298,560 algorithmic bytes per 40,960-point cloud for one CRF layer fwd+bwd at S1 — the roofline numerator."""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.ALGO_BYTES_PER_CLOUD == 79_298_560
+    assert bench.crf_layer_algo_bytes(40960, 10240, 128, 64, 64, 16) == bench.ALGO_BYTES_PER_CLOUD
+    a3 = bench.network_algo_bytes(40960, 13)
+    assert 230e6 < a3 < 240e6                                  # DESIGN.md §6: 236 MB per cloud for the whole network at C3
+    assert bench.network_algo_bytes(45056, 19) > a3 and bench.network_algo_bytes(65536, 8) > a3
